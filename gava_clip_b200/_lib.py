@@ -1,0 +1,88 @@
+"""ctypes binding of libgava_sm100.so (C ABI in include/gava_sm100.h).
+
+There is no fallback: if the shared object is missing or a symbol is absent this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "lib" / "libgava_sm100.so"
+
+EPI_BIAS_BF16 = 0
+EPI_BIAS_GELU_BF16 = 1
+EPI_BIAS_RESID_F32 = 2
+EPI_BIAS_F32 = 3
+EPI_PATCH_F32 = 4
+
+
+class GemmEpilogue(C.Structure):
+    """mirror of `struct gava_gemm_epilogue`"""
+    _fields_ = [
+        ("mode", C.c_int32),
+        ("bias", C.c_void_p),
+        ("resid", C.c_void_p),
+        ("ldr", C.c_int64),
+        ("out", C.c_void_p),
+        ("ldo", C.c_int64),
+        ("group", C.c_int32),
+        ("group_stride", C.c_int32),
+        ("row_offset", C.c_int32),
+        ("T", C.c_int32),
+        ("pos", C.c_void_p),
+        ("time_embed", C.c_void_p),
+    ]
+
+
+_p, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); must match include/gava_sm100.h
+SIGNATURES = {
+    "gava_version": [],
+    "gava_last_error_string": [],
+    "gava_init": [],
+    "gava_gemm_bf16_fwd": [_p, _i64, _p, _i64, _i64, _i64, _i64, C.POINTER(GemmEpilogue), _p],
+    "gava_layernorm_fwd": [_p, _i64, _p, _p, _p, _i64, _i32, _i64, _i32, _f32, _p],
+    "gava_patch_gather_fwd": [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p],
+    "gava_cls_rows_fwd": [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _p],
+    "gava_temporal_attention_fwd": [_p, _p, _i32, _i32, _i32, _p],
+    "gava_prompt_rows_fwd": [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p],
+    "gava_attention_fwd": [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p],
+    "gava_head_fwd": [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _p],
+}
+_RESTYPES = {"gava_last_error_string": C.c_char_p}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the library (building it first if only sources are present and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists() and os.environ.get("GAVA_NO_AUTOBUILD") != "1":
+        from . import build as _build
+        _build.build()
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m gava_clip_b200.build` (no fallback path exists)")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing -> loud
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    if lib.gava_version() != 1:
+        raise RuntimeError(f"libgava_sm100 ABI version {lib.gava_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    s = load().gava_last_error_string()
+    return s.decode() if s else ""
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (status {rc}): {last_error()}")

@@ -1,0 +1,90 @@
+// extern "C" surface of libgava_sm100.so (declared in include/gava_sm100.h).  Thin shim: argument
+// hand-off to the kernels' host launchers, integer status + thread-local error string, no exceptions.
+#include "common.cuh"
+#include "kernels.h"
+
+#include <stdarg.h>
+
+namespace gava {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s launch failed: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return GAVA_OK;
+}
+
+}  // namespace gava
+
+using namespace gava;
+
+extern "C" {
+
+int gava_version(void) { return GAVA_ABI_VERSION; }
+
+const char* gava_last_error_string(void) { return g_err; }
+
+int gava_init(void) {
+  int dev = 0, major = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) { set_error("gava_init: %s", cudaGetErrorString(e)); return (int)e; }
+  if (major != 10) { set_error("gava_init: device compute capability %d.x is not sm_100", major); return GAVA_ERR_DRIVER; }
+  return GAVA_OK;
+}
+
+int gava_gemm_bf16_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                       const gava_gemm_epilogue* epi, void* stream) {
+  return gemm_bf16(A, lda, W, ldw, M, N, K, epi, (cudaStream_t)stream);
+}
+
+int gava_layernorm_fwd(const float* x, int64_t in_row_stride, const float* weight, const float* bias, void* out,
+                       int64_t out_row_stride, int32_t out_bf16, int64_t rows, int32_t D, float eps, void* stream) {
+  return layernorm(x, in_row_stride, weight, bias, out, out_row_stride, out_bf16, rows, D, eps, (cudaStream_t)stream);
+}
+
+int gava_patch_gather_fwd(const float* video, void* A, int32_t B, int32_t T, int32_t H, int32_t W, int32_t P,
+                          int32_t Kpad, void* stream) {
+  return patch_gather(video, A, B, T, H, W, P, Kpad, (cudaStream_t)stream);
+}
+
+int gava_cls_rows_fwd(float* x, int32_t tokens_per_frame, const float* cls_token, const float* pos_embed,
+                      const float* time_embed, int32_t BT, int32_t T, int32_t D, void* stream) {
+  return cls_rows(x, tokens_per_frame, cls_token, pos_embed, time_embed, BT, T, D, (cudaStream_t)stream);
+}
+
+int gava_temporal_attention_fwd(const void* qkv, void* out, int32_t B, int32_t T, int32_t H, void* stream) {
+  return temporal_attention(qkv, out, B, T, H, (cudaStream_t)stream);
+}
+
+int gava_prompt_rows_fwd(const float* global_prompts, const float* local_prompts, const float* cls_proj_out,
+                         const float* summary, const float* ln_weight, const float* ln_bias, void* out, int32_t G,
+                         int32_t B, int32_t T, int32_t D, float eps, void* stream) {
+  return prompt_rows(global_prompts, local_prompts, cls_proj_out, summary, ln_weight, ln_bias, out, G, B, T, D, eps,
+                     (cudaStream_t)stream);
+}
+
+int gava_attention_fwd(const void* qkv, const void* kv_aux, void* out, int32_t B, int32_t T, int32_t N0, int32_t G,
+                       int32_t H, int32_t n_q, void* stream) {
+  return attention(qkv, kv_aux, out, B, T, N0, G, H, n_q, (cudaStream_t)stream);
+}
+
+int gava_head_fwd(const float* frame_feat, const float* summary_tok, const float* text_hat,
+                  const int32_t* class_offsets, float* video_features, float* summary_out, float* logits, int32_t B,
+                  int32_t T, int32_t E, int32_t D, int32_t n_cls, float scale, float logit_bias, void* stream) {
+  return head(frame_feat, summary_tok, text_hat, class_offsets, video_features, summary_out, logits, B, T, E, D, n_cls,
+              scale, logit_bias, (cudaStream_t)stream);
+}
+
+}  // extern "C"

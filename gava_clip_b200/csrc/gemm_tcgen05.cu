@@ -1,0 +1,337 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a:  C[M,N] = A[M,K] * W[N,K]^T (+ fused epilogue)
+//
+//   A, W : bf16, K-major (row-major [rows, K]); moved by TMA (128-byte swizzle) into a 4..6 stage smem ring
+//   D    : fp32 accumulators in TMEM, 2 accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
+//   roles: warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane), warp 2 = TMEM allocator,
+//          warps 4..7 = epilogue (one TMEM lane == one output row per thread)
+//
+// Replaces the nn.Linear / Conv2d(k=s=patch) library calls of the reference hot path:
+//   q/k/v/out_proj  training/VitaCLIP_vision_encoder_utils.py:66,79
+//   mlp fc1/fc2     training/VitaCLIP_vision_encoder_utils.py:110-115
+//   cls_proj        training/VitaCLIP_vision_encoder_utils.py:164-165
+//   patch_embed     training/VitaCLIP_vision_encoder_utils.py:215-219
+//   final proj      training/VitaCLIP_vision_encoder.py:127
+#include "common.cuh"
+#include "kernels.h"
+
+#include <mutex>
+
+namespace gava {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle atom
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kBytesA = BM * BK * 2;
+  static constexpr int kBytesB = BN * BK * 2;
+  static constexpr int kBytesStage = kBytesA + kBytesB;
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
+  static constexpr int kSmemBytes = kStages * kBytesStage + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct GemmArgs {
+  int M, N, K;
+  const float* bias;    // [N] or null
+  const float* resid;   // fp32 [M, ldr] (EPI_BIAS_RESID_F32)
+  long long ldr;
+  void* out;            // bf16 or fp32 [M(out rows), ldo]
+  long long ldo;
+  int group, group_stride, row_offset;  // EPI_PATCH_F32: out_row = (r/group)*group_stride + r%group + row_offset
+  const float* pos;     // [group+1, N]
+  const float* time_embed;  // [T, N]
+  int T;
+};
+
+template <int MODE>
+__device__ __forceinline__ void epilogue_store(const GemmArgs& p, int row, int col0, uint32_t (&v)[32]) {
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+  if (p.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 b = __ldg(b4 + j);
+      acc[4 * j + 0] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
+    }
+  }
+  if constexpr (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16) {
+    if constexpr (MODE == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = quick_gelu(acc[j]);
+    }
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0;
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 w;
+      w.x = pack_bf16x2(acc[8 * j + 0], acc[8 * j + 1]);
+      w.y = pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]);
+      w.z = pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]);
+      w.w = pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]);
+      o4[j] = w;
+    }
+  } else if constexpr (MODE == EPI_BIAS_RESID_F32) {
+    const float4* r4 = reinterpret_cast<const float4*>(p.resid + (long long)row * p.ldr + col0);
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0);
+    float4 r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = r4[j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 w = make_float4(acc[4 * j] + r[j].x, acc[4 * j + 1] + r[j].y, acc[4 * j + 2] + r[j].z,
+                             acc[4 * j + 3] + r[j].w);
+      o4[j] = w;
+    }
+  } else if constexpr (MODE == EPI_BIAS_F32) {
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+  } else {  // EPI_PATCH_F32: + pos_embed[1+n] + time_embed[t], scatter to the frame's token slot
+    const int grp = row / p.group, n = row - grp * p.group;
+    const long long orow = (long long)grp * p.group_stride + n + p.row_offset;
+    const float4* pe = reinterpret_cast<const float4*>(p.pos + (long long)(n + 1) * p.N + col0);
+    const float4* te = reinterpret_cast<const float4*>(p.time_embed + (long long)(grp % p.T) * p.N + col0);
+    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 a = __ldg(pe + j), b = __ldg(te + j);
+      o4[j] = make_float4(acc[4 * j] + a.x + b.x, acc[4 * j + 1] + a.y + b.y, acc[4 * j + 2] + a.z + b.z,
+                          acc[4 * j + 3] + a.w + b.w);
+    }
+  }
+}
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmArgs p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kBytesA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kBytesStage);
+  uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + kStages;           // [kStages]  MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * kStages;       // [2]        MMA -> epilogue
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]        epilogue -> MMA
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_n = p.N / BN;
+  const int num_m = (p.M + BM - 1) / BM;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = p.K / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_base_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kBytesStage);
+          tma_load_2d(smem_a + stage * Cfg::kBytesA, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(smem_b + stage * Cfg::kBytesB, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kBytesA));
+          const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBytesB));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements (32 bytes) along K inside the swizzle atom: +2 in 16-byte units
+            umma_bf16_ss(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      const int row = m_blk * BM + ew * 32 + lane;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
+        tmem_ld_wait();
+        if (row < p.M) epilogue_store<MODE>(p, row, n_blk * BN + c * 32, v);
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------- host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major [rows, cols] with row pitch ld (elements); box = [box_rows, 64 cols], 128B swizzle
+static int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return GAVA_ERR_DRIVER; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || ((ld * 2) & 15)) {
+    set_error("TMA operand must be 16-byte aligned (ptr %p, ld %lld)", ptr, ld);
+    return GAVA_ERR_ARG;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return GAVA_ERR_DRIVER; }
+  return GAVA_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int MODE>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  auto kern = gemm_tcgen05_kernel<BN, MODE>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(gemm): %s", cudaGetErrorString(e)); return (int)e; }
+    attr_set = true;
+  }
+  const int tiles = ((args.M + BM - 1) / BM) * (args.N / BN);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, args);
+  return check_launch("gemm_tcgen05");
+}
+
+template <int BN>
+static int dispatch_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t s) {
+  switch (mode) {
+    case EPI_BIAS_BF16: return launch_gemm<BN, EPI_BIAS_BF16>(ta, tb, a, s);
+    case EPI_BIAS_GELU_BF16: return launch_gemm<BN, EPI_BIAS_GELU_BF16>(ta, tb, a, s);
+    case EPI_BIAS_RESID_F32: return launch_gemm<BN, EPI_BIAS_RESID_F32>(ta, tb, a, s);
+    case EPI_BIAS_F32: return launch_gemm<BN, EPI_BIAS_F32>(ta, tb, a, s);
+    case EPI_PATCH_F32: return launch_gemm<BN, EPI_PATCH_F32>(ta, tb, a, s);
+  }
+  set_error("gemm: unknown epilogue mode %d", mode);
+  return GAVA_ERR_ARG;
+}
+
+int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long long M, long long N, long long K,
+              const gava_gemm_epilogue* epi, cudaStream_t stream) {
+  if (!A || !W || !epi || !epi->out) { set_error("gemm: null pointer"); return GAVA_ERR_ARG; }
+  if (M <= 0 || N <= 0 || K <= 0 || (K % BK) != 0 || (N % 128) != 0) {
+    set_error("gemm: unsupported shape M=%lld N=%lld K=%lld (need K%%64==0, N%%128==0)", M, N, K);
+    return GAVA_ERR_SHAPE;
+  }
+  if (epi->mode == EPI_BIAS_RESID_F32 && !epi->resid) { set_error("gemm: residual epilogue without resid"); return GAVA_ERR_ARG; }
+  if (epi->mode == EPI_PATCH_F32 && (!epi->pos || !epi->time_embed || epi->group <= 0 || epi->T <= 0)) {
+    set_error("gemm: patch epilogue needs pos/time_embed/group/T");
+    return GAVA_ERR_ARG;
+  }
+  const int bn = (N % 256 == 0) ? 256 : 128;
+  CUtensorMap ta, tb;
+  int rc = make_tmap_bf16(&ta, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tb, W, N, K, ldw, bn);
+  if (rc) return rc;
+  GemmArgs a;
+  a.M = (int)M; a.N = (int)N; a.K = (int)K;
+  a.bias = epi->bias; a.resid = epi->resid; a.ldr = epi->ldr;
+  a.out = epi->out; a.ldo = epi->ldo;
+  a.group = epi->group; a.group_stride = epi->group_stride; a.row_offset = epi->row_offset;
+  a.pos = epi->pos; a.time_embed = epi->time_embed; a.T = epi->T;
+  return bn == 256 ? dispatch_mode<256>(epi->mode, ta, tb, a, stream) : dispatch_mode<128>(epi->mode, ta, tb, a, stream);
+}
+
+}  // namespace gava

@@ -1,0 +1,42 @@
+// Internal C++ declarations shared by the kernel translation units and the C-ABI shim (api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/gava_sm100.h"
+
+namespace gava {
+
+enum : int {
+  EPI_BIAS_BF16 = GAVA_EPI_BIAS_BF16,
+  EPI_BIAS_GELU_BF16 = GAVA_EPI_BIAS_GELU_BF16,
+  EPI_BIAS_RESID_F32 = GAVA_EPI_BIAS_RESID_F32,
+  EPI_BIAS_F32 = GAVA_EPI_BIAS_F32,
+  EPI_PATCH_F32 = GAVA_EPI_PATCH_F32,
+};
+
+int num_sms();
+
+int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long long M, long long N, long long K,
+              const gava_gemm_epilogue* epi, cudaStream_t stream);
+
+int layernorm(const float* x, long long in_row_stride, const float* w, const float* b, void* out,
+              long long out_row_stride, int out_bf16, long long rows, int D, float eps, cudaStream_t stream);
+
+int patch_gather(const float* video, void* A, int B, int T, int H, int W, int P, int Kpad, cudaStream_t stream);
+
+int cls_rows(float* x, int tokens_per_frame, const float* cls_token, const float* pos_embed, const float* time_embed,
+             int BT, int T, int D, cudaStream_t stream);
+
+int temporal_attention(const void* qkv, void* out, int B, int T, int H, cudaStream_t stream);
+
+int prompt_rows(const float* global_prompts, const float* local_prompts, const float* cls_proj_out,
+                const float* summary, const float* ln_w, const float* ln_b, void* out, int G, int B, int T, int D,
+                float eps, cudaStream_t stream);
+
+int attention(const void* qkv, const void* kv_aux, void* out, int B, int T, int N0, int G, int H, int n_q,
+              cudaStream_t stream);
+
+int head(const float* frame_feat, const float* summary_tok, const float* text_hat, const int* class_offsets,
+         float* video_features, float* summary_out, float* logits, int B, int T, int E, int D, int n_cls, float scale,
+         float logit_bias, cudaStream_t stream);
+
+}  // namespace gava

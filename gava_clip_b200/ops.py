@@ -1,0 +1,179 @@
+"""Tensor-level wrappers over the C ABI (include/gava_sm100.h).
+
+PyTorch is used only for device memory and streams: every function takes CUDA tensors, checks
+dtype/layout, and launches the sm_100a kernel on the current stream.  Outputs are preallocated by the
+caller (or allocated here when `out=None`).  No function has a fallback implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PATCH_F32,
+                   GemmEpilogue)
+
+Tensor = torch.Tensor
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: Tensor, dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (the sm_100a path has no CPU fallback)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
+
+
+def _ptr(t: Optional[Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def gemm(a: Tensor, w: Tensor, out: Tensor, *, mode: int, bias: Optional[Tensor] = None,
+         resid: Optional[Tensor] = None, pos: Optional[Tensor] = None, time_embed: Optional[Tensor] = None,
+         group: int = 0, group_stride: int = 0, row_offset: int = 0, T: int = 0) -> Tensor:
+    """out = epilogue(a @ w.T).  a: bf16 [M,K] (row stride free), w: bf16 [N,K], fp32 bias [N]."""
+    _req(a, torch.bfloat16, "gemm a"); _req(w, torch.bfloat16, "gemm w")
+    assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K, (a.shape, w.shape)
+    want = torch.bfloat16 if mode in (EPI_BIAS_BF16, EPI_BIAS_GELU_BF16) else torch.float32
+    _req(out, want, "gemm out")
+    assert out.dim() == 2 and out.stride(1) == 1 and out.shape[1] >= N
+    if bias is not None:
+        _req(bias, torch.float32, "gemm bias"); assert bias.numel() == N and bias.is_contiguous()
+    epi = GemmEpilogue()
+    epi.mode = mode
+    epi.bias = _ptr(bias)
+    epi.out = out.data_ptr()
+    epi.ldo = out.stride(0)
+    if mode == EPI_BIAS_RESID_F32:
+        _req(resid, torch.float32, "gemm resid")
+        assert resid.dim() == 2 and resid.stride(1) == 1 and resid.shape[0] >= M
+        epi.resid = resid.data_ptr(); epi.ldr = resid.stride(0)
+        assert out.shape[0] >= M
+    elif mode == EPI_PATCH_F32:
+        _req(pos, torch.float32, "gemm pos"); _req(time_embed, torch.float32, "gemm time_embed")
+        assert pos.is_contiguous() and time_embed.is_contiguous()
+        assert pos.shape == (group + 1, N) and time_embed.shape == (T, N)
+        assert M % group == 0 and out.shape[0] >= (M // group) * group_stride
+        epi.pos = pos.data_ptr(); epi.time_embed = time_embed.data_ptr()
+        epi.group, epi.group_stride, epi.row_offset, epi.T = group, group_stride, row_offset, T
+    else:
+        assert out.shape[0] >= M
+    rc = _lib.load().gava_gemm_bf16_fwd(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K,
+                                        C.byref(epi), _stream())
+    _lib.check(rc, "gava_gemm_bf16_fwd")
+    return out
+
+
+def layernorm(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], out: Tensor, *, rows: int,
+              in_row_stride: int, out_row_stride: Optional[int] = None, eps: float = 1e-5) -> Tensor:
+    """LayerNorm (or plain cast when weight is None) of `rows` rows of width D = weight/out last dim.
+
+    Row r is read at x.data_ptr + r*in_row_stride floats: lets the caller gather e.g. the cls rows.
+    """
+    _req(x, torch.float32, "layernorm x")
+    D = out.shape[-1]
+    out_bf16 = 1 if out.dtype == torch.bfloat16 else 0
+    if not out_bf16:
+        _req(out, torch.float32, "layernorm out")
+    if weight is not None:
+        _req(weight, torch.float32, "layernorm weight"); _req(bias, torch.float32, "layernorm bias")
+        assert weight.numel() == D and bias.numel() == D
+    if out_row_stride is None:
+        out_row_stride = D
+    assert x.numel() >= (rows - 1) * in_row_stride + D and out.numel() >= (rows - 1) * out_row_stride + D
+    rc = _lib.load().gava_layernorm_fwd(x.data_ptr(), in_row_stride, _ptr(weight), _ptr(bias), out.data_ptr(),
+                                        out_row_stride, out_bf16, rows, D, eps, _stream())
+    _lib.check(rc, "gava_layernorm_fwd")
+    return out
+
+
+def patch_gather(video: Tensor, out: Tensor, patch: int) -> Tensor:
+    """video fp32 [B,3,T,H,W] contiguous -> bf16 [B*T*gh*gw, Kpad] patch rows (conv-weight column order)."""
+    _req(video, torch.float32, "patch_gather video"); _req(out, torch.bfloat16, "patch_gather out")
+    assert video.is_contiguous() and out.is_contiguous() and video.dim() == 5 and video.shape[1] == 3
+    B, _, T, H, W = video.shape
+    assert out.shape[0] == B * T * (H // patch) * (W // patch)
+    rc = _lib.load().gava_patch_gather_fwd(video.data_ptr(), out.data_ptr(), B, T, H, W, patch, out.shape[1], _stream())
+    _lib.check(rc, "gava_patch_gather_fwd")
+    return out
+
+
+def cls_rows(x: Tensor, tokens_per_frame: int, cls_token: Tensor, pos_embed: Tensor, time_embed: Tensor,
+             BT: int, T: int) -> Tensor:
+    _req(x, torch.float32, "cls_rows x")
+    for t in (cls_token, pos_embed, time_embed):
+        _req(t, torch.float32, "cls_rows param"); assert t.is_contiguous()
+    D = cls_token.numel()
+    assert x.is_contiguous() and x.numel() >= BT * tokens_per_frame * D and time_embed.shape == (T, D)
+    rc = _lib.load().gava_cls_rows_fwd(x.data_ptr(), tokens_per_frame, cls_token.data_ptr(), pos_embed.data_ptr(),
+                                       time_embed.data_ptr(), BT, T, D, _stream())
+    _lib.check(rc, "gava_cls_rows_fwd")
+    return x
+
+
+def temporal_attention(qkv: Tensor, out: Tensor, B: int, T: int, H: int) -> Tensor:
+    _req(qkv, torch.bfloat16, "temporal_attention qkv"); _req(out, torch.bfloat16, "temporal_attention out")
+    D = H * 64
+    assert qkv.is_contiguous() and out.is_contiguous() and qkv.shape == (B * T, 3 * D) and out.shape == (B * T, D)
+    rc = _lib.load().gava_temporal_attention_fwd(qkv.data_ptr(), out.data_ptr(), B, T, H, _stream())
+    _lib.check(rc, "gava_temporal_attention_fwd")
+    return out
+
+
+def prompt_rows(global_prompts: Tensor, local_prompts: Tensor, cls_proj_out: Tensor, summary: Tensor,
+                ln_w: Tensor, ln_b: Tensor, out: Tensor, B: int, T: int, eps: float = 1e-5) -> Tensor:
+    for t in (global_prompts, local_prompts, cls_proj_out, summary, ln_w, ln_b):
+        _req(t, torch.float32, "prompt_rows input"); assert t.is_contiguous()
+    _req(out, torch.bfloat16, "prompt_rows out")
+    G, D = global_prompts.shape
+    assert local_prompts.shape[-2:] == (T, D) and cls_proj_out.shape == (B * T, D) and summary.shape == (B * T, D)
+    assert out.is_contiguous() and out.shape == (G + 2 * B * T, D)
+    rc = _lib.load().gava_prompt_rows_fwd(global_prompts.data_ptr(), local_prompts.data_ptr(), cls_proj_out.data_ptr(),
+                                          summary.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), out.data_ptr(),
+                                          G, B, T, D, eps, _stream())
+    _lib.check(rc, "gava_prompt_rows_fwd")
+    return out
+
+
+def attention(qkv: Tensor, kv_aux: Tensor, out: Tensor, *, B: int, T: int, N0: int, G: int, H: int,
+              n_q: Optional[int] = None) -> Tensor:
+    _req(qkv, torch.bfloat16, "attention qkv"); _req(kv_aux, torch.bfloat16, "attention kv_aux")
+    _req(out, torch.bfloat16, "attention out")
+    D = H * 64
+    assert qkv.is_contiguous() and kv_aux.is_contiguous() and out.is_contiguous()
+    assert qkv.shape == (B * T * N0, 3 * D) and kv_aux.shape == (G + 2 * B * T, 2 * D) and out.shape == (B * T * N0, D)
+    rc = _lib.load().gava_attention_fwd(qkv.data_ptr(), kv_aux.data_ptr(), out.data_ptr(), B, T, N0, G, H,
+                                        N0 if n_q is None else n_q, _stream())
+    _lib.check(rc, "gava_attention_fwd")
+    return out
+
+
+def head(frame_feat: Tensor, summary_tok: Optional[Tensor], text_hat: Tensor, class_offsets: Tensor,
+         video_features: Tensor, summary_out: Optional[Tensor], logits: Tensor, *, B: int, T: int, scale: float,
+         logit_bias: float = 0.0) -> Tensor:
+    _req(frame_feat, torch.float32, "head frame_feat"); _req(text_hat, torch.float32, "head text_hat")
+    _req(class_offsets, torch.int32, "head class_offsets")
+    _req(video_features, torch.float32, "head video_features"); _req(logits, torch.float32, "head logits")
+    E = frame_feat.shape[1]
+    n_cls = class_offsets.numel() - 1
+    D = 0
+    if summary_tok is not None:
+        _req(summary_tok, torch.float32, "head summary_tok"); _req(summary_out, torch.float32, "head summary_out")
+        D = summary_tok.shape[1]
+        assert summary_tok.is_contiguous() and summary_out.is_contiguous() and summary_out.shape == (B, D)
+    assert frame_feat.is_contiguous() and text_hat.is_contiguous() and text_hat.shape[1] == E
+    assert frame_feat.shape[0] == B * T and video_features.shape == (B, E) and logits.shape == (B, n_cls)
+    assert video_features.is_contiguous() and logits.is_contiguous()
+    rc = _lib.load().gava_head_fwd(frame_feat.data_ptr(), _ptr(summary_tok), text_hat.data_ptr(),
+                                   class_offsets.data_ptr(), video_features.data_ptr(), _ptr(summary_out),
+                                   logits.data_ptr(), B, T, E, D, n_cls, scale, logit_bias, _stream())
+    _lib.check(rc, "gava_head_fwd")
+    return logits

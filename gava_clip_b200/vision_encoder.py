@@ -1,0 +1,353 @@
+"""Drop-in `CLIPVisionEncoder` whose forward runs on hand-written sm_100a kernels.
+
+Interface mirrors the reference module (constructor kwargs, parameter names/shapes, return tuple):
+    training/VitaCLIP_vision_encoder.py:18-132   (CLIPVisionEncoder)
+    training/VitaCLIP_vision_encoder_utils.py:83-203 (TransformerEncoderLayer), :205-220 (ImagePatchEmbed2D)
+
+The nn.Modules below only *hold* parameters under the reference's state_dict keys; the arithmetic is
+done by `TowerEngine`, which keeps a packed bf16 copy of the weights and a per-shape workspace in HBM
+and drives the C-ABI kernels (ops.py).  There is no PyTorch/CPU fallback for the forward.
+
+HBM layout (all row-major, one frame f = b*T + t after the other):
+    x      fp32 [BT*N0, D]   residual stream, live rows only: [cls | patches] per frame
+    xn     bf16 [BT*N0, D]   LayerNorm output / attention output (aliased)
+    qkv    bf16 [BT*N0, 3D]  q | k | v of the live rows
+    kvaux  bf16 [G+2BT, 2D]  k | v of the K/V-only rows: G global prompts, BT local prompts, BT summary tokens
+    h      bf16 [BT*N0, 4D]  QuickGELU(fc1)
+Prompt tokens never occupy rows of the residual stream: their query rows are dead in the reference
+(utils.py:194-197, vision_encoder.py:121) and only their keys/values are ever needed.
+"""
+from __future__ import annotations
+
+import math
+import os
+from collections import OrderedDict
+from functools import reduce
+from operator import mul
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+Tensor = torch.Tensor
+LN_EPS = 1e-5
+
+
+class QuickGELU(nn.Module):
+    """x * sigmoid(1.702 x) -- kept for interface parity (utils.py:18-20); the kernels fuse it into fc1."""
+
+    def forward(self, x: Tensor) -> Tensor:
+        return x * torch.sigmoid(1.702 * x)
+
+
+class LayerNorm(nn.LayerNorm):
+    """Parameter holder; fp32-statistics semantics (utils.py:22-28) are implemented in gava_layernorm_fwd."""
+
+    def forward(self, x: Tensor) -> Tensor:
+        return F.layer_norm(x.float(), self.normalized_shape, self.weight, self.bias, self.eps).to(x.dtype)
+
+
+class Attention(nn.Module):
+    """Holder of q/k/v/out projections (utils.py:31-59): xavier-uniform weights, zero biases."""
+
+    def __init__(self, q_in_dim: int, k_in_dim: int, v_in_dim: int, qk_proj_dim: int, v_proj_dim: int,
+                 num_heads: int, out_dim: int):
+        super().__init__()
+        self.q_proj = nn.Linear(q_in_dim, qk_proj_dim)
+        self.k_proj = nn.Linear(k_in_dim, qk_proj_dim)
+        self.v_proj = nn.Linear(v_in_dim, v_proj_dim)
+        self.out_proj = nn.Linear(v_proj_dim, out_dim)
+        self.num_heads = num_heads
+        assert qk_proj_dim % num_heads == 0 and v_proj_dim % num_heads == 0
+        for lin in (self.q_proj, self.k_proj, self.v_proj, self.out_proj):
+            nn.init.xavier_uniform_(lin.weight)
+            nn.init.zeros_(lin.bias)
+
+
+def _prompt_init_bound(patch_size, dim: int) -> float:
+    return math.sqrt(6.0 / float(3 * reduce(mul, patch_size, 1) + dim))
+
+
+class TransformerEncoderLayer(nn.Module):
+    """Parameter holder for one block; key layout of utils.py:104-139 (29 tensors with all prompt options)."""
+
+    def __init__(self, in_feature_dim: int = 768, qkv_dim: int = 768, num_heads: int = 12, mlp_factor: float = 4.0,
+                 mlp_dropout: float = 0.0, act=QuickGELU, use_summary_token: bool = False,
+                 use_local_prompts: bool = False, num_frames: int = 8, patch_size: Tuple[int, int] = (16, 16)):
+        super().__init__()
+        d = in_feature_dim
+        self.attn = Attention(d, d, d, qkv_dim, qkv_dim, num_heads, d)
+        mlp_dim = round(mlp_factor * d)
+        self.mlp = nn.Sequential(OrderedDict([
+            ("fc1", nn.Linear(d, mlp_dim)), ("act", act()), ("dropout", nn.Dropout(mlp_dropout)),
+            ("fc2", nn.Linear(mlp_dim, d)),
+        ]))
+        self.norm1 = LayerNorm(d)
+        self.norm2 = LayerNorm(d)
+        self.use_summary_token = use_summary_token
+        self.use_local_prompts = use_local_prompts
+        if use_summary_token or use_local_prompts:
+            self.cls_proj = nn.Linear(d, d)
+            self.num_frames = num_frames
+        if use_summary_token:
+            self.summary_ln = LayerNorm(d)
+            self.summary_attn_layer = Attention(d, d, d, qkv_dim, qkv_dim, num_heads, d)
+        if use_local_prompts:
+            self.local_prompts = nn.Parameter(torch.zeros(1, num_frames, d))
+            bound = _prompt_init_bound(patch_size, d)
+            nn.init.uniform_(self.local_prompts.data, -bound, bound)
+        for lin in (self.mlp.fc1, self.mlp.fc2):
+            nn.init.xavier_uniform_(lin.weight)
+            nn.init.normal_(lin.bias, std=1e-6)
+
+
+class ImagePatchEmbed2D(nn.Module):
+    """Holder of the patch conv (utils.py:205-220); executed as patch gather + tcgen05 GEMM."""
+
+    def __init__(self, img_size: int = 224, patch_size: int = 16, in_chans: int = 3, embed_dim: int = 768):
+        super().__init__()
+        self.img_size = img_size
+        self.patch_size = patch_size
+        self.num_patches = (img_size // patch_size) ** 2
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+
+def _ceil_to(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+class TowerEngine:
+    """Packed weights + workspaces + kernel schedule for one CLIPVisionEncoder on one GPU."""
+
+    def __init__(self, enc: "CLIPVisionEncoder", device: torch.device):
+        self.enc = enc
+        self.device = device
+        self.packed: Dict[str, Tensor] = {}
+        self.signature = None
+        self.ws: Dict[Tuple[int, int], Dict[str, Tensor]] = {}
+        self.graphs: Dict[Tuple[int, int], Tuple[torch.cuda.CUDAGraph, Tensor]] = {}
+        self.seen: Dict[Tuple[int, int], int] = {}
+
+    # ------------------------------------------------------------------ weights
+    def _sig(self):
+        return tuple((p.data_ptr(), p._version) for p in self.enc.parameters())
+
+    def pack(self) -> None:
+        """bf16 K-major copies of every GEMM weight; q|k|v concatenated to one [3D, D] operand."""
+        sig = self._sig()
+        if sig == self.signature:
+            return
+        e, dev = self.enc, self.device
+        bf = lambda t: t.detach().to(dev, torch.bfloat16).contiguous()
+        f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
+        P: Dict[str, Tensor] = {}
+        D = e.feature_dim
+        w = e.patch_embed.proj.weight.detach().reshape(D, -1)
+        kpad = _ceil_to(w.shape[1], 64)
+        wp = torch.zeros(D, kpad, device=dev, dtype=torch.bfloat16)
+        wp[:, : w.shape[1]] = w.to(dev, torch.bfloat16)
+        P["patch.w"], P["patch.b"] = wp, f32(e.patch_embed.proj.bias)
+        P["cls_token"], P["pos_embed"] = f32(e.cls_token), f32(e.pos_embed)
+        P["time_embed"] = f32(e.time_embed)
+        for n in ("ln_pre", "ln_post"):
+            P[n + ".w"], P[n + ".b"] = f32(getattr(e, n).weight), f32(getattr(e, n).bias)
+        ep = _ceil_to(e.embed_dim, 128)
+        pj = torch.zeros(ep, D, device=dev, dtype=torch.bfloat16)       # proj^T, rows padded to the N tile
+        pj[: e.embed_dim] = e.proj.detach().t().to(dev, torch.bfloat16)
+        P["proj.wT"] = pj
+        P["global_prompts"] = f32(e.global_prompts)
+        for i, blk in enumerate(e.blocks):
+            k = f"b{i}."
+            a = blk.attn
+            P[k + "qkv.w"] = bf(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0))
+            P[k + "qkv.b"] = f32(torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0))
+            P[k + "out.w"], P[k + "out.b"] = bf(a.out_proj.weight), f32(a.out_proj.bias)
+            P[k + "fc1.w"], P[k + "fc1.b"] = bf(blk.mlp.fc1.weight), f32(blk.mlp.fc1.bias)
+            P[k + "fc2.w"], P[k + "fc2.b"] = bf(blk.mlp.fc2.weight), f32(blk.mlp.fc2.bias)
+            for n in ("norm1", "norm2", "summary_ln"):
+                P[k + n + ".w"], P[k + n + ".b"] = f32(getattr(blk, n).weight), f32(getattr(blk, n).bias)
+            P[k + "cls.w"], P[k + "cls.b"] = bf(blk.cls_proj.weight), f32(blk.cls_proj.bias)
+            s = blk.summary_attn_layer
+            P[k + "sqkv.w"] = bf(torch.cat([s.q_proj.weight, s.k_proj.weight, s.v_proj.weight], 0))
+            P[k + "sqkv.b"] = f32(torch.cat([s.q_proj.bias, s.k_proj.bias, s.v_proj.bias], 0))
+            P[k + "sout.w"], P[k + "sout.b"] = bf(s.out_proj.weight), f32(s.out_proj.bias)
+            P[k + "local"] = f32(blk.local_prompts)
+        self.packed = P
+        self.signature = sig
+        self.graphs.clear()  # captured graphs hold pointers into the old packed tensors
+
+    def time_embed_for(self, T: int) -> Tensor:
+        """nearest-neighbour resize when T differs from the trained length (vision_encoder.py:91-97)."""
+        te = self.packed["time_embed"]
+        if te.shape[0] == T:
+            return te
+        key = f"time_embed@{T}"
+        if key not in self.packed:
+            r = F.interpolate(te.t().unsqueeze(0), size=(T,), mode="nearest").squeeze(0).t().contiguous()
+            self.packed[key] = r
+        return self.packed[key]
+
+    # ------------------------------------------------------------------ workspace
+    def workspace(self, B: int, T: int) -> Dict[str, Tensor]:
+        key = (B, T)
+        if key in self.ws:
+            return self.ws[key]
+        e, dev = self.enc, self.device
+        D, N0, G = e.feature_dim, int(e.num_patches), e.num_global_prompts
+        BT = B * T
+        M = BT * N0
+        Dm = e.blocks[0].mlp.fc1.out_features
+        bf, f32 = torch.bfloat16, torch.float32
+        z = lambda *s, dt: torch.empty(*s, device=dev, dtype=dt)
+        W = {
+            "patches": z(BT * (N0 - 1), self.packed["patch.w"].shape[1], dt=bf),
+            "x": z(M, D, dt=f32),
+            "xn": z(M, D, dt=bf),
+            "qkv": z(M, 3 * D, dt=bf),
+            "h": z(M, Dm, dt=bf),
+            "cls_bf": z(BT, D, dt=bf),
+            "cls_proj": z(BT, D, dt=f32),
+            "sum_n": z(BT, D, dt=bf),
+            "sqkv": z(BT, 3 * D, dt=bf),
+            "smix": z(BT, D, dt=bf),
+            "summary": z(BT, D, dt=f32),
+            "aux_n": z(G + 2 * BT, D, dt=bf),
+            "kvaux": z(G + 2 * BT, 2 * D, dt=bf),
+            "frame_feat": z(BT, self.packed["proj.wT"].shape[0], dt=f32),
+        }
+        self.ws[key] = W
+        return W
+
+    # ------------------------------------------------------------------ schedule
+    def encode_frames(self, video: Tensor) -> Tuple[Tensor, Tensor]:
+        """video fp32 [B,3,T,H,W] -> (frame_feat fp32 [BT, >=E], summary tokens fp32 [BT, D]).
+
+        Everything up to (not including) the temporal mean of vision_encoder.py:128-130.
+        """
+        e, P = self.enc, self.packed
+        B, _, T, Hh, Ww = video.shape
+        D, N0, G, H = e.feature_dim, int(e.num_patches), e.num_global_prompts, e.num_heads
+        BT = B * T
+        M = BT * N0
+        W = self.workspace(B, T)
+        te = self.time_embed_for(T)
+        x, xn, qkv, h = W["x"], W["xn"], W["qkv"], W["h"]
+
+        # patch embedding (+bias +pos +time), cls rows, ln_pre          vision_encoder.py:105-113
+        ops.patch_gather(video, W["patches"], e.patch_embed.patch_size)
+        ops.gemm(W["patches"], P["patch.w"], x, mode=ops.EPI_PATCH_F32, bias=P["patch.b"], pos=P["pos_embed"],
+                 time_embed=te, group=N0 - 1, group_stride=N0, row_offset=1, T=T)
+        ops.cls_rows(x, N0, P["cls_token"], P["pos_embed"], te, BT, T)
+        ops.layernorm(x, P["ln_pre.w"], P["ln_pre.b"], x, rows=M, in_row_stride=D)
+
+        L = len(e.blocks)
+        for i in range(L):
+            k = f"b{i}."
+            # ---- temporal message: cls_proj -> summary attention -> K/V-only prompt rows   utils.py:160-188
+            ops.layernorm(x, None, None, W["cls_bf"], rows=BT, in_row_stride=N0 * D)
+            ops.gemm(W["cls_bf"], P[k + "cls.w"], W["cls_proj"], mode=ops.EPI_BIAS_F32, bias=P[k + "cls.b"])
+            ops.layernorm(W["cls_proj"], P[k + "summary_ln.w"], P[k + "summary_ln.b"], W["sum_n"], rows=BT,
+                          in_row_stride=D)
+            ops.gemm(W["sum_n"], P[k + "sqkv.w"], W["sqkv"], mode=ops.EPI_BIAS_BF16, bias=P[k + "sqkv.b"])
+            ops.temporal_attention(W["sqkv"], W["smix"], B, T, H)
+            ops.gemm(W["smix"], P[k + "sout.w"], W["summary"], mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "sout.b"],
+                     resid=W["cls_proj"])
+            ops.prompt_rows(P["global_prompts"][i], P[k + "local"], W["cls_proj"], W["summary"], P[k + "norm1.w"],
+                            P[k + "norm1.b"], W["aux_n"], B, T, LN_EPS)
+            ops.gemm(W["aux_n"], P[k + "qkv.w"][D:], W["kvaux"], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:])
+            # ---- x = x + attn(norm1(x)) on the live rows                                     utils.py:190-191
+            ops.layernorm(x, P[k + "norm1.w"], P[k + "norm1.b"], xn, rows=M, in_row_stride=D)
+            ops.gemm(xn, P[k + "qkv.w"], qkv, mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"])
+            ops.attention(qkv, W["kvaux"], xn, B=B, T=T, N0=N0, G=G, H=H)
+            ops.gemm(xn, P[k + "out.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "out.b"], resid=x)
+            # ---- x = x + fc2(QuickGELU(fc1(norm2(x))))                                        utils.py:199
+            ops.layernorm(x, P[k + "norm2.w"], P[k + "norm2.b"], xn, rows=M, in_row_stride=D)
+            ops.gemm(xn, P[k + "fc1.w"], h, mode=ops.EPI_BIAS_GELU_BF16, bias=P[k + "fc1.b"])
+            ops.gemm(h, P[k + "fc2.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"], resid=x)
+
+        # ln_post(cls) @ proj per frame                                   vision_encoder.py:126-127
+        ops.layernorm(x, P["ln_post.w"], P["ln_post.b"], W["cls_bf"], rows=BT, in_row_stride=N0 * D)
+        ops.gemm(W["cls_bf"], P["proj.wT"], W["frame_feat"], mode=ops.EPI_BIAS_F32)
+        return W["frame_feat"], W["summary"]
+
+
+class CLIPVisionEncoder(nn.Module):
+    """Same constructor / parameters / outputs as the reference class (vision_encoder.py:18-132)."""
+
+    def __init__(self, input_size: Tuple[int, int] = (224, 224), num_frames: int = 8, feature_dim: int = 768,
+                 patch_size: Tuple[int, int] = (16, 16), num_heads: int = 12, num_layers: int = 12,
+                 mlp_factor: float = 4.0, act=QuickGELU, embed_dim: int = 512, use_summary_token: bool = False,
+                 use_local_prompts: bool = False, use_global_prompts: bool = False, num_global_prompts: int = 8):
+        super().__init__()
+        self.feature_dim = feature_dim
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.num_frames = num_frames
+        self.patch_embed = ImagePatchEmbed2D(img_size=input_size[0], patch_size=patch_size[0], in_chans=3,
+                                             embed_dim=feature_dim)
+        self.num_patches = (input_size[0] // patch_size[0]) * (input_size[1] // patch_size[1]) + 1  # incl. cls
+        self.cls_token = nn.Parameter(torch.zeros([feature_dim]))
+        self.pos_embed = nn.Parameter(torch.zeros([self.num_patches, feature_dim]))
+        self.time_embed = nn.Parameter(torch.zeros([num_frames, feature_dim]))
+        self.blocks = nn.ModuleList([
+            TransformerEncoderLayer(in_feature_dim=feature_dim, qkv_dim=feature_dim, num_heads=num_heads,
+                                    mlp_factor=mlp_factor, act=act, use_summary_token=use_summary_token,
+                                    use_local_prompts=use_local_prompts, num_frames=num_frames, patch_size=patch_size)
+            for _ in range(num_layers)])
+        self.ln_pre = LayerNorm(feature_dim)
+        self.ln_post = LayerNorm(feature_dim)
+        self.proj = nn.Parameter(feature_dim ** -0.5 * torch.randn(feature_dim, embed_dim))
+        self.use_summary_token = use_summary_token
+        self.use_local_prompts = use_local_prompts
+        self.use_global_prompts = use_global_prompts
+        self.num_global_prompts = num_global_prompts
+        if use_global_prompts:
+            self.global_prompts = nn.Parameter(torch.zeros(num_layers, num_global_prompts, feature_dim))
+            bound = _prompt_init_bound(patch_size, feature_dim)
+            nn.init.uniform_(self.global_prompts.data, -bound, bound)
+        for p in (self.cls_token, self.pos_embed, self.time_embed):
+            nn.init.normal_(p, std=0.02)
+        self._engine: Optional[TowerEngine] = None
+
+    # -- engine plumbing ---------------------------------------------------------------------------
+    def engine(self, device: torch.device) -> TowerEngine:
+        if not (self.use_global_prompts and self.use_summary_token and self.use_local_prompts):
+            # the reference itself only runs with all three enabled (the other branch crashes)
+            raise NotImplementedError("the sm_100a tower implements the summary+local+global prompt configuration")
+        if self.feature_dim // self.num_heads != 64:
+            raise NotImplementedError("attention kernel is specialised for head_dim 64")
+        if self._engine is None or self._engine.device != device:
+            self._engine = TowerEngine(self, device)
+        self._engine.pack()
+        return self._engine
+
+    def _check_input(self, x: Tensor) -> Tensor:
+        if x.dim() != 5 or x.shape[1] != 3:
+            raise ValueError(f"expected video of shape (B,3,T,H,W), got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError("gava_clip_b200 runs on sm_100a only: move the clip to a CUDA device "
+                               "(there is no CPU fallback)")
+        if x.shape[2] != self.num_frames:
+            # the reference blocks hard-code num_frames (utils.py:161): other lengths mis-shape its views
+            raise ValueError(f"clip has T={x.shape[2]} frames but the encoder was built with num_frames={self.num_frames}")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("backward kernels are not part of this build: call under torch.no_grad() / eval()")
+        return x.contiguous().float()
+
+    def frames_forward(self, x: Tensor) -> Tuple[Tensor, Tensor, int, int]:
+        """per-frame projected cls features [BT, E(+pad)] and summary tokens [BT, D] (workspace views)."""
+        x = self._check_input(x)
+        eng = self.engine(x.device)
+        ff, st = eng.encode_frames(x)
+        return ff, st, x.shape[0], x.shape[2]
+
+    def forward(self, x: Tensor):
+        ff, st, B, T = self.frames_forward(x)
+        E = self.embed_dim
+        # temporal means (vision_encoder.py:128-130); the fused head kernel does the same inside VitaCLIP.forward
+        cls_x = ff[:, :E].reshape(B, T, E).mean(dim=1)
+        summary = st.reshape(B, T, -1).mean(dim=1)
+        return cls_x, summary

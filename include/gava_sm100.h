@@ -1,0 +1,123 @@
+/* gava_sm100.h -- C ABI of libgava_sm100.so: hand-written sm_100a (B200) kernels for the
+ * GaVA-CLIP / Vita-CLIP video-encoder forward and contrastive logit head.
+ *
+ * The reference (lisqzqng/GaVA-CLIP) is pure PyTorch and has no FFI of its own; the boundary it
+ * exposes is the nn.Module API of training/VitaCLIP_model.py.  Each entry point below replaces the
+ * ATen library call(s) at the cited reference lines (paths relative to the reference root).
+ *
+ * Conventions:
+ *   - plain pointers + sizes only; every pointer is DEVICE memory owned by the caller; nothing is
+ *     allocated, freed or retained by the library; outputs are caller-preallocated.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), CUDA-graph capturable.
+ *   - return value: 0 = OK, >0 = cudaError_t of the launch, <0 = invalid argument / unsupported shape.
+ *     gava_last_error_string() returns a thread-local description of the last failure.
+ *   - bf16 = __nv_bfloat16 (2 bytes), f32 = float.  All matrices are row-major.
+ */
+#ifndef GAVA_SM100_H_
+#define GAVA_SM100_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAVA_ABI_VERSION 1
+
+/* epilogue modes of gava_gemm_bf16_fwd */
+enum gava_epilogue_mode {
+  GAVA_EPI_BIAS_BF16 = 0,      /* out(bf16) = acc + bias                                  (q/k/v proj)     */
+  GAVA_EPI_BIAS_GELU_BF16 = 1, /* out(bf16) = QuickGELU(acc + bias)                       (mlp.fc1 + act)  */
+  GAVA_EPI_BIAS_RESID_F32 = 2, /* out(f32)  = resid + acc + bias  (out may alias resid)   (out_proj, fc2)  */
+  GAVA_EPI_BIAS_F32 = 3,       /* out(f32)  = acc + bias                                  (cls_proj, proj) */
+  GAVA_EPI_PATCH_F32 = 4       /* out(f32)[(r/group)*group_stride + r%group + row_offset]
+                                    = acc + bias + pos[1 + r%group] + time_embed[(r/group)%T] (patch embed) */
+};
+
+typedef struct gava_gemm_epilogue {
+  int32_t mode;            /* enum gava_epilogue_mode */
+  const float* bias;       /* [N] or NULL */
+  const float* resid;      /* f32 [M, ldr], mode RESID only */
+  int64_t ldr;
+  void* out;               /* bf16 or f32, row pitch ldo (elements) */
+  int64_t ldo;
+  int32_t group;           /* PATCH: patches per frame (196) */
+  int32_t group_stride;    /* PATCH: token rows per frame in `out` (197) */
+  int32_t row_offset;      /* PATCH: first patch slot inside a frame (1, after cls) */
+  int32_t T;               /* PATCH: frames per clip */
+  const float* pos;        /* PATCH: f32 [group+1, N]  (visual.pos_embed) */
+  const float* time_embed; /* PATCH: f32 [T, N]        (visual.time_embed, already resized to T) */
+} gava_gemm_epilogue;
+
+int gava_version(void);
+const char* gava_last_error_string(void);
+/* one-time per-process setup (kernel attributes); optional, every entry point self-initialises */
+int gava_init(void);
+
+/* C[M,N] = A[M,K] * W[N,K]^T with a fused epilogue.  A: bf16 [M,K] pitch lda; W: bf16 [N,K] pitch ldw
+ * (nn.Linear weight layout).  tcgen05.mma / TMEM accumulators / TMA operand loads.
+ * Needs K % 64 == 0, N % 128 == 0, 16-byte aligned pointers and pitches.
+ * Replaces nn.Linear at VitaCLIP_vision_encoder_utils.py:66,79,110-115,164-165, Conv2d at :215-219 and
+ * `cls_x @ self.proj` at VitaCLIP_vision_encoder.py:127. */
+int gava_gemm_bf16_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                       const gava_gemm_epilogue* epi, void* stream);
+
+/* LayerNorm over the last dim (fp32 statistics, eps inside the sqrt), row r read from
+ * x + r * in_row_stride (elements, f32), written to out + r * out_row_stride as bf16 (out_bf16 != 0) or f32.
+ * weight == NULL: no normalisation, plain copy/cast (used to gather the cls rows).  In-place (out == x, f32) is safe.
+ * D must be a multiple of 128 and <= 1024.  Replaces LayerNorm.forward, VitaCLIP_vision_encoder_utils.py:22-28. */
+int gava_layernorm_fwd(const float* x, int64_t in_row_stride, const float* weight, const float* bias, void* out,
+                       int64_t out_row_stride, int32_t out_bf16, int64_t rows, int32_t D, float eps, void* stream);
+
+/* Patch gather (im2col) for Conv2d(3, D, k=s=P): video f32 [B,3,T,H,W] -> A bf16 [B*T*(H/P)*(W/P), Kpad] with
+ * column index c*P*P + ph*P + pw (the flattened conv weight order); columns >= 3*P*P are zero.
+ * Replaces the frame flatten + conv input read, VitaCLIP_vision_encoder.py:105, ..._utils.py:219. */
+int gava_patch_gather_fwd(const float* video, void* A, int32_t B, int32_t T, int32_t H, int32_t W, int32_t P,
+                          int32_t Kpad, void* stream);
+
+/* cls rows of the embedded stream: x[f*tokens_per_frame + 0, :] = cls_token + pos_embed[0] + time_embed[f % T].
+ * Replaces the cls concat + broadcasts, VitaCLIP_vision_encoder.py:108-111. */
+int gava_cls_rows_fwd(float* x, int32_t tokens_per_frame, const float* cls_token, const float* pos_embed,
+                      const float* time_embed, int32_t BT, int32_t T, int32_t D, void* stream);
+
+/* Summary-token attention core: for every video b and head h, softmax(q k^T / sqrt(dh)) v over the T cls-derived
+ * tokens.  qkv: bf16 [B*T, 3*D] = [q | k | v] of summary_attn_layer; out: bf16 [B*T, D].  dh must be 64.
+ * Replaces the einsum/softmax/einsum of Attention.forward for L=T, VitaCLIP_vision_encoder_utils.py:71-77,170. */
+int gava_temporal_attention_fwd(const void* qkv, void* out, int32_t B, int32_t T, int32_t H, void* stream);
+
+/* K/V-only prompt rows of one layer, LayerNorm(norm1)-ed and cast to bf16:
+ *   row g (g < G)            : global_prompts[g]
+ *   row G + b*T + t          : local_prompts[t] + cls_proj_out[b*T + t]
+ *   row G + B*T + f          : summary[f]                     (f = b*T + t)
+ * out: bf16 [G + 2*B*T, D].  Replaces the global/local/summary token construction + norm1 on those rows,
+ * VitaCLIP_vision_encoder.py:117-119 and ..._utils.py:171-190. */
+int gava_prompt_rows_fwd(const float* global_prompts, const float* local_prompts, const float* cls_proj_out,
+                         const float* summary, const float* ln_weight, const float* ln_bias, void* out, int32_t G,
+                         int32_t B, int32_t T, int32_t D, float eps, void* stream);
+
+/* Main multi-head self-attention core with a K/V-only prompt prefix (flash-style, scores never leave the SM).
+ * For frame f (video b = f / T) and head h the queries are the first n_q live rows of the frame and the keys/values
+ * are: the N0 live rows of the frame (from qkv) + G global rows + the T local rows of video b + the summary row of
+ * frame f (from kv_aux, row layout of gava_prompt_rows_fwd).
+ *   qkv    : bf16 [B*T*N0, 3*D]  = [q | k | v] (q NOT pre-scaled; 1/sqrt(dh) is applied inside)
+ *   kv_aux : bf16 [G + 2*B*T, 2*D] = [k | v]
+ *   out    : bf16 [B*T*N0, D]; only rows f*N0 + i, i < n_q are written
+ * dh = D / H must be 64.  Replaces Attention.forward core, VitaCLIP_vision_encoder_utils.py:71-77, for the
+ * token set built at :171-188 (dead query rows :194-197 are never computed). */
+int gava_attention_fwd(const void* qkv, const void* kv_aux, void* out, int32_t B, int32_t T, int32_t N0, int32_t G,
+                       int32_t H, int32_t n_q, void* stream);
+
+/* Logit head.  frame_feat: f32 [B*T, E] (ln_post(cls) @ proj per frame); summary_tok: f32 [B*T, D] or NULL.
+ *   video_features[b] = mean_t frame_feat[b*T + t]                               (f32 [B, E], un-normalised)
+ *   summary_out[b]    = mean_t summary_tok[b*T + t]                              (f32 [B, D], optional)
+ *   logits[b, c]      = mean_{k in class c} scale * <v_hat_b, t_hat_k> + bias    (f32 [B, n_cls])
+ * text_hat: f32 [R, E], rows already L2-normalised, grouped by class; class_offsets: int32 [n_cls + 1].
+ * Replaces VitaCLIP_vision_encoder.py:128-130 and VitaCLIP_model.py:255,287-289 / :303-306, :308-309. */
+int gava_head_fwd(const float* frame_feat, const float* summary_tok, const float* text_hat,
+                  const int32_t* class_offsets, float* video_features, float* summary_out, float* logits, int32_t B,
+                  int32_t T, int32_t E, int32_t D, int32_t n_cls, float scale, float logit_bias, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAVA_SM100_H_ */

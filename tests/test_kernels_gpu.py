@@ -1,0 +1,248 @@
+"""Per-kernel parity on the B200: each C-ABI entry point against a plain PyTorch fp32 reference
+of the same op (the op as the reference model computes it; file:line in include/gava_sm100.h).
+
+Tolerances: bf16 tensor-core inputs with fp32 accumulation -> compare against an fp32 reference fed
+the SAME bf16-rounded operands, so only accumulation order / output rounding differ.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, ref):
+    return float((a.double() - ref.double()).abs().max() / ref.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 768, 768), (1000, 256, 128), (1032, 1536, 768),
+                                   (4096, 2304, 768), (197 * 16, 768, 3072), (512, 128, 768), (333, 384, 192)])
+def test_gemm_bias_bf16(cuda, M, N, K):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=cuda, generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device=cuda, generator=g)
+    out = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(a, w, out, mode=ops.EPI_BIAS_BF16, bias=bias)
+    ref = a.float() @ w.float().t() + bias
+    torch.cuda.synchronize()
+    assert _rel(out.float(), ref) < 1e-2  # bf16 output rounding: 2^-8 relative
+
+
+def test_gemm_gelu(cuda):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    M, N, K = 640, 3072, 768
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=cuda, generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device=cuda, generator=g) * 0.1
+    out = torch.empty(M, N, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(a, w, out, mode=ops.EPI_BIAS_GELU_BF16, bias=bias)
+    y = a.float() @ w.float().t() + bias
+    ref = y * torch.sigmoid(1.702 * y)
+    assert _rel(out.float(), ref) < 1e-2
+
+
+def test_gemm_resid_inplace_and_strided_a(cuda):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(2)
+    M, N, K = 1970, 768, 3072
+    big = torch.randn(M, K + 64, device=cuda, generator=g).bfloat16()
+    a = big[:, :K]                      # row pitch K+64: exercises lda != K
+    w = (torch.randn(N, K, device=cuda, generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(N, device=cuda, generator=g)
+    x = torch.randn(M, N, device=cuda, generator=g)
+    ref = x + a.float() @ w.float().t() + bias
+    ops.gemm(a, w, x, mode=ops.EPI_BIAS_RESID_F32, bias=bias, resid=x)
+    assert _rel(x, ref) < 2e-5
+
+
+def test_gemm_f32_no_bias(cuda):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    M, N, K = 512, 512, 768
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    w = (torch.randn(N, K, device=cuda, generator=g) * K ** -0.5).bfloat16()
+    out = torch.empty(M, N, device=cuda)
+    ops.gemm(a, w, out, mode=ops.EPI_BIAS_F32)
+    assert _rel(out, a.float() @ w.float().t()) < 2e-5
+
+
+def test_gemm_patch_epilogue(cuda):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(4)
+    BT, T, Np, D, K = 6, 3, 196, 768, 768
+    a = torch.randn(BT * Np, K, device=cuda, generator=g).bfloat16()
+    w = (torch.randn(D, K, device=cuda, generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(D, device=cuda, generator=g)
+    pos = torch.randn(Np + 1, D, device=cuda, generator=g)
+    te = torch.randn(T, D, device=cuda, generator=g)
+    x = torch.full((BT * (Np + 1), D), float("nan"), device=cuda)
+    ops.gemm(a, w, x, mode=ops.EPI_PATCH_F32, bias=bias, pos=pos, time_embed=te, group=Np, group_stride=Np + 1,
+             row_offset=1, T=T)
+    y = (a.float() @ w.float().t() + bias).view(BT, Np, D) + pos[1:] + te[torch.arange(BT, device=cuda) % T][:, None]
+    xv = x.view(BT, Np + 1, D)
+    assert torch.isnan(xv[:, 0]).all()           # cls slots untouched
+    assert _rel(xv[:, 1:], y) < 2e-5
+
+
+def test_gemm_rejects_bad_shape(cuda):
+    from gava_clip_b200 import ops
+    a = torch.zeros(128, 100, device=cuda, dtype=torch.bfloat16)
+    w = torch.zeros(128, 100, device=cuda, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, w, torch.empty(128, 128, device=cuda, dtype=torch.bfloat16), mode=ops.EPI_BIAS_BF16)
+
+
+@pytest.mark.parametrize("D", [512, 768, 1024])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_layernorm(cuda, D, out_dtype):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(D)
+    rows = 1001
+    x = torch.randn(rows, D, device=cuda, generator=g) * 3 + 1
+    w = torch.randn(D, device=cuda, generator=g)
+    b = torch.randn(D, device=cuda, generator=g)
+    out = torch.empty(rows, D, device=cuda, dtype=out_dtype)
+    ops.layernorm(x, w, b, out, rows=rows, in_row_stride=D)
+    ref = F.layer_norm(x, (D,), w, b, 1e-5)
+    tol = 1e-2 if out_dtype == torch.bfloat16 else 1e-5
+    assert _rel(out.float(), ref) < tol
+
+
+def test_layernorm_gather_cast_and_inplace(cuda):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(7)
+    BT, N0, D = 24, 197, 768
+    x = torch.randn(BT * N0, D, device=cuda, generator=g)
+    out = torch.empty(BT, D, device=cuda, dtype=torch.bfloat16)
+    ops.layernorm(x, None, None, out, rows=BT, in_row_stride=N0 * D)       # gather cls rows, cast only
+    assert torch.equal(out, x.view(BT, N0, D)[:, 0].bfloat16())
+    w = torch.randn(D, device=cuda, generator=g); b = torch.randn(D, device=cuda, generator=g)
+    ref = F.layer_norm(x, (D,), w, b, 1e-5)
+    ops.layernorm(x, w, b, x, rows=BT * N0, in_row_stride=D)               # in place, fp32
+    assert _rel(x, ref) < 1e-5
+
+
+@pytest.mark.parametrize("P,H,Kpad", [(16, 224, 768), (14, 224, 640), (16, 64, 768)])
+def test_patch_gather(cuda, P, H, Kpad):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(P)
+    B, T = 2, 3
+    v = torch.randn(B, 3, T, H, H, device=cuda, generator=g)
+    gh = H // P
+    out = torch.full((B * T * gh * gh, Kpad), 7.0, device=cuda, dtype=torch.bfloat16)
+    ops.patch_gather(v, out, P)
+    frames = v.permute(0, 2, 1, 3, 4).flatten(0, 1)
+    ref = F.unfold(frames, kernel_size=P, stride=P).transpose(1, 2).reshape(-1, 3 * P * P).bfloat16()
+    assert torch.equal(out[:, :3 * P * P], ref)
+    if Kpad > 3 * P * P:
+        assert (out[:, 3 * P * P:] == 0).all()
+
+
+def test_cls_rows(cuda):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(9)
+    BT, T, N0, D = 12, 4, 197, 768
+    x = torch.zeros(BT * N0, D, device=cuda)
+    cls = torch.randn(D, device=cuda, generator=g); pos = torch.randn(N0, D, device=cuda, generator=g)
+    te = torch.randn(T, D, device=cuda, generator=g)
+    ops.cls_rows(x, N0, cls, pos, te, BT, T)
+    ref = cls + pos[0] + te[torch.arange(BT, device=cuda) % T]
+    assert torch.allclose(x.view(BT, N0, D)[:, 0], ref, atol=1e-6)
+    assert (x.view(BT, N0, D)[:, 1:] == 0).all()
+
+
+@pytest.mark.parametrize("T", [8, 16, 70])
+def test_temporal_attention(cuda, T):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(T)
+    B, H = 3, 12
+    D = H * 64
+    qkv = torch.randn(B * T, 3 * D, device=cuda, generator=g).bfloat16()
+    out = torch.empty(B * T, D, device=cuda, dtype=torch.bfloat16)
+    ops.temporal_attention(qkv, out, B, T, H)
+    q, k, v = qkv.float().view(B, T, 3, H, 64).unbind(2)
+    aff = torch.einsum("nqhc,nkhc->nqkh", q / 8.0, k).softmax(dim=-2)
+    ref = torch.einsum("nqlh,nlhc->nqhc", aff, v).reshape(B * T, D)
+    assert _rel(out.float(), ref) < 1e-2
+
+
+def test_prompt_rows(cuda):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, T, G, D = 3, 8, 8, 768
+    gp = torch.randn(G, D, device=cuda, generator=g); lp = torch.randn(1, T, D, device=cuda, generator=g)
+    cp = torch.randn(B * T, D, device=cuda, generator=g); sm = torch.randn(B * T, D, device=cuda, generator=g)
+    w = torch.randn(D, device=cuda, generator=g); b = torch.randn(D, device=cuda, generator=g)
+    out = torch.empty(G + 2 * B * T, D, device=cuda, dtype=torch.bfloat16)
+    ops.prompt_rows(gp, lp, cp, sm, w, b, out, B, T)
+    rows = torch.cat([gp, (lp.expand(B, -1, -1) + cp.view(B, T, D)).reshape(B * T, D), sm])
+    ref = F.layer_norm(rows, (D,), w, b, 1e-5)
+    assert _rel(out.float(), ref) < 1e-2
+
+
+def _attention_ref(qkv, kv_aux, B, T, N0, G, H):
+    D = H * 64
+    BT = B * T
+    q, k, v = qkv.float().view(BT, N0, 3, H, 64).unbind(2)
+    ka, va = kv_aux.float().view(-1, 2, H, 64).unbind(1)
+    outs = []
+    for f in range(BT):
+        b = f // T
+        idx = list(range(G)) + list(range(G + b * T, G + (b + 1) * T)) + [G + BT + f]
+        kk = torch.cat([k[f], ka[idx]]); vv = torch.cat([v[f], va[idx]])
+        aff = torch.einsum("qhc,khc->qkh", q[f] / 8.0, kk).softmax(dim=1)
+        outs.append(torch.einsum("qkh,khc->qhc", aff, vv).reshape(N0, D))
+    return torch.stack(outs).reshape(BT * N0, D)
+
+
+@pytest.mark.parametrize("T,N0,H", [(8, 197, 12), (16, 197, 12), (16, 257, 16), (3, 50, 2)])
+def test_attention(cuda, T, N0, H):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(T * N0)
+    B, G = 2, 8
+    D = H * 64
+    qkv = torch.randn(B * T * N0, 3 * D, device=cuda, generator=g).bfloat16()
+    kv_aux = torch.randn(G + 2 * B * T, 2 * D, device=cuda, generator=g).bfloat16()
+    out = torch.zeros(B * T * N0, D, device=cuda, dtype=torch.bfloat16)
+    ops.attention(qkv, kv_aux, out, B=B, T=T, N0=N0, G=G, H=H)
+    ref = _attention_ref(qkv, kv_aux, B, T, N0, G, H)
+    assert _rel(out.float(), ref) < 1.5e-2   # P is rounded to bf16 before PV
+
+
+def test_attention_cls_only(cuda):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, T, N0, G, H = 2, 8, 197, 8, 12
+    D = H * 64
+    qkv = torch.randn(B * T * N0, 3 * D, device=cuda, generator=g).bfloat16()
+    kv_aux = torch.randn(G + 2 * B * T, 2 * D, device=cuda, generator=g).bfloat16()
+    out = torch.zeros(B * T * N0, D, device=cuda, dtype=torch.bfloat16)
+    ops.attention(qkv, kv_aux, out, B=B, T=T, N0=N0, G=G, H=H, n_q=1)
+    ref = _attention_ref(qkv, kv_aux, B, T, N0, G, H).view(B * T, N0, D)
+    o = out.float().view(B * T, N0, D)
+    assert _rel(o[:, 0], ref[:, 0]) < 1.5e-2
+    assert (o[:, 1:] == 0).all()
+
+
+@pytest.mark.parametrize("n_kv", [1, 5])
+def test_head(cuda, n_kv):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(13)
+    B, T, E, D, n_cls = 5, 8, 512, 768, 3
+    ff = torch.randn(B * T, E, device=cuda, generator=g); st = torch.randn(B * T, D, device=cuda, generator=g)
+    txt = torch.randn(n_cls * n_kv, E, device=cuda, generator=g)
+    txt = txt / txt.norm(dim=-1, keepdim=True)
+    offs = torch.arange(0, n_cls * n_kv + 1, n_kv, device=cuda, dtype=torch.int32)
+    vf = torch.empty(B, E, device=cuda); so = torch.empty(B, D, device=cuda); lg = torch.empty(B, n_cls, device=cuda)
+    scale = math.exp(math.log(1 / 0.07))
+    ops.head(ff, st, txt, offs, vf, so, lg, B=B, T=T, scale=scale, logit_bias=-0.5)
+    v = ff.view(B, T, E).mean(1)
+    vh = v / v.norm(dim=-1, keepdim=True)
+    ref = (scale * vh @ txt.t()).view(B, n_cls, n_kv).mean(-1) - 0.5
+    assert _rel(vf, v) < 1e-6 and _rel(so, st.view(B, T, D).mean(1)) < 1e-6
+    assert _rel(lg, ref) < 1e-5
