@@ -73,12 +73,13 @@ int layernorm(const float* x, long long in_row_stride, const float* w, const flo
   if (rows == 0) return GAVA_OK;
   if ((in_row_stride & 3) || (out_row_stride & 3)) { set_error("layernorm: row strides must be multiples of 4"); return GAVA_ERR_ARG; }
   const unsigned grid = (unsigned)((rows + 7) / 8);
+#define GAVA_LN_CASE(V) \
+  case 128 * V: layernorm_kernel<V><<<grid, 256, 0, stream>>>(x, in_row_stride, w, b, out, out_row_stride, out_bf16, rows, eps); break;
   switch (D) {
-    case 512: layernorm_kernel<4><<<grid, 256, 0, stream>>>(x, in_row_stride, w, b, out, out_row_stride, out_bf16, rows, eps); break;
-    case 768: layernorm_kernel<6><<<grid, 256, 0, stream>>>(x, in_row_stride, w, b, out, out_row_stride, out_bf16, rows, eps); break;
-    case 1024: layernorm_kernel<8><<<grid, 256, 0, stream>>>(x, in_row_stride, w, b, out, out_row_stride, out_bf16, rows, eps); break;
-    default: set_error("layernorm: unsupported width D=%d (512/768/1024)", D); return GAVA_ERR_SHAPE;
+    GAVA_LN_CASE(1) GAVA_LN_CASE(2) GAVA_LN_CASE(3) GAVA_LN_CASE(4) GAVA_LN_CASE(6) GAVA_LN_CASE(8)
+    default: set_error("layernorm: unsupported width D=%d (128/256/384/512/768/1024)", D); return GAVA_ERR_SHAPE;
   }
+#undef GAVA_LN_CASE
   return check_launch("layernorm");
 }
 
@@ -224,11 +225,13 @@ int prompt_rows(const float* global_prompts, const float* local_prompts, const f
   const int BT = B * T, rows = G + 2 * BT;
   const unsigned grid = (unsigned)((rows + 7) / 8);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+#define GAVA_PR_CASE(V) \
+  case 128 * V: prompt_rows_kernel<V><<<grid, 256, 0, stream>>>(global_prompts, local_prompts, cls_proj_out, summary, ln_w, ln_b, o, G, BT, T, eps); break;
   switch (D) {
-    case 768: prompt_rows_kernel<6><<<grid, 256, 0, stream>>>(global_prompts, local_prompts, cls_proj_out, summary, ln_w, ln_b, o, G, BT, T, eps); break;
-    case 1024: prompt_rows_kernel<8><<<grid, 256, 0, stream>>>(global_prompts, local_prompts, cls_proj_out, summary, ln_w, ln_b, o, G, BT, T, eps); break;
+    GAVA_PR_CASE(1) GAVA_PR_CASE(2) GAVA_PR_CASE(3) GAVA_PR_CASE(4) GAVA_PR_CASE(6) GAVA_PR_CASE(8)
     default: set_error("prompt_rows: unsupported width D=%d", D); return GAVA_ERR_SHAPE;
   }
+#undef GAVA_PR_CASE
   return check_launch("prompt_rows");
 }
 

@@ -65,7 +65,7 @@ int gava_gemm_bf16_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, i
 /* LayerNorm over the last dim (fp32 statistics, eps inside the sqrt), row r read from
  * x + r * in_row_stride (elements, f32), written to out + r * out_row_stride as bf16 (out_bf16 != 0) or f32.
  * weight == NULL: no normalisation, plain copy/cast (used to gather the cls rows).  In-place (out == x, f32) is safe.
- * D must be a multiple of 128 and <= 1024.  Replaces LayerNorm.forward, VitaCLIP_vision_encoder_utils.py:22-28. */
+ * D in {128,256,384,512,768,1024}.  Replaces LayerNorm.forward, VitaCLIP_vision_encoder_utils.py:22-28. */
 int gava_layernorm_fwd(const float* x, int64_t in_row_stride, const float* weight, const float* bias, void* out,
                        int64_t out_row_stride, int32_t out_bf16, int64_t rows, int32_t D, float eps, void* stream);
 

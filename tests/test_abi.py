@@ -1,0 +1,39 @@
+"""CPU: the C-ABI shared library builds/loads here and exports exactly what include/gava_sm100.h declares.
+No compute call is made (no GPU in the build container)."""
+import ctypes
+import re
+
+from tests.util import ROOT
+
+
+def declared_symbols():
+    text = open(f"{ROOT}/include/gava_sm100.h").read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(gava_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    from gava_clip_b200 import _lib
+    lib = _lib.load()
+    syms = declared_symbols()
+    assert len(syms) >= 11
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/gava_sm100.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in gava_clip_b200/_lib.py"
+    assert sorted(_lib.SIGNATURES) == syms
+    assert lib.gava_version() == 1
+
+
+def test_epilogue_struct_layout():
+    from gava_clip_b200._lib import GemmEpilogue
+    # int32 mode (+4 pad), 2 ptr, i64, ptr, i64, 4 x i32, 2 ptr  -> 80 bytes on LP64
+    assert ctypes.sizeof(GemmEpilogue) == 80
+    assert GemmEpilogue.out.offset == 32 and GemmEpilogue.group.offset == 48 and GemmEpilogue.pos.offset == 64
+
+
+def test_no_oracle_in_product():
+    """The product package must never import the oracle (it is test infrastructure)."""
+    import pathlib
+    for p in pathlib.Path(f"{ROOT}/gava_clip_b200").rglob("*.py"):
+        src = p.read_text()
+        assert "import oracle" not in src and "from oracle" not in src, p

@@ -1,0 +1,108 @@
+"""B200: end-to-end parity of the drop-in VitaCLIP (sm_100a kernels, bf16 tensor-core inputs, fp32 accumulate and
+fp32 residual stream) against outputs of the fp32 REFERENCE (tests/golden/*.pt) and against the CPU oracle.
+
+Tolerance (BASELINE.json north_star): logits within 2e-2 relative (max|l - l_ref| / max|l_ref|) on the bf16 path, identical
+top-1 on every sample whose reference margin is decisive.
+"""
+import pytest
+import torch
+
+from tests.util import build_model, fx, load_golden, rel_err, rel_l2, top1_matches
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-2
+
+
+def _run(name, cuda, **fw):
+    model, kw, B = build_model(name, device=cuda)
+    inp = {k: v.to(cuda) for k, v in fx.make_inputs(name).items()}
+    with torch.no_grad():
+        out = model(inp["video"], memory=inp.get("memory"), video_nte=inp.get("video_nte"), **fw)
+    torch.cuda.synchronize()
+    return model, out
+
+
+@pytest.mark.parametrize("name", ["tiny", "b16_t8", "b16_t16_k400", "l14_t16", "kapt_b16_t8"])
+def test_logits_match_reference(cuda, name):
+    g = load_golden(name)
+    model, (logits, logits_mt, logits_vm) = _run(name, cuda)
+    assert logits.shape == g["logits"].shape and logits.dtype == torch.float32
+    err = rel_err(logits, g["logits"])
+    ok, n_sub = top1_matches(logits, g["logits"], TOL)
+    print(f"\n[{name}] logits rel err {err:.3e}; video_features rel-L2 {rel_l2(model.video_features, g['video_features']):.3e}; "
+          f"summary rel-L2 {rel_l2(model.summary, g['summary']):.3e}; sub-margin samples {n_sub}")
+    assert err < TOL
+    assert ok, "top-1 differs on a sample with a decisive reference margin"
+    assert rel_l2(model.video_features, g["video_features"]) < TOL
+    assert rel_l2(model.summary, g["summary"]) < TOL
+    assert rel_err(model.text_features, g["text_features"]) < 1e-3          # fp32 text tower
+    if g["logits_mt"] is not None:
+        assert rel_err(logits_mt, g["logits_mt"]) < 1e-3
+    else:
+        assert logits_mt is None
+    if g["logits_vm"] is not None:
+        assert rel_err(logits_vm, g["logits_vm"]) < TOL
+    else:
+        assert logits_vm is None
+
+
+@pytest.mark.parametrize("name", ["tiny", "kapt_b16_t8"])
+def test_desc_wise(cuda, name):
+    g = load_golden(name)
+    model, (logits, _, _) = _run(name, cuda, desc_wise=True)
+    assert isinstance(logits, list) and len(logits) == len(g["desc_wise"])
+    for a, b in zip(logits, g["desc_wise"]):
+        assert a.shape == b.shape and rel_err(a, b) < TOL
+    assert rel_err(model.text_features, g["desc_text_features"]) < 1e-3
+
+
+def test_visual_tower_standalone_and_layer_taps(cuda):
+    """CLIPVisionEncoder used directly (evaluation/iwa.py:62, utils/prepare_embedding.py:382)."""
+    g = load_golden("b16_t8")
+    model, kw, B = build_model("b16_t8", device=cuda)
+    video = fx.make_inputs("b16_t8")["video"].to(cuda)
+    with torch.no_grad():
+        cls_x, summary = model.visual(video)
+    assert cls_x.shape == (B, 512) and summary.shape == (B, 768)
+    assert rel_l2(cls_x, g["video_features"]) < TOL and rel_l2(summary, g["summary"]) < TOL
+
+
+def test_zeroshot_branch(cuda, tmp_path):
+    """zero-shot evaluation branch with preloaded text features (VitaCLIP_model.py:296-306)."""
+    from gava_clip_b200 import VitaCLIP
+    from oracle import vita_oracle as vo
+    g = load_golden("b16_t8")
+    tf = torch.randn(7, 512, generator=torch.Generator().manual_seed(3))
+    torch.save({"text_features": tf}, tmp_path / "tf.pth")
+    kw, B = fx.case_kwargs("b16_t8")
+    kw.update(use_text_prompt_learning=False, zeroshot_evaluation=True, zeroshot_text_features_path=str(tmp_path / "tf.pth"))
+    model = VitaCLIP(**kw)
+    fx.fill_params_(model.state_dict().items(), seed=0)
+    model = model.eval().to(cuda)
+    with torch.no_grad():
+        logits, _, _ = model(fx.make_inputs("b16_t8")["video"].to(cuda))
+    ref = vo.zeroshot_head(g["video_features"], tf, torch.tensor(2.65926))
+    assert rel_err(logits, ref) < TOL
+
+
+def test_batch_sharding_equivalence(cuda):
+    """Clips are independent: running a batch in two shards gives the same logits as one call."""
+    model, kw, B = build_model("tiny", device=cuda)
+    g = torch.Generator().manual_seed(5)
+    video = torch.randn(6, 3, 3, 64, 64, generator=g).to(cuda)
+    with torch.no_grad():
+        full = model(video)[0].clone()
+        parts = torch.cat([model(video[:2])[0].clone(), model(video[2:])[0].clone()])
+    assert torch.allclose(full, parts, atol=1e-6, rtol=0)
+
+
+def test_repack_after_param_update(cuda):
+    model, kw, B = build_model("tiny", device=cuda)
+    video = fx.make_inputs("tiny")["video"].to(cuda)
+    with torch.no_grad():
+        a = model(video)[0].clone()
+        model.visual.global_prompts.add_(0.5)
+        model.logit_scale.add_(0.3)
+        b = model(video)[0].clone()
+    assert not torch.allclose(a, b)

@@ -1,0 +1,63 @@
+"""CPU: pin the oracle (oracle/vita_oracle.py) against outputs of the REFERENCE ITSELF (tests/golden/*.pt, produced
+by oracle/make_golden.py from /root/reference in the build container), and check the drop-in's host-side contract
+(state_dict layout, frozen set, tokenisation) against what the reference reported."""
+import pytest
+import torch
+
+from tests.util import build_model, fx, load_golden, rel_err
+
+from oracle import vita_oracle as vo
+
+FAST = ["tiny", "b16_t8", "kapt_b16_t8"]
+SLOW = ["l14_t16", "b16_t16_k400"]
+
+
+@pytest.mark.parametrize("name", FAST + SLOW)
+def test_state_dict_contract(name):
+    g = load_golden(name)
+    model, kw, B = build_model(name)
+    sd = model.state_dict()
+    assert {k: list(v.shape) for k, v in sd.items()} == g["state_dict_shapes"]
+    assert list(sd.keys()) == list(g["state_dict_shapes"].keys())          # same order, too
+    assert sorted(n for n, p in model.named_parameters() if p.requires_grad) == g["requires_grad"]
+    assert len(model.tokenized_prompts) == len(g["tokenized_prompts"])
+    for a, b in zip(model.tokenized_prompts, g["tokenized_prompts"]):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("name", FAST + SLOW)
+def test_oracle_matches_reference(name):
+    g = load_golden(name)
+    model, kw, B = build_model(name)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    inp = fx.make_inputs(name)
+    kapt = bool(kw.get("text_prompt_init"))
+    cntn = model.prompt_learner.context_prompt_learner.cntn_embeds if kapt else None
+    taps = {}
+    out = vo.vita_forward(sd, inp["video"], model.tokenized_prompts, num_frames=kw["num_frames"],
+                          num_heads=kw.get("num_heads", 12), num_layers=kw.get("num_layers", 12),
+                          text_heads=kw.get("text_transformer_heads", 8), text_layers=kw.get("text_transformer_layers", 12),
+                          n_ctx=8, kapt=kapt, cntn_embeds=cntn, taps=taps)
+    # same algorithm, same fp32 weights, same CPU: only summation-order noise is allowed
+    assert rel_err(out["logits"], g["logits"]) < 1e-4
+    assert rel_err(out["video_features"], g["video_features"]) < 1e-4
+    assert rel_err(out["summary"], g["summary"]) < 1e-4
+    assert rel_err(out["text_features"], g["text_features"]) < 1e-4
+    assert torch.equal(out["logits"].argmax(-1), g["logits"].argmax(-1))
+    if g["layer_cls"] is not None:
+        assert rel_err(torch.stack(taps["layer_cls"]), g["layer_cls"]) < 1e-4
+        assert rel_err(torch.stack(taps["layer_summary"]).flatten(1, 2), g["layer_summary"].flatten(1, 2)) < 1e-4
+    if g["logits_mt"] is not None:
+        mt = vo.memory_head(sd, out["text_features"], inp["memory"], kw["num_classes"])
+        assert rel_err(mt, g["logits_mt"]) < 1e-4
+
+
+def test_oracle_zeroshot_head_consistent():
+    """zero-shot branch == prompt branch when every class has one description (VitaCLIP_model.py:296-306)."""
+    g = load_golden("tiny")
+    v = g["video_features"]
+    ls = torch.tensor(2.65926)
+    tf = torch.randn(3, v.shape[1], generator=torch.Generator().manual_seed(0))
+    a = vo.zeroshot_head(v, tf, ls)
+    b, _ = vo.logit_head(v, [t[None] for t in tf], ls)
+    assert torch.allclose(a, b, atol=1e-6)
