@@ -18,7 +18,17 @@ from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_RES
 Tensor = torch.Tensor
 
 
+_launches = 0
+
+
+def launch_count() -> int:
+    """number of sm_100a kernel launches issued through this module so far (bench.py's `gpu_launches`)."""
+    return _launches
+
+
 def _stream() -> int:
+    global _launches
+    _launches += 1          # every wrapper below fetches the stream exactly once, right before its one launch
     return torch.cuda.current_stream().cuda_stream
 
 

@@ -66,7 +66,7 @@ def run_case(ref_model, name: str, tokens: dict) -> None:
     finally:
         if ctx:
             ctx.__exit__()
-    fx.fill_params_(model.state_dict().items(), seed=0)      # state_dict tensors alias the parameters
+    fx.fill_params_(model.state_dict().items(), seed=fx.case_seed(name))      # state_dict tensors alias the parameters
     # the reference snapshots the prefix/suffix token embeddings at construction (text_encoder.py:283-300), i.e.
     # from the backbone loaded BEFORE the prompt learner is built; emulate that order for the fixture weights.
     pl = model.prompt_learner

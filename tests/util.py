@@ -24,7 +24,7 @@ def build_model(name, device="cpu"):
     ctx = fx.kapt_cwd() if kw.get("text_prompt_init") else contextlib.nullcontext()
     with ctx:
         model = VitaCLIP(**kw)
-    fx.fill_params_(model.state_dict().items(), seed=0)
+    fx.fill_params_(model.state_dict().items(), seed=fx.case_seed(name))
     model.prompt_learner.refresh_token_embeddings(model.textual)   # same order as make_golden.py: weights, then snapshot
     model.eval()
     return model.to(device), kw, B
