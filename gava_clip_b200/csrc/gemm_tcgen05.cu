@@ -3,7 +3,7 @@
 //   A, W : bf16, K-major (row-major [rows, K]); moved by TMA (128-byte swizzle) into a 4..6 stage smem ring
 //   D    : fp32 accumulators in TMEM, 2 accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1
 //   roles: warp 0 = TMA producer (1 lane), warp 1 = MMA issuer (1 lane), warp 2 = TMEM allocator,
-//          warps 4..7 = epilogue (one TMEM lane == one output row per thread)
+//          warps 4..11 = epilogue (TMEM lane == output row; transposed through smem for coalesced global access)
 //
 // Replaces the nn.Linear / Conv2d(k=s=patch) library calls of the reference hot path:
 //   q/k/v/out_proj  training/VitaCLIP_vision_encoder_utils.py:66,79
@@ -21,7 +21,9 @@ namespace gava {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = one 128-byte swizzle atom
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int EPI_WARPS = 8;                       // 2 warps per TMEM lane quarter, each takes half of the N columns
+constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4..: epilogue
+constexpr int EPI_STAGE_BYTES = 4096;               // per-warp transpose buffer
 
 template <int BN>
 struct GemmCfg {
@@ -30,7 +32,7 @@ struct GemmCfg {
   static constexpr int kBytesB = BN * BK * 2;
   static constexpr int kBytesStage = kBytesA + kBytesB;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
-  static constexpr int kSmemBytes = kStages * kBytesStage + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kBytesStage + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct GemmArgs {
@@ -46,26 +48,31 @@ struct GemmArgs {
   int T;
 };
 
+// ---- epilogue: TMEM -> registers (one row per thread) -> swizzled smem staging -> transposed, coalesced global access.
+// After tcgen05.ld a thread owns 32 consecutive columns of ONE row, so direct global stores would touch 32 different
+// rows per warp instruction (measured: l1tex 77 % busy, tensor pipe 64 %).  Each warp therefore transposes its
+// 32x32 block through a private 4 KB staging buffer (XOR-swizzled 16-byte chunks: conflict-free both ways) so that
+// every warp-level global load/store covers whole 64/128-byte row segments.
 template <int MODE>
-__device__ __forceinline__ void epilogue_store(const GemmArgs& p, int row, int col0, uint32_t (&v)[32]) {
-  float acc[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-  if (p.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 b = __ldg(b4 + j);
-      acc[4 * j + 0] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
-    }
-  }
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage, int row0, int col0,
+                                               uint32_t (&v)[32], const float4 (&resid)[8], int lane) {
   if constexpr (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16) {
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+    if (p.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(b4 + j);
+        acc[4 * j + 0] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
+      }
+    }
     if constexpr (MODE == EPI_BIAS_GELU_BF16) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = quick_gelu(acc[j]);
     }
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0;
-    uint4* o4 = reinterpret_cast<uint4*>(o);
+    // stage as bf16: row pitch 64 B (4 chunks of 16 B), chunk' = chunk ^ ((row >> 1) & 3)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint4 w;
@@ -73,36 +80,52 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& p, int row, int c
       w.y = pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]);
       w.z = pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]);
       w.w = pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]);
-      o4[j] = w;
+      *reinterpret_cast<uint4*>(stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = w;
     }
-  } else if constexpr (MODE == EPI_BIAS_RESID_F32) {
-    const float4* r4 = reinterpret_cast<const float4*>(p.resid + (long long)row * p.ldr + col0);
-    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0);
-    float4 r[8];
+    __syncwarp();
+    const int c = lane & 3;
+    __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + col0 + 8 * c;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = r4[j];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 w = make_float4(acc[4 * j] + r[j].x, acc[4 * j + 1] + r[j].y, acc[4 * j + 2] + r[j].z,
-                             acc[4 * j + 3] + r[j].w);
-      o4[j] = w;
+    for (int i = 0; i < 4; ++i) {
+      const int r = 8 * i + (lane >> 2);
+      const uint4 w = *reinterpret_cast<const uint4*>(stage + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+      if (row0 + r < p.M) *reinterpret_cast<uint4*>(obase + (long long)(row0 + r) * p.ldo) = w;
     }
-  } else if constexpr (MODE == EPI_BIAS_F32) {
-    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0);
+    __syncwarp();
+  } else {
+    // stage raw fp32 accumulators: row pitch 128 B (8 chunks of 16 B), chunk' = chunk ^ (row & 7)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-  } else {  // EPI_PATCH_F32: + pos_embed[1+n] + time_embed[t], scatter to the frame's token slot
-    const int grp = row / p.group, n = row - grp * p.group;
-    const long long orow = (long long)grp * p.group_stride + n + p.row_offset;
-    const float4* pe = reinterpret_cast<const float4*>(p.pos + (long long)(n + 1) * p.N + col0);
-    const float4* te = reinterpret_cast<const float4*>(p.time_embed + (long long)(grp % p.T) * p.N + col0);
-    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col0);
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<uint4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+          make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+    const int c = lane & 7;
+    const int col = col0 + 4 * c;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float4 a = __ldg(pe + j), b = __ldg(te + j);
-      o4[j] = make_float4(acc[4 * j] + a.x + b.x, acc[4 * j + 1] + a.y + b.y, acc[4 * j + 2] + a.z + b.z,
-                          acc[4 * j + 3] + a.w + b.w);
+    for (int i = 0; i < 8; ++i) {
+      const int r = 4 * i + (lane >> 3);
+      const int grow = row0 + r;
+      float4 a = *reinterpret_cast<const float4*>(stage + r * 128 + ((c ^ (r & 7)) << 4));
+      a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+      if (grow < p.M) {
+        if constexpr (MODE == EPI_BIAS_RESID_F32) {
+          a.x += resid[i].x; a.y += resid[i].y; a.z += resid[i].z; a.w += resid[i].w;
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)grow * p.ldo + col) = a;
+        } else if constexpr (MODE == EPI_BIAS_F32) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)grow * p.ldo + col) = a;
+        } else {  // EPI_PATCH_F32: + pos_embed[1+n] + time_embed[t], scatter to the frame's token slot
+          const int grp = grow / p.group, n = grow - grp * p.group;
+          const long long orow = (long long)grp * p.group_stride + n + p.row_offset;
+          const float4 pe = __ldg(reinterpret_cast<const float4*>(p.pos + (long long)(n + 1) * p.N + col));
+          const float4 te = __ldg(reinterpret_cast<const float4*>(p.time_embed + (long long)(grp % p.T) * p.N + col));
+          a.x += pe.x + te.x; a.y += pe.y + te.y; a.z += pe.z + te.z; a.w += pe.w + te.w;
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + orow * p.ldo + col) = a;
+        }
+      }
     }
+    __syncwarp();
   }
 }
 
@@ -116,7 +139,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kBytesA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kBytesStage);
+  uint8_t* smem_epi = smem + kStages * Cfg::kBytesStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_WARPS * EPI_STAGE_BYTES);
   uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;           // [kStages]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * kStages;       // [2]        MMA -> epilogue
@@ -141,7 +165,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], 32 * EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -200,21 +224,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     __syncwarp();
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
+    const int ew = warp - 4;
+    const int quarter = ew & 3;   // == warp % 4: the TMEM lane quarter this warp may access
+    const int half = ew >> 2;     // which half of the tile's columns
+    constexpr int kChunksPerWarp = (BN / 32) / (EPI_WARPS / 4);
+    uint8_t* stage = smem_epi + ew * EPI_STAGE_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
-      const int row = m_blk * BM + ew * 32 + lane;
+      const int row0 = m_blk * BM + quarter * 32;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+        const int c = half * kChunksPerWarp + cc;
+        const int col0 = n_blk * BN + c * 32;
+        float4 resid[8];
+        if constexpr (MODE == EPI_BIAS_RESID_F32) {  // coalesced residual loads, in flight while TMEM is read
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int grow = row0 + 4 * i + (lane >> 3);
+            resid[i] = (grow < p.M) ? *reinterpret_cast<const float4*>(p.resid + (long long)grow * p.ldr + col0 + 4 * (lane & 7))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         uint32_t v[32];
         tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
         tmem_ld_wait();
-        if (row < p.M) epilogue_store<MODE>(p, row, n_blk * BN + c * 32, v);
+        epilogue_chunk<MODE>(p, stage, row0, col0, v, resid, lane);
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
