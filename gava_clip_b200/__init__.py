@@ -4,7 +4,8 @@ Drop-in for the reference's `training/VitaCLIP_model.py` API:
     from gava_clip_b200 import VitaCLIP, CLIPVisionEncoder
 """
 from .model import VitaCLIP  # noqa: F401
+from .streaming import ClipStreamer  # noqa: F401
 from .text_encoder import CLIPTextEncoder, TextPromptLearner, tokenize  # noqa: F401
 from .vision_encoder import CLIPVisionEncoder  # noqa: F401
 
-__all__ = ["VitaCLIP", "CLIPVisionEncoder", "CLIPTextEncoder", "TextPromptLearner", "tokenize"]
+__all__ = ["VitaCLIP", "ClipStreamer", "CLIPVisionEncoder", "CLIPTextEncoder", "TextPromptLearner", "tokenize"]

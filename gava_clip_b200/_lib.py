@@ -9,7 +9,7 @@ import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "lib" / "libgava_sm100.so"
+LIB_PATH = Path(os.environ["GAVA_LIB_PATH"]) if os.environ.get("GAVA_LIB_PATH") else _PKG / "lib" / "libgava_sm100.so"
 
 EPI_BIAS_BF16 = 0
 EPI_BIAS_GELU_BF16 = 1

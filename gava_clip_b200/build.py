@@ -41,6 +41,20 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def build_variant(name: str, defines) -> Path:
+    """Experiment build (tools/gemm_bench.py): same sources with extra -D flags -> lib/variants/libgava_<name>.so."""
+    vdir = LIBDIR / "variants"
+    vdir.mkdir(parents=True, exist_ok=True)
+    out = vdir / f"libgava_{name}.so"
+    cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")], *[f"-D{d}" for d in defines], "-shared",
+           *[str(CSRC / s) for s in SOURCES], "-o", str(out), "-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError(f"variant build {name} failed")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     LIBDIR.mkdir(exist_ok=True)
     digest = _digest()

@@ -15,6 +15,11 @@
 #include "kernels.h"
 
 #include <mutex>
+#include <stdlib.h>
+
+#ifndef GAVA_GEMM_DEBUG
+#define GAVA_GEMM_DEBUG 0
+#endif
 
 namespace gava {
 
@@ -129,6 +134,33 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
   }
 }
 
+// One warp's share of one accumulator tile: NCH chunks of 32 columns starting at column `col_base`, rows row0..row0+31.
+template <int MODE, int NCH>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage, uint64_t* tmem_full_bar,
+                                              uint32_t full_phase, uint32_t t_addr, int row0, int col_base, int lane) {
+  mbar_wait(tmem_full_bar, full_phase);
+  tc_fence_after();
+#pragma unroll 1
+  for (int cc = 0; cc < NCH; ++cc) {
+    const int col0 = col_base + cc * 32;
+    float4 resid[8];
+    if constexpr (MODE == EPI_BIAS_RESID_F32) {  // coalesced residual loads, in flight while TMEM is read
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int grow = row0 + 4 * i + (lane >> 3);
+        resid[i] = (grow < p.M) ? *reinterpret_cast<const float4*>(p.resid + (long long)grow * p.ldr + col0 + 4 * (lane & 7))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    uint32_t v[32];
+    tmem_ld_32x32(t_addr + (uint32_t)(cc * 32), v);
+    tmem_ld_wait();
+#if GAVA_GEMM_DEBUG != 1
+    epilogue_chunk<MODE>(p, stage, row0, col0, v, resid, lane);
+#endif
+  }
+}
+
 template <int BN, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -234,27 +266,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
       const int row0 = m_blk * BM + quarter * 32;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int cc = 0; cc < kChunksPerWarp; ++cc) {
-        const int c = half * kChunksPerWarp + cc;
-        const int col0 = n_blk * BN + c * 32;
-        float4 resid[8];
-        if constexpr (MODE == EPI_BIAS_RESID_F32) {  // coalesced residual loads, in flight while TMEM is read
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int grow = row0 + 4 * i + (lane >> 3);
-            resid[i] = (grow < p.M) ? *reinterpret_cast<const float4*>(p.resid + (long long)grow * p.ldr + col0 + 4 * (lane & 7))
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        uint32_t v[32];
-        tmem_ld_32x32(t_row + (uint32_t)(c * 32), v);
-        tmem_ld_wait();
-        epilogue_chunk<MODE>(p, stage, row0, col0, v, resid, lane);
-      }
+      const int col_base = n_blk * BN + half * kChunksPerWarp * 32;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * kChunksPerWarp * 32);
+      epilogue_tile<MODE, kChunksPerWarp>(p, stage, &tmem_full[acc], acc_phase, t_addr, row0, col_base, lane);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -266,6 +280,154 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ----------------------------------------------------------------------------- CTA-pair (cta_group::2) kernel
+// One 256x256 output tile per 2-CTA cluster: CTA r loads A rows [m0 + 128 r, +128) and W rows [n0 + 128 r, +128)
+// (half of the B operand each), the leader CTA issues tcgen05.mma.cta_group::2 (M = 256) and each CTA drains the
+// 128 accumulator rows that live in its own TMEM.  Halving the per-SM B traffic turns the 4-stage ring into a 6-stage
+// ring in the same shared memory (more TMA latency cover) and halves the operand read bandwidth per SM.
+struct Gemm2Cfg {
+  static constexpr int BN = 256;
+  static constexpr int kStages = 6;
+  static constexpr int kBytesA = BM * BK * 2;        // 128 rows of A
+  static constexpr int kBytesB = (BN / 2) * BK * 2;  // 128 rows of W (this CTA's half of N)
+  static constexpr int kBytesStage = kBytesA + kBytesB;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kBytesStage + EPI_WARPS * EPI_STAGE_BYTES + 1024 + 256;
+};
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const GemmArgs p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * Cfg::kBytesA;
+  uint8_t* smem_epi = smem + kStages * Cfg::kBytesStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_WARPS * EPI_STAGE_BYTES);
+  uint64_t* full_bar = bars;                      // [kStages]  TMA (both CTAs) -> MMA; only the leader's copy is used
+  uint64_t* empty_bar = bars + kStages;           // [kStages]  MMA -> TMA; multicast to both CTAs
+  uint64_t* tmem_full = bars + 2 * kStages;       // [2]        MMA -> epilogue; multicast to both CTAs
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;  // [2]        epilogue (both CTAs) -> MMA; only the leader's copy is used
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int num_n = p.N / BN;
+  const int num_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const int num_tiles = num_m * num_n;
+  const int num_kb = p.K / BK;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 2 * EPI_WARPS);  // one arrive per epilogue warp of both CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_base_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();  // peer barriers initialised, both TMEM allocations done
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+        const int row_a = m_blk * 2 * BM + (int)rank * BM;
+        const int row_b = n_blk * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+#if GAVA_GEMM_DEBUG == 2   // experiment: no operand loads (mainloop on stale smem)
+          if (leader) mbar_arrive(&full_bar[stage]);
+#else
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kBytesStage);  // bytes of BOTH CTAs
+          tma_load_2d_2sm(smem_a + stage * Cfg::kBytesA, &tmap_a, &full_bar[stage], kb * BK, row_a);
+          tma_load_2d_2sm(smem_b + stage * Cfg::kBytesB, &tmap_b, &full_bar[stage], kb * BK, row_b);
+#endif
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kBytesA));
+          const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBytesB));
+#if GAVA_GEMM_DEBUG != 3   // experiment 3: no MMAs (TMA + epilogue only)
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_ss_2sm(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+#endif
+          umma_commit_2sm(&empty_bar[stage], 0b11);  // slot free in both CTAs
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit_2sm(&tmem_full[acc], 0b11);  // accumulator halves ready in both CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own TMEM half) =====================
+    const int ew = warp - 4;
+    const int quarter = ew & 3;
+    const int half = ew >> 2;
+    constexpr int kChunksPerWarp = (BN / 32) / (EPI_WARPS / 4);
+    uint8_t* stage = smem_epi + ew * EPI_STAGE_BYTES;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
+      const int row0 = m_blk * 2 * BM + (int)rank * BM + quarter * 32;
+      const int col_base = n_blk * BN + half * kChunksPerWarp * 32;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * kChunksPerWarp * 32);
+      epilogue_tile<MODE, kChunksPerWarp>(p, stage, &tmem_full[acc], acc_phase, t_addr, row0, col_base, lane);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // tell the leader this warp drained its part
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody exits (or frees TMEM) while the peer may still touch this CTA's smem/TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -333,6 +495,35 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
   return check_launch("gemm_tcgen05");
 }
 
+template <int MODE>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg;
+  static bool attr_set = false;
+  auto kern = gemm2_tcgen05_kernel<MODE>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(gemm2): %s", cudaGetErrorString(e)); return (int)e; }
+    attr_set = true;
+  }
+  const int tiles = ((args.M + 2 * BM - 1) / (2 * BM)) * (args.N / Cfg::BN);
+  const int max_clusters = num_sms() / 2;
+  const int clusters = tiles < max_clusters ? tiles : max_clusters;
+  kern<<<2 * clusters, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, args);
+  return check_launch("gemm2_tcgen05");
+}
+
+static int dispatch_mode2(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t s) {
+  switch (mode) {
+    case EPI_BIAS_BF16: return launch_gemm2<EPI_BIAS_BF16>(ta, tb, a, s);
+    case EPI_BIAS_GELU_BF16: return launch_gemm2<EPI_BIAS_GELU_BF16>(ta, tb, a, s);
+    case EPI_BIAS_RESID_F32: return launch_gemm2<EPI_BIAS_RESID_F32>(ta, tb, a, s);
+    case EPI_BIAS_F32: return launch_gemm2<EPI_BIAS_F32>(ta, tb, a, s);
+    case EPI_PATCH_F32: return launch_gemm2<EPI_PATCH_F32>(ta, tb, a, s);
+  }
+  set_error("gemm: unknown epilogue mode %d", mode);
+  return GAVA_ERR_ARG;
+}
+
 template <int BN>
 static int dispatch_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t s) {
   switch (mode) {
@@ -359,10 +550,12 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
     return GAVA_ERR_ARG;
   }
   const int bn = (N % 256 == 0) ? 256 : 128;
+  static const bool use_pair = [] { const char* e = getenv("GAVA_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+  const bool pair = use_pair && bn == 256;   // CTA-pair kernel for every N % 256 == 0 shape
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16(&ta, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tb, W, N, K, ldw, bn);
+  rc = make_tmap_bf16(&tb, W, N, K, ldw, pair ? 128 : bn);
   if (rc) return rc;
   GemmArgs a;
   a.M = (int)M; a.N = (int)N; a.K = (int)K;
@@ -370,6 +563,7 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
   a.out = epi->out; a.ldo = epi->ldo;
   a.group = epi->group; a.group_stride = epi->group_stride; a.row_offset = epi->row_offset;
   a.pos = epi->pos; a.time_embed = epi->time_embed; a.T = epi->T;
+  if (pair) return dispatch_mode2(epi->mode, ta, tb, a, stream);
   return bn == 256 ? dispatch_mode<256>(epi->mode, ta, tb, a, stream) : dispatch_mode<128>(epi->mode, ta, tb, a, stream);
 }
 

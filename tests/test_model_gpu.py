@@ -106,3 +106,19 @@ def test_repack_after_param_update(cuda):
         model.logit_scale.add_(0.3)
         b = model(video)[0].clone()
     assert not torch.allclose(a, b)
+
+
+def test_clip_streamer_matches_direct_calls(cuda):
+    """Pipelined H2D/forward/D2H (ClipStreamer) returns exactly what batch-by-batch calls return."""
+    from gava_clip_b200 import ClipStreamer
+    model, kw, B = build_model("tiny", device=cuda)
+    g = torch.Generator().manual_seed(11)
+    batches = [torch.randn(4, 3, 3, 64, 64, generator=g).pin_memory() for _ in range(5)]
+    with torch.no_grad():
+        direct = [model(b.to(cuda))[0].cpu().clone() for b in batches]
+    st = ClipStreamer(model)
+    streamed = [o.clone() for o in st.run(batches)]
+    assert len(streamed) == len(direct)
+    for a, b in zip(streamed, direct):
+        assert torch.equal(a, b)
+    assert st.h2d_bytes == sum(b.numel() * 4 for b in batches)
