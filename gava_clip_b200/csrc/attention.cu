@@ -12,6 +12,8 @@
 #include "common.cuh"
 #include "kernels.h"
 
+#include <stdlib.h>
+
 namespace gava {
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -213,6 +215,10 @@ int attention(const void* qkv, const void* kv_aux, void* out, int B, int T, int 
     set_error("attention: bad arguments");
     return GAVA_ERR_ARG;
   }
+  // tcgen05 path for every shape inside its specialisation (G = 8, T % 8 == 0, <= 256 keys); the mma.sync kernel
+  // below covers the remaining shapes (ViT-L/14: 282 keys, long clips).  GAVA_ATTN_TC=0 forces the latter (A/B tests).
+  static const bool use_tc = [] { const char* e = getenv("GAVA_ATTN_TC"); return !(e && e[0] == '0'); }();
+  if (use_tc && G == 8 && (T % 8) == 0 && ((N0 + 7) / 8 * 8 + 16 + T) <= 256) return attention_tc(qkv, kv_aux, out, B, T, N0, G, H, n_q, stream);
   AttnArgs a;
   a.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
   a.kv_aux = reinterpret_cast<const __nv_bfloat16*>(kv_aux);

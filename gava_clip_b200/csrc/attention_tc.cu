@@ -1,0 +1,362 @@
+// tcgen05 / TMEM / TMA version of the prompt-prefix attention core (same contract as attention.cu).
+//
+// Work item = (frame f, head h); a persistent CTA streams items through a 2-stage TMA ring:
+//   smem stage : Q tiles 0/1 [128 x 64], K [NK x 64], V [NK x 64]  (bf16, 128-byte swizzle, K/V rows gathered by
+//                several TMA boxes: live rows of the frame | 8 global prompts | T local prompts | summary token)
+//   TMEM       : S_w = Q_w K^T (128 x NK fp32) for the two query tiles w = 0,1 at columns 0 / 256;
+//                P_w (bf16, unnormalised probabilities) overwrites the first NK/2 columns of S_w;
+//                O_w = P_w V (128 x 64 fp32) lives at columns +128..+191 of the same region
+//   roles      : warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
+//                warps 4-7 softmax/output group of query tile 0, warps 8-11 of query tile 1 (thread == query row)
+// QK^T is an SS MMA (both operands K-major in smem); P V is a TS MMA (A = P from TMEM, B = V MN-major in smem).
+//
+// Restates Attention.forward core, training/VitaCLIP_vision_encoder_utils.py:71-77 (see attention.cu).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gava {
+
+constexpr int ATC_THREADS = 384;
+constexpr int ATC_QTILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
+
+struct AttnTcArgs {
+  __nv_bfloat16* out;
+  int T, N0, G, H, n_q, BT, D;
+  int kb_live;     // N0 rounded up to 8: smem row where the prompt rows start
+  int num_items;   // BT * H
+  uint32_t stage_tx_bytes;
+};
+
+// TS MMA: D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+// ---- softmax building blocks; a chunk is 32 keys of one query row (the thread's row)
+template <bool MASK>
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int j0, int v0, int v1, int v2, float mx) {
+  float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]), a2 = __uint_as_float(v[j + 2]), a3 = __uint_as_float(v[j + 3]);
+    if (MASK) {
+      const int k = j0 + j;
+      if (!(k < v0 || (k >= v1 && k <= v2))) a0 = -INFINITY;
+      if (!(k + 1 < v0 || (k + 1 >= v1 && k + 1 <= v2))) a1 = -INFINITY;
+      if (!(k + 2 < v0 || (k + 2 >= v1 && k + 2 <= v2))) a2 = -INFINITY;
+      if (!(k + 3 < v0 || (k + 3 >= v1 && k + 3 <= v2))) a3 = -INFINITY;
+    }
+    m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1); m2 = fmaxf(m2, a2); m3 = fmaxf(m3, a3);
+  }
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+template <bool MASK>
+__device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t (&pk)[16], int j0, int v0, int v1, int v2,
+                                           float c, float mc) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float p0 = exp2f(fmaf(__uint_as_float(v[j]), c, -mc));
+    float p1 = exp2f(fmaf(__uint_as_float(v[j + 1]), c, -mc));
+    if (MASK) {
+      const int k = j0 + j;
+      if (!(k < v0 || (k >= v1 && k <= v2))) p0 = 0.f;
+      if (!(k + 1 < v0 || (k + 1 >= v1 && k + 1 <= v2))) p1 = 0.f;
+    }
+    s0 += p0; s1 += p1;
+    pk[j >> 1] = pack_bf16x2(p0, p1);
+  }
+  return s0 + s1;
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// MN-major (rows = K index, 64 contiguous N elements per 128-byte row) smem descriptor, 128-byte swizzle:
+// SBO = 1024 B between 8-row groups along K; LBO = stride between 64-wide N atoms (single atom here).
+__device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(uint32_t M, uint32_t N) {  // B operand MN-major
+  return make_idesc_bf16(M, N) | (1u << 16);
+}
+
+template <int NK>
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                    const __grid_constant__ CUtensorMap tm_aux, const AttnTcArgs p) {
+  constexpr int kKVBytes = NK * 128;
+  constexpr int kStageBytes = 2 * ATC_QTILE_BYTES + 2 * kKVBytes;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kStageBytes);
+  uint64_t* kv_full = bars;         // [2] TMA -> MMA
+  uint64_t* kv_empty = bars + 2;    // [2] MMA -> TMA
+  uint64_t* s_full = bars + 4;      // [2] MMA -> softmax group w
+  uint64_t* p_ready = bars + 6;     // [2] softmax group w -> MMA
+  uint64_t* o_full = bars + 8;      // [2] MMA -> softmax group w
+  uint64_t* s_free = bars + 10;     // [2] softmax group w -> MMA (S/P/O region of tile w reusable)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_units = (p.n_q + 127) >> 7;  // query tiles per item (1 or 2)
+
+  // K/V rows that no TMA box covers (and nothing else) must still be finite: zero both stages once
+  for (int i = threadIdx.x; i < 2 * kStageBytes / 16; i += ATC_THREADS)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_kv);
+    tma_prefetch_desc(&tm_aux);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&s_free[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int f = item / p.H, h = item - f * p.H;
+        const int b = f / p.T;
+        uint8_t* sQ = smem + st * kStageBytes;
+        uint8_t* sK = sQ + 2 * ATC_QTILE_BYTES;
+        uint8_t* sV = sK + kKVBytes;
+        mbar_wait(&kv_empty[st], ph ^ 1u);
+        mbar_arrive_expect_tx(&kv_full[st], p.stage_tx_bytes);
+        const int xq = h * 64, xk = p.D + h * 64, xv = 2 * p.D + h * 64;
+        const int row = f * p.N0;
+        tma_load_2d(sQ, &tm_q, &kv_full[st], xq, row);
+        tma_load_2d(sQ + ATC_QTILE_BYTES, &tm_q, &kv_full[st], xq, row + 128);
+        tma_load_2d(sK, &tm_kv, &kv_full[st], xk, row);
+        tma_load_2d(sV, &tm_kv, &kv_full[st], xv, row);
+        int r = p.kb_live;                       // prompt rows, 8 per box
+        tma_load_2d(sK + r * 128, &tm_aux, &kv_full[st], h * 64, 0);
+        tma_load_2d(sV + r * 128, &tm_aux, &kv_full[st], p.D + h * 64, 0);
+        r += 8;
+        for (int i = 0; i < p.T; i += 8, r += 8) {
+          tma_load_2d(sK + r * 128, &tm_aux, &kv_full[st], h * 64, p.G + b * p.T + i);
+          tma_load_2d(sV + r * 128, &tm_aux, &kv_full[st], p.D + h * 64, p.G + b * p.T + i);
+        }
+        tma_load_2d(sK + r * 128, &tm_aux, &kv_full[st], h * 64, p.G + p.BT + f);
+        tma_load_2d(sV + r * 128, &tm_aux, &kv_full[st], p.D + h * 64, p.G + p.BT + f);
+        if (++st == 2) { st = 0; ph ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, NK);
+      constexpr uint32_t idesc_o = make_idesc_bf16_bmn(128, 64);
+      int st = 0;
+      uint32_t ph = 0, it_ph = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        uint8_t* sQ = smem + st * kStageBytes;
+        uint8_t* sK = sQ + 2 * ATC_QTILE_BYTES;
+        uint8_t* sV = sK + kKVBytes;
+        mbar_wait(&kv_full[st], ph);
+        tc_fence_after();
+        const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK));
+        for (int w = 0; w < n_units; ++w) {
+          mbar_wait(&s_free[w], it_ph ^ 1u);
+          tc_fence_after();
+          const uint64_t dq = make_sw128_kmajor_desc(smem_u32(sQ + w * ATC_QTILE_BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_ss(tmem_base + (uint32_t)(w * 256), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
+          umma_commit(&s_full[w]);
+        }
+        const uint64_t dv = make_sw128_mnmajor_desc(smem_u32(sV), (uint32_t)kKVBytes);
+        for (int w = 0; w < n_units; ++w) {
+          mbar_wait(&p_ready[w], it_ph);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < NK / 16; ++k)   // 16 keys per MMA: P advances 8 columns, V advances 16 rows (2048 B)
+            umma_bf16_ts(tmem_base + (uint32_t)(w * 256 + 128), tmem_base + (uint32_t)(w * 256 + 8 * k),
+                         dv + (uint64_t)(128 * k), idesc_o, (uint32_t)(k != 0));
+          umma_commit(&o_full[w]);
+        }
+        umma_commit(&kv_empty[st]);
+        it_ph ^= 1u;
+        if (++st == 2) { st = 0; ph ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================== softmax + output groups =====================
+    const int w = (warp - 4) >> 2;          // query tile of this group
+    const int quarter = warp & 3;           // TMEM lane quarter
+    const int row_in_tile = quarter * 32 + lane;
+    const uint32_t t_s = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(w * 256);
+    const float c = 0.125f * 1.4426950408889634f;  // dh^-0.5 * log2(e)
+    const int v0 = p.N0, v1 = p.kb_live, v2 = p.kb_live + 8 + p.T;   // valid keys: [0,v0) u [v1,v2]
+    uint32_t it_ph = 0;
+    if (w < n_units) {
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int f = item / p.H, h = item - f * p.H;
+        mbar_wait(&s_full[w], it_ph);
+        tc_fence_after();
+        // ---- pass 1: row maximum over the valid keys (TMEM load of chunk i+1 in flight while chunk i is reduced;
+        //      only chunks that contain masked keys pay for the mask)
+        float mx = -INFINITY;
+        {
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32(t_s, va);
+#pragma unroll
+          for (int ch = 0; ch < NK / 32; ++ch) {
+            tmem_ld_wait();
+            uint32_t (&cur)[32] = (ch & 1) ? vb : va;
+            uint32_t (&nxt)[32] = (ch & 1) ? va : vb;
+            if (ch + 1 < NK / 32) tmem_ld_32x32(t_s + (uint32_t)((ch + 1) * 32), nxt);
+            if (ch * 32 + 32 <= v0) mx = chunk_max<false>(cur, ch * 32, v0, v1, v2, mx);
+            else mx = chunk_max<true>(cur, ch * 32, v0, v1, v2, mx);
+          }
+        }
+        const float mc = mx * c;
+        // ---- pass 2: p = exp2(s*c - m*c); P (bf16) overwrites S in place (column j/2 <- keys j, j+1)
+        float sum = 0.f;
+        {
+          uint32_t va[32], vb[32];
+          tmem_ld_32x32(t_s, va);
+#pragma unroll
+          for (int ch = 0; ch < NK / 32; ++ch) {
+            tmem_ld_wait();
+            uint32_t (&cur)[32] = (ch & 1) ? vb : va;
+            uint32_t (&nxt)[32] = (ch & 1) ? va : vb;
+            if (ch + 1 < NK / 32) tmem_ld_32x32(t_s + (uint32_t)((ch + 1) * 32), nxt);
+            uint32_t pk[16];
+            if (ch * 32 + 32 <= v0) sum += chunk_exp<false>(cur, pk, ch * 32, v0, v1, v2, c, mc);
+            else sum += chunk_exp<true>(cur, pk, ch * 32, v0, v1, v2, c, mc);
+            tmem_st_32x16(t_s + (uint32_t)(ch * 16), pk);   // columns [16 ch, 16 ch + 16) < 32 (ch + 1): already consumed
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&p_ready[w]);
+        // ---- O = P V done: normalise, cast, store this thread's row (128 contiguous bytes)
+        mbar_wait(&o_full[w], it_ph);
+        tc_fence_after();
+        const float inv = 1.0f / sum;
+        const int qrow = w * 128 + row_in_tile;
+        __nv_bfloat16* orow = p.out + ((long long)f * p.N0 + qrow) * p.D + h * 64;
+#pragma unroll
+        for (int d0 = 0; d0 < 64; d0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x16(t_s + 128u + (uint32_t)d0, v);
+          tmem_ld_wait();
+          if (qrow < p.n_q) {
+            uint4 a, b2;
+            a.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+            a.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+            a.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+            a.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+            b2.x = pack_bf16x2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
+            b2.y = pack_bf16x2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+            b2.z = pack_bf16x2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
+            b2.w = pack_bf16x2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
+            *reinterpret_cast<uint4*>(orow + d0) = a;
+            *reinterpret_cast<uint4*>(orow + d0 + 8) = b2;
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&s_free[w]);
+        it_ph ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int NK>
+static int launch_attention_tc(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& taux,
+                               const AttnTcArgs& a, cudaStream_t stream) {
+  constexpr int smem_bytes = 2 * (2 * ATC_QTILE_BYTES + 2 * NK * 128) + 1024 + 256;
+  static bool attr_set = false;
+  auto kern = attention_tc_kernel<NK>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(attention_tc): %s", cudaGetErrorString(e)); return (int)e; }
+    attr_set = true;
+  }
+  const int grid = a.num_items < num_sms() ? a.num_items : num_sms();
+  kern<<<grid, ATC_THREADS, smem_bytes, stream>>>(tq, tkv, taux, a);
+  return check_launch("attention_tc");
+}
+
+int attention_tc(const void* qkv, const void* kv_aux, void* out, int B, int T, int N0, int G, int H, int n_q,
+                 cudaStream_t stream) {
+  const int kb_live = (N0 + 7) / 8 * 8;
+  const int keys = kb_live + 8 + T + 8;          // live | global | local | summary box
+  if (G != 8 || (T % 8) != 0 || kb_live > 256 || keys > 256 || N0 > 256) {
+    set_error("attention_tc: shape outside the tcgen05 specialisation (G=%d T=%d N0=%d)", G, T, N0);
+    return GAVA_ERR_SHAPE;
+  }
+  const int nk = keys <= 224 ? 224 : 256;   // softmax works in 32-key chunks
+  const int D = H * 64, BT = B * T;
+  CUtensorMap tq, tkv, taux;
+  int rc = make_tmap_bf16(&tq, qkv, (long long)BT * N0, 3LL * D, 3LL * D, 128);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&tkv, qkv, (long long)BT * N0, 3LL * D, 3LL * D, kb_live);
+  if (rc) return rc;
+  rc = make_tmap_bf16(&taux, kv_aux, (long long)G + 2LL * BT, 2LL * D, 2LL * D, 8);
+  if (rc) return rc;
+  AttnTcArgs a;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.T = T; a.N0 = N0; a.G = G; a.H = H; a.n_q = n_q; a.BT = BT; a.D = D;
+  a.kb_live = kb_live;
+  a.num_items = BT * H;
+  a.stage_tx_bytes = (uint32_t)(2 * ATC_QTILE_BYTES + 2 * 128 * keys);
+  if (nk == 224) return launch_attention_tc<224>(tq, tkv, taux, a, stream);
+  return launch_attention_tc<256>(tq, tkv, taux, a, stream);
+}
+
+}  // namespace gava

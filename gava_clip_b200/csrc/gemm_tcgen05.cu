@@ -450,7 +450,7 @@ static PFN_encodeTiled get_encode_fn() {
 }
 
 // 2-D bf16 row-major [rows, cols] with row pitch ld (elements); box = [box_rows, 64 cols], 128B swizzle
-static int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return GAVA_ERR_DRIVER; }
   if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || ((ld * 2) & 15)) {

@@ -1,6 +1,7 @@
 // Internal C++ declarations shared by the kernel translation units and the C-ABI shim (api.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda.h>
 #include "../../include/gava_sm100.h"
 
 namespace gava {
@@ -14,6 +15,9 @@ enum : int {
 };
 
 int num_sms();
+
+// 2-D bf16 row-major [rows, cols] (row pitch ld elements) TMA map, box = [box_rows, 64 cols], 128-byte swizzle
+int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows);
 
 int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long long M, long long N, long long K,
               const gava_gemm_epilogue* epi, cudaStream_t stream);
@@ -31,6 +35,10 @@ int temporal_attention(const void* qkv, void* out, int B, int T, int H, cudaStre
 int prompt_rows(const float* global_prompts, const float* local_prompts, const float* cls_proj_out,
                 const float* summary, const float* ln_w, const float* ln_b, void* out, int G, int B, int T, int D,
                 float eps, cudaStream_t stream);
+
+// tcgen05/TMEM/TMA attention (attention_tc.cu); returns GAVA_ERR_SHAPE when the shape is outside its specialisation
+int attention_tc(const void* qkv, const void* kv_aux, void* out, int B, int T, int N0, int G, int H, int n_q,
+                 cudaStream_t stream);
 
 int attention(const void* qkv, const void* kv_aux, void* out, int B, int T, int N0, int G, int H, int n_q,
               cudaStream_t stream);
