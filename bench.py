@@ -198,6 +198,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the single JSON line (no "NCCL version ..." banner)
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().gava_init(), "gava_init")
 
