@@ -211,6 +211,7 @@ class TowerEngine:
             "h": z(M, Dm, dt=bf),
             "cls_bf": z(BT, D, dt=bf),
             "cls_proj": z(BT, D, dt=f32),
+            "x_cls": z(BT, D, dt=f32),
             "sum_n": z(BT, D, dt=bf),
             "sqkv": z(BT, 3 * D, dt=bf),
             "smix": z(BT, D, dt=bf),
@@ -298,16 +299,33 @@ class TowerEngine:
             ops.gemm(W["aux_n"], P[k + "qkv.w"][D:], W["kvaux"], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:])
             # ---- x = x + attn(norm1(x)) on the live rows                                     utils.py:190-191
             ops.layernorm(x, P[k + "norm1.w"], P[k + "norm1.b"], xn, rows=M, in_row_stride=D)
-            ops.gemm(xn, P[k + "qkv.w"], qkv, mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"])
-            ops.attention(qkv, W["kvaux"], xn, B=B, T=T, N0=N0, G=G, H=H)
-            ops.gemm(xn, P[k + "out.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "out.b"], resid=x)
-            # ---- x = x + fc2(QuickGELU(fc1(norm2(x))))                                        utils.py:199
-            ops.layernorm(x, P[k + "norm2.w"], P[k + "norm2.b"], xn, rows=M, in_row_stride=D)
-            ops.gemm(xn, P[k + "fc1.w"], h, mode=ops.EPI_BIAS_GELU_BF16, bias=P[k + "fc1.b"])
-            ops.gemm(h, P[k + "fc2.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"], resid=x)
+            if i < L - 1:
+                ops.gemm(xn, P[k + "qkv.w"], qkv, mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"])
+                ops.attention(qkv, W["kvaux"], xn, B=B, T=T, N0=N0, G=G, H=H)
+                ops.gemm(xn, P[k + "out.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "out.b"], resid=x)
+                # ---- x = x + fc2(QuickGELU(fc1(norm2(x))))                                    utils.py:199
+                ops.layernorm(x, P[k + "norm2.w"], P[k + "norm2.b"], xn, rows=M, in_row_stride=D)
+                ops.gemm(xn, P[k + "fc1.w"], h, mode=ops.EPI_BIAS_GELU_BF16, bias=P[k + "fc1.b"])
+                ops.gemm(h, P[k + "fc2.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"], resid=x)
+            else:
+                # Last layer: only the cls row of each frame reaches the output (vision_encoder.py:126), so every row-wise
+                # op after the key/value projection runs on the BT cls rows alone: K/V for all rows, Q / attention query /
+                # out-proj / MLP for one row per frame.  Row-independent ops => bit-for-meaning identical results.
+                xn_cls = xn.view(BT, N0 * D)[:, :D]                      # row f*N0 of a [M, D] buffer, pitch N0*D
+                x_cls_src = x.view(BT, N0 * D)[:, :D]
+                ops.gemm(xn, P[k + "qkv.w"][D:], qkv[:, D:], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:])
+                ops.gemm(xn_cls, P[k + "qkv.w"][:D], qkv.view(BT, N0 * 3 * D)[:, :D], mode=ops.EPI_BIAS_BF16,
+                         bias=P[k + "qkv.b"][:D])
+                ops.attention(qkv, W["kvaux"], xn, B=B, T=T, N0=N0, G=G, H=H, n_q=1)
+                ops.gemm(xn_cls, P[k + "out.w"], W["x_cls"], mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "out.b"],
+                         resid=x_cls_src)
+                ops.layernorm(W["x_cls"], P[k + "norm2.w"], P[k + "norm2.b"], W["cls_bf"], rows=BT, in_row_stride=D)
+                ops.gemm(W["cls_bf"], P[k + "fc1.w"], h[:BT], mode=ops.EPI_BIAS_GELU_BF16, bias=P[k + "fc1.b"])
+                ops.gemm(h[:BT], P[k + "fc2.w"], W["x_cls"], mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"],
+                         resid=W["x_cls"])
 
         # ln_post(cls) @ proj per frame                                   vision_encoder.py:126-127
-        ops.layernorm(x, P["ln_post.w"], P["ln_post.b"], W["cls_bf"], rows=BT, in_row_stride=N0 * D)
+        ops.layernorm(W["x_cls"], P["ln_post.w"], P["ln_post.b"], W["cls_bf"], rows=BT, in_row_stride=D)
         ops.gemm(W["cls_bf"], P["proj.wT"], W["frame_feat"], mode=ops.EPI_BIAS_F32)
         return W["frame_feat"], W["summary"]
 
