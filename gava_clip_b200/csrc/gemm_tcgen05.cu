@@ -37,7 +37,7 @@ struct GemmCfg {
   static constexpr int kBytesB = BN * BK * 2;
   static constexpr int kBytesStage = kBytesA + kBytesB;
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
-  static constexpr int kSmemBytes = kStages * kBytesStage + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kBytesStage + EPI_WARPS * EPI_STAGE_BYTES + 2 * BN * 4 /*bias*/ + 256 /*barriers*/;
 };
 
 struct GemmArgs {
@@ -60,17 +60,17 @@ struct GemmArgs {
 // every warp-level global load/store covers whole 64/128-byte row segments.
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage, int row0, int col0,
-                                               uint32_t (&v)[32], const float4 (&resid)[8], int lane) {
+                                               const uint32_t (&v)[32], const float4 (&resid)[8], const float* bias_s,
+                                               int lane) {
   if constexpr (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16) {
     float acc[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-    if (p.bias != nullptr) {
-      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+    {  // bias of this chunk from shared memory (staged per tile before the accumulator wait; broadcast LDS.128)
+      const float4* b4 = reinterpret_cast<const float4*>(bias_s);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 b = __ldg(b4 + j);
-        acc[4 * j + 0] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
+        const float4 b = b4[j];
+        acc[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x; acc[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+        acc[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z; acc[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
       }
     }
     if constexpr (MODE == EPI_BIAS_GELU_BF16) {
@@ -135,29 +135,68 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
 }
 
 // One warp's share of one accumulator tile: NCH chunks of 32 columns starting at column `col_base`, rows row0..row0+31.
+// bf16-output modes: the tile's bias slice is staged in shared memory BEFORE the accumulator wait (its global-load latency
+// disappears under the mainloop) and the TMEM load of chunk c+1 is in flight while chunk c is converted and stored.
 template <int MODE, int NCH>
-__device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage, uint64_t* tmem_full_bar,
-                                              uint32_t full_phase, uint32_t t_addr, int row0, int col_base, int lane) {
-  mbar_wait(tmem_full_bar, full_phase);
-  tc_fence_after();
-#pragma unroll 1
-  for (int cc = 0; cc < NCH; ++cc) {
-    const int col0 = col_base + cc * 32;
-    float4 resid[8];
-    if constexpr (MODE == EPI_BIAS_RESID_F32) {  // coalesced residual loads, in flight while TMEM is read
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int grow = row0 + 4 * i + (lane >> 3);
-        resid[i] = (grow < p.M) ? *reinterpret_cast<const float4*>(p.resid + (long long)grow * p.ldr + col0 + 4 * (lane & 7))
-                                : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage, float* bias_s, uint64_t* tmem_full_bar,
+                                              uint32_t full_phase, uint32_t t_addr, int row0, int col_base, int lane,
+                                              long long& dbg_wait) {
+  if constexpr (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16) {
+    static_assert(NCH * 32 <= 128, "one float4 per lane covers the warp's columns");
+    if (lane < NCH * 8) {
+      const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col_base) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4*>(bias_s)[lane] = b;   // the 4 lane-quarter warps of a column half write identical values
     }
-    uint32_t v[32];
-    tmem_ld_32x32(t_addr + (uint32_t)(cc * 32), v);
-    tmem_ld_wait();
-#if GAVA_GEMM_DEBUG != 1
-    epilogue_chunk<MODE>(p, stage, row0, col0, v, resid, lane);
+    __syncwarp();
+#if GAVA_GEMM_DEBUG == 4
+    const long long t0 = clock64();
 #endif
+    mbar_wait(tmem_full_bar, full_phase);
+#if GAVA_GEMM_DEBUG == 4
+    dbg_wait += clock64() - t0;
+#endif
+    tc_fence_after();
+    uint32_t va[32], vb[32];
+    float4 resid[8];
+    tmem_ld_32x32(t_addr, va);
+#pragma unroll
+    for (int cc = 0; cc < NCH; ++cc) {
+      tmem_ld_wait();
+      uint32_t (&cur)[32] = (cc & 1) ? vb : va;
+      uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
+      if (cc + 1 < NCH) tmem_ld_32x32(t_addr + (uint32_t)((cc + 1) * 32), nxt);
+#if GAVA_GEMM_DEBUG != 1
+      epilogue_chunk<MODE>(p, stage, row0, col_base + cc * 32, cur, resid, bias_s + cc * 32, lane);
+#endif
+    }
+  } else {
+#if GAVA_GEMM_DEBUG == 4
+    const long long t0 = clock64();
+#endif
+    mbar_wait(tmem_full_bar, full_phase);
+#if GAVA_GEMM_DEBUG == 4
+    dbg_wait += clock64() - t0;
+#endif
+    tc_fence_after();
+#pragma unroll 1
+    for (int cc = 0; cc < NCH; ++cc) {
+      const int col0 = col_base + cc * 32;
+      float4 resid[8];
+      if constexpr (MODE == EPI_BIAS_RESID_F32) {  // coalesced residual loads, in flight while TMEM is read
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int grow = row0 + 4 * i + (lane >> 3);
+          resid[i] = (grow < p.M) ? *reinterpret_cast<const float4*>(p.resid + (long long)grow * p.ldr + col0 + 4 * (lane & 7))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      uint32_t v[32];
+      tmem_ld_32x32(t_addr + (uint32_t)(cc * 32), v);
+      tmem_ld_wait();
+#if GAVA_GEMM_DEBUG != 1
+      epilogue_chunk<MODE>(p, stage, row0, col0, v, resid, nullptr, lane);
+#endif
+    }
   }
 }
 
@@ -167,12 +206,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                     const GemmArgs p) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128-byte-swizzle tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw;
+  if (smem_u32(smem) & 1023u) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kBytesA;
   uint8_t* smem_epi = smem + kStages * Cfg::kBytesStage;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_WARPS * EPI_STAGE_BYTES);
+  float* smem_bias = reinterpret_cast<float*>(smem_epi + EPI_WARPS * EPI_STAGE_BYTES);   // [2 accumulator stages][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + 2 * BN);
   uint64_t* full_bar = bars;                      // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + kStages;           // [kStages]  MMA -> TMA
   uint64_t* tmem_full = bars + 2 * kStages;       // [2]        MMA -> epilogue
@@ -263,12 +304,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     uint8_t* stage = smem_epi + ew * EPI_STAGE_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
+    long long g_dbg_wait = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
       const int row0 = m_blk * BM + quarter * 32;
       const int col_base = n_blk * BN + half * kChunksPerWarp * 32;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * kChunksPerWarp * 32);
-      epilogue_tile<MODE, kChunksPerWarp>(p, stage, &tmem_full[acc], acc_phase, t_addr, row0, col_base, lane);
+      epilogue_tile<MODE, kChunksPerWarp>(p, stage, smem_bias + acc * BN + half * kChunksPerWarp * 32, &tmem_full[acc],
+                                          acc_phase, t_addr, row0, col_base, lane, g_dbg_wait);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -295,7 +338,7 @@ struct Gemm2Cfg {
   static constexpr int kBytesB = (BN / 2) * BK * 2;  // 128 rows of W (this CTA's half of N)
   static constexpr int kBytesStage = kBytesA + kBytesB;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kBytesStage + EPI_WARPS * EPI_STAGE_BYTES + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kBytesStage + EPI_WARPS * EPI_STAGE_BYTES + 2 * BN * 4 /*bias*/ + 256 /*barriers*/;
 };
 
 template <int MODE>
@@ -305,12 +348,14 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   using Cfg = Gemm2Cfg;
   constexpr int kStages = Cfg::kStages;
   constexpr int BN = Cfg::BN;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128-byte-swizzle tiles need 1024-byte alignment
+  uint8_t* smem = smem_raw;
+  if (smem_u32(smem) & 1023u) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * Cfg::kBytesA;
   uint8_t* smem_epi = smem + kStages * Cfg::kBytesStage;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + EPI_WARPS * EPI_STAGE_BYTES);
+  float* smem_bias = reinterpret_cast<float*>(smem_epi + EPI_WARPS * EPI_STAGE_BYTES);   // [2 accumulator stages][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_bias + 2 * BN);
   uint64_t* full_bar = bars;                      // [kStages]  TMA (both CTAs) -> MMA; only the leader's copy is used
   uint64_t* empty_bar = bars + kStages;           // [kStages]  MMA -> TMA; multicast to both CTAs
   uint64_t* tmem_full = bars + 2 * kStages;       // [2]        MMA -> epilogue; multicast to both CTAs
@@ -379,12 +424,27 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+#if GAVA_GEMM_DEBUG == 4
+      long long w_empty = 0, w_full = 0, t_start = clock64();
+#endif
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+#if GAVA_GEMM_DEBUG == 4
+        long long t0 = clock64();
+#endif
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+#if GAVA_GEMM_DEBUG == 4
+        w_empty += clock64() - t0;
+#endif
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
+#if GAVA_GEMM_DEBUG == 4
+          long long t1 = clock64();
+#endif
           mbar_wait(&full_bar[stage], phase);
+#if GAVA_GEMM_DEBUG == 4
+          w_full += clock64() - t1;
+#endif
           tc_fence_after();
           const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * Cfg::kBytesA));
           const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBytesB));
@@ -399,6 +459,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         umma_commit_2sm(&tmem_full[acc], 0b11);  // accumulator halves ready in both CTAs
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
+#if GAVA_GEMM_DEBUG == 4
+      if (blockIdx.x == 0 || blockIdx.x == 64)
+        printf("[mma  cta %d] total %lld cyc, wait tmem_empty %lld, wait full %lld\n", blockIdx.x, clock64() - t_start, w_empty, w_full);
+#endif
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -410,17 +474,26 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     uint8_t* stage = smem_epi + ew * EPI_STAGE_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
+#if GAVA_GEMM_DEBUG == 4
+    long long e_start = clock64();
+#endif
+    long long g_dbg_wait = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const int m_blk = tile / num_n, n_blk = tile - m_blk * num_n;
       const int row0 = m_blk * 2 * BM + (int)rank * BM + quarter * 32;
       const int col_base = n_blk * BN + half * kChunksPerWarp * 32;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * kChunksPerWarp * 32);
-      epilogue_tile<MODE, kChunksPerWarp>(p, stage, &tmem_full[acc], acc_phase, t_addr, row0, col_base, lane);
+      epilogue_tile<MODE, kChunksPerWarp>(p, stage, smem_bias + acc * BN + half * kChunksPerWarp * 32, &tmem_full[acc],
+                                          acc_phase, t_addr, row0, col_base, lane, g_dbg_wait);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // tell the leader this warp drained its part
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+#if GAVA_GEMM_DEBUG == 4
+    if ((blockIdx.x == 0 || blockIdx.x == 65) && lane == 0 && (ew == 0 || ew == 7))
+      printf("[epi  cta %d warp %d] total %lld cyc, waiting tmem_full %lld\n", blockIdx.x, ew, clock64() - e_start, g_dbg_wait);
+#endif
   }
 
   tc_fence_before();
