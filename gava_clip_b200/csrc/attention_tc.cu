@@ -4,19 +4,33 @@
 //   smem stage : Q tiles 0/1 [128 x 64], K [NK x 64], V [NK x 64]  (bf16, 128-byte swizzle, K/V rows gathered by
 //                several TMA boxes: live rows of the frame | 8 global prompts | T local prompts | summary token)
 //   TMEM       : S_w = Q_w K^T (128 x NK fp32) for the two query tiles w = 0,1 at columns 0 / 256;
-//                P_w (bf16, unnormalised probabilities) overwrites the first NK/2 columns of S_w;
-//                O_w = P_w V (128 x 64 fp32) lives at columns +128..+191 of the same region
-//   roles      : warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator,
-//                warps 4-7 softmax/output group of query tile 0, warps 8-11 of query tile 1 (thread == query row)
+//                P_w (bf16, unnormalised probabilities) overwrites S_w in place, each key-column half inside its own
+//                columns (keys [0,NK/2) -> cols [0,NK/4), keys [NK/2,NK) -> cols [NK/2, 3NK/4));
+//                O_w = P_w V (128 x 64 fp32) lives at columns +192..+255 of the same region
+//   roles      : warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 3-18 softmax/output:
+//                8 warps per query tile, TWO threads per query row (each owns one half of the key columns; row max and
+//                row sum are exchanged through shared memory), so four independent softmax streams hide the
+//                TMEM-load / MUFU latency chains
 // QK^T is an SS MMA (both operands K-major in smem); P V is a TS MMA (A = P from TMEM, B = V MN-major in smem).
 //
 // Restates Attention.forward core, training/VitaCLIP_vision_encoder_utils.py:71-77 (see attention.cu).
 #include "common.cuh"
 #include "kernels.h"
 
+#ifndef GAVA_ATTN_DEBUG
+#define GAVA_ATTN_DEBUG 0
+#endif
+#if GAVA_ATTN_DEBUG
+#define ATC_T0() const long long _t0 = clock64()
+#define ATC_ACC(x) x += clock64() - _t0
+#else
+#define ATC_T0()
+#define ATC_ACC(x)
+#endif
+
 namespace gava {
 
-constexpr int ATC_THREADS = 384;
+constexpr int ATC_THREADS = 608;   // 19 warps
 constexpr int ATC_QTILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
 
 struct AttnTcArgs {
@@ -107,6 +121,45 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(uint32_t M, uint32_t 
   return make_idesc_bf16(M, N) | (1u << 16);
 }
 
+template <bool MASK>
+__device__ __forceinline__ float chunk16_max(const uint32_t (&v)[16], int j0, int v0, int v1, int v2, float mx) {
+  float m0 = mx, m1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]);
+    if (MASK) {
+      const int k = j0 + j;
+      if (!(k < v0 || (k >= v1 && k <= v2))) a0 = -INFINITY;
+      if (!(k + 1 < v0 || (k + 1 >= v1 && k + 1 <= v2))) a1 = -INFINITY;
+    }
+    m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1);
+  }
+  return fmaxf(m0, m1);
+}
+template <bool MASK>
+__device__ __forceinline__ float chunk16_exp(const uint32_t (&v)[16], uint32_t (&pk)[8], int j0, int v0, int v1, int v2,
+                                             float c, float mc) {
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; j += 2) {
+    float p0 = exp2f(fmaf(__uint_as_float(v[j]), c, -mc));
+    float p1 = exp2f(fmaf(__uint_as_float(v[j + 1]), c, -mc));
+    if (MASK) {
+      const int k = j0 + j;
+      if (!(k < v0 || (k >= v1 && k <= v2))) p0 = 0.f;
+      if (!(k + 1 < v0 || (k + 1 >= v1 && k + 1 <= v2))) p1 = 0.f;
+    }
+    s0 += p0; s1 += p1;
+    pk[j >> 1] = pack_bf16x2(p0, p1);
+  }
+  return s0 + s1;
+}
+__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+
 template <int NK>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
@@ -123,6 +176,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint64_t* o_full = bars + 8;      // [2] MMA -> softmax group w
   uint64_t* s_free = bars + 10;     // [2] softmax group w -> MMA (S/P/O region of tile w reusable)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* xch = reinterpret_cast<float*>(bars + 16);   // [tile 2][max|sum 2][half 2][row 128] row statistics exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = (p.n_q + 127) >> 7;  // query tiles per item (1 or 2)
@@ -141,9 +195,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 128);
+      mbar_init(&p_ready[i], 256);
       mbar_init(&o_full[i], 1);
-      mbar_init(&s_free[i], 128);
+      mbar_init(&s_free[i], 256);
     }
     fence_barrier_init();
   }
@@ -193,15 +247,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       constexpr uint32_t idesc_o = make_idesc_bf16_bmn(128, 64);
       int st = 0;
       uint32_t ph = 0, it_ph = 0;
+#if GAVA_ATTN_DEBUG
+      long long d_kv = 0, d_sfree = 0, d_pready = 0, d_start = clock64();
+#endif
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         uint8_t* sQ = smem + st * kStageBytes;
         uint8_t* sK = sQ + 2 * ATC_QTILE_BYTES;
         uint8_t* sV = sK + kKVBytes;
-        mbar_wait(&kv_full[st], ph);
+        { ATC_T0(); mbar_wait(&kv_full[st], ph); ATC_ACC(d_kv); }
         tc_fence_after();
         const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK));
         for (int w = 0; w < n_units; ++w) {
-          mbar_wait(&s_free[w], it_ph ^ 1u);
+          { ATC_T0(); mbar_wait(&s_free[w], it_ph ^ 1u); ATC_ACC(d_sfree); }
           tc_fence_after();
           const uint64_t dq = make_sw128_kmajor_desc(smem_u32(sQ + w * ATC_QTILE_BYTES));
 #pragma unroll
@@ -211,81 +268,103 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         const uint64_t dv = make_sw128_mnmajor_desc(smem_u32(sV), (uint32_t)kKVBytes);
         for (int w = 0; w < n_units; ++w) {
-          mbar_wait(&p_ready[w], it_ph);
+          { ATC_T0(); mbar_wait(&p_ready[w], it_ph); ATC_ACC(d_pready); }
           tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < NK / 16; ++k)   // 16 keys per MMA: P advances 8 columns, V advances 16 rows (2048 B)
-            umma_bf16_ts(tmem_base + (uint32_t)(w * 256 + 128), tmem_base + (uint32_t)(w * 256 + 8 * k),
+          for (int k = 0; k < NK / 16; ++k) {  // 16 keys per MMA; V advances 16 rows (2048 B); P of key half 0 sits at
+            // columns 8k, P of key half 1 at NK/2 + 8(k - NK/32) (each half writes P inside its own S columns)
+            const int pcol = k < NK / 32 ? 8 * k : NK / 2 + 8 * (k - NK / 32);
+            umma_bf16_ts(tmem_base + (uint32_t)(w * 256 + 192), tmem_base + (uint32_t)(w * 256 + pcol),
                          dv + (uint64_t)(128 * k), idesc_o, (uint32_t)(k != 0));
+          }
           umma_commit(&o_full[w]);
         }
         umma_commit(&kv_empty[st]);
         it_ph ^= 1u;
         if (++st == 2) { st = 0; ph ^= 1u; }
       }
+#if GAVA_ATTN_DEBUG
+      if (blockIdx.x == 3) printf("[attn mma] total %lld: wait kv_full %lld, s_free %lld, p_ready %lld\n", clock64() - d_start, d_kv, d_sfree, d_pready);
+#endif
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // ===================== softmax + output groups =====================
-    const int w = (warp - 4) >> 2;          // query tile of this group
-    const int quarter = warp & 3;           // TMEM lane quarter
+  } else if (warp >= 3) {
+    // ===================== softmax + output: 2 threads per query row =====================
+    const int idx = warp - 3;               // 0..15
+    const int w = idx >> 3;                 // query tile
+    const int hh = (idx >> 2) & 1;          // key-column half owned by this thread
+    const int quarter = warp & 3;           // TMEM lane quarter (hardware rule: warp % 4)
     const int row_in_tile = quarter * 32 + lane;
+    constexpr int HALF = NK / 2;            // keys per half (112 or 128): HALF/16 chunks of 16
     const uint32_t t_s = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(w * 256);
+    const uint32_t t_mine = t_s + (uint32_t)(hh * HALF);
     const float c = 0.125f * 1.4426950408889634f;  // dh^-0.5 * log2(e)
     const int v0 = p.N0, v1 = p.kb_live, v2 = p.kb_live + 8 + p.T;   // valid keys: [0,v0) u [v1,v2]
+    float* my_max = xch + ((w * 2 + 0) * 2 + hh) * 128 + row_in_tile;
+    float* ot_max = xch + ((w * 2 + 0) * 2 + (hh ^ 1)) * 128 + row_in_tile;
+    float* my_sum = xch + ((w * 2 + 1) * 2 + hh) * 128 + row_in_tile;
+    float* ot_sum = xch + ((w * 2 + 1) * 2 + (hh ^ 1)) * 128 + row_in_tile;
     uint32_t it_ph = 0;
+#if GAVA_ATTN_DEBUG
+    long long d_sfull = 0, d_bar = 0, d_ofull = 0, d_start = clock64();
+#endif
     if (w < n_units) {
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         const int f = item / p.H, h = item - f * p.H;
-        mbar_wait(&s_full[w], it_ph);
+        { ATC_T0(); mbar_wait(&s_full[w], it_ph); ATC_ACC(d_sfull); }
         tc_fence_after();
-        // ---- pass 1: row maximum over the valid keys (TMEM load of chunk i+1 in flight while chunk i is reduced;
-        //      only chunks that contain masked keys pay for the mask)
+        // ---- pass 1: maximum over this thread's half of the keys, then exchange with the partner thread
         float mx = -INFINITY;
         {
-          uint32_t va[32], vb[32];
-          tmem_ld_32x32(t_s, va);
+          uint32_t va[16], vb[16];
+          tmem_ld_32x16(t_mine, va);
 #pragma unroll
-          for (int ch = 0; ch < NK / 32; ++ch) {
+          for (int ch = 0; ch < HALF / 16; ++ch) {
             tmem_ld_wait();
-            uint32_t (&cur)[32] = (ch & 1) ? vb : va;
-            uint32_t (&nxt)[32] = (ch & 1) ? va : vb;
-            if (ch + 1 < NK / 32) tmem_ld_32x32(t_s + (uint32_t)((ch + 1) * 32), nxt);
-            if (ch * 32 + 32 <= v0) mx = chunk_max<false>(cur, ch * 32, v0, v1, v2, mx);
-            else mx = chunk_max<true>(cur, ch * 32, v0, v1, v2, mx);
+            uint32_t (&cur)[16] = (ch & 1) ? vb : va;
+            uint32_t (&nxt)[16] = (ch & 1) ? va : vb;
+            if (ch + 1 < HALF / 16) tmem_ld_32x16(t_mine + (uint32_t)((ch + 1) * 16), nxt);
+            const int j0 = hh * HALF + ch * 16;
+            if (j0 + 16 <= v0) mx = chunk16_max<false>(cur, j0, v0, v1, v2, mx);
+            else mx = chunk16_max<true>(cur, j0, v0, v1, v2, mx);
           }
         }
+        *my_max = mx;
+        { ATC_T0(); asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory"); ATC_ACC(d_bar); }
+        mx = fmaxf(mx, *ot_max);
         const float mc = mx * c;
-        // ---- pass 2: p = exp2(s*c - m*c); P (bf16) overwrites S in place (column j/2 <- keys j, j+1)
+        // ---- pass 2: p = exp2(s*c - m*c); P (bf16) overwrites S inside this thread's own columns
         float sum = 0.f;
         {
-          uint32_t va[32], vb[32];
-          tmem_ld_32x32(t_s, va);
+          uint32_t va[16], vb[16];
+          tmem_ld_32x16(t_mine, va);
 #pragma unroll
-          for (int ch = 0; ch < NK / 32; ++ch) {
+          for (int ch = 0; ch < HALF / 16; ++ch) {
             tmem_ld_wait();
-            uint32_t (&cur)[32] = (ch & 1) ? vb : va;
-            uint32_t (&nxt)[32] = (ch & 1) ? va : vb;
-            if (ch + 1 < NK / 32) tmem_ld_32x32(t_s + (uint32_t)((ch + 1) * 32), nxt);
-            uint32_t pk[16];
-            if (ch * 32 + 32 <= v0) sum += chunk_exp<false>(cur, pk, ch * 32, v0, v1, v2, c, mc);
-            else sum += chunk_exp<true>(cur, pk, ch * 32, v0, v1, v2, c, mc);
-            tmem_st_32x16(t_s + (uint32_t)(ch * 16), pk);   // columns [16 ch, 16 ch + 16) < 32 (ch + 1): already consumed
+            uint32_t (&cur)[16] = (ch & 1) ? vb : va;
+            uint32_t (&nxt)[16] = (ch & 1) ? va : vb;
+            if (ch + 1 < HALF / 16) tmem_ld_32x16(t_mine + (uint32_t)((ch + 1) * 16), nxt);
+            uint32_t pk[8];
+            const int j0 = hh * HALF + ch * 16;
+            if (j0 + 16 <= v0) sum += chunk16_exp<false>(cur, pk, j0, v0, v1, v2, c, mc);
+            else sum += chunk16_exp<true>(cur, pk, j0, v0, v1, v2, c, mc);
+            tmem_st_32x8(t_mine + (uint32_t)(ch * 8), pk);   // columns [8 ch, 8 ch + 8) of the own half: already consumed
           }
         }
+        *my_sum = sum;
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&p_ready[w]);
-        // ---- O = P V done: normalise, cast, store this thread's row (128 contiguous bytes)
-        mbar_wait(&o_full[w], it_ph);
+        // ---- O = P V done: normalise, cast, store this thread's 32 of the row's 64 output values
+        { ATC_T0(); mbar_wait(&o_full[w], it_ph); ATC_ACC(d_ofull); }
         tc_fence_after();
-        const float inv = 1.0f / sum;
+        const float inv = 1.0f / (sum + *ot_sum);   // partner's sum was written before its p_ready arrive
         const int qrow = w * 128 + row_in_tile;
-        __nv_bfloat16* orow = p.out + ((long long)f * p.N0 + qrow) * p.D + h * 64;
+        __nv_bfloat16* orow = p.out + ((long long)f * p.N0 + qrow) * p.D + h * 64 + hh * 32;
 #pragma unroll
-        for (int d0 = 0; d0 < 64; d0 += 16) {
+        for (int d0 = 0; d0 < 32; d0 += 16) {
           uint32_t v[16];
-          tmem_ld_32x16(t_s + 128u + (uint32_t)d0, v);
+          tmem_ld_32x16(t_s + 192u + (uint32_t)(hh * 32 + d0), v);
           tmem_ld_wait();
           if (qrow < p.n_q) {
             uint4 a, b2;
@@ -305,6 +384,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mbar_arrive(&s_free[w]);
         it_ph ^= 1u;
       }
+#if GAVA_ATTN_DEBUG
+      if (blockIdx.x == 3 && lane == 0 && (idx == 0 || idx == 12))
+        printf("[attn smx warp %d] total %lld: wait s_full %lld, bar %lld, o_full %lld\n", idx, clock64() - d_start, d_sfull, d_bar, d_ofull);
+#endif
     }
   }
 
@@ -319,7 +402,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 template <int NK>
 static int launch_attention_tc(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& taux,
                                const AttnTcArgs& a, cudaStream_t stream) {
-  constexpr int smem_bytes = 2 * (2 * ATC_QTILE_BYTES + 2 * NK * 128) + 1024 + 256;
+  constexpr int smem_bytes = 2 * (2 * ATC_QTILE_BYTES + 2 * NK * 128) + 1024 + 128 + 2 * 2 * 2 * 128 * 4;
   static bool attr_set = false;
   auto kern = attention_tc_kernel<NK>;
   if (!attr_set) {
