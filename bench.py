@@ -39,10 +39,24 @@ CLASSES = ROOT / "tests" / "golden" / "classes" / "updrs_3cls_classes.txt"
 TOKENS = ROOT / "tests" / "golden" / "tokens.json"
 
 
+ARCH = "b16"      # set from --arch; "l14" = BASELINE.json configs[3] (ViT-L/14)
+
+
 def model_kwargs(frames: int) -> dict:
-    return dict(num_frames=frames, num_classes=3, text_prompt_classes_path=str(CLASSES), use_summary_token=True,
-                use_local_prompts=True, use_global_prompts=True, num_global_prompts=8, use_text_prompt_learning=True,
-                text_num_prompts=8, text_prompt_CSC=True)
+    kw = dict(num_frames=frames, num_classes=3, text_prompt_classes_path=str(CLASSES), use_summary_token=True,
+              use_local_prompts=True, use_global_prompts=True, num_global_prompts=8, use_text_prompt_learning=True,
+              text_num_prompts=8, text_prompt_CSC=True)
+    if ARCH == "l14":
+        kw.update(feature_dim=1024, patch_size=(14, 14), num_heads=16, num_layers=24, embed_dim=768,
+                  text_transformer_width=768, text_transformer_heads=12)
+    return kw
+
+
+def tower_config(frames: int):
+    from gava_clip_b200.config import TowerConfig
+    if ARCH == "l14":
+        return TowerConfig(num_frames=frames, feature_dim=1024, patch_size=(14, 14), num_heads=16, num_layers=24, embed_dim=768)
+    return TowerConfig(num_frames=frames)
 
 
 def load_peaks() -> dict:
@@ -273,7 +287,7 @@ def run_ours(args):
         assert torch.isfinite(host_logits).all()
 
     peaks = load_peaks()
-    cfg = TowerConfig(num_frames=T)
+    cfg = tower_config(T)
     f_clip = cfg.flops_per_clip(n_text_rows=3)
     clips_total = B * world * args.steps
     value = clips_total / (ms * 1e-3)
@@ -288,8 +302,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"VitaCLIP ViT-B/16, {T} frames 224^2, batch {B} per GPU, bf16 inference, 3-class UPDRS prompts "
-                               "(BASELINE.json configs[1])", "global_batch": B * world, "frames": T,
+        "config": {"workload": f"VitaCLIP {'ViT-L/14' if ARCH == 'l14' else 'ViT-B/16'}, {T} frames 224^2, batch {B} per GPU, bf16 inference, "
+                               f"3-class UPDRS prompts ({'BASELINE.json configs[1]' if (ARCH == 'b16' and T == 8 and B == 64) else 'non-headline shape'})", "global_batch": B * world, "frames": T,
                    "parallelism": f"dp{world} (clips sharded, no collective)",
                    "l2": "inputs (308 MB clip) and activations (>1 GB per layer) exceed the 126 MB L2; no flush needed",
                    "cuda_graph": bool(model.visual._engine.use_graph)},
@@ -322,7 +336,10 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--arch", default="b16", choices=["b16", "l14"], help="b16 = the metric's config; l14 = configs[3]")
     args = ap.parse_args()
+    global ARCH
+    ARCH = args.arch
     if args.impl == "reference":
         run_reference(args)
     else:
