@@ -87,4 +87,33 @@ int gava_head_fwd(const float* frame_feat, const float* summary_tok, const float
               scale, logit_bias, (cudaStream_t)stream);
 }
 
+int gava_split_bf16_fwd(const float* x, int64_t in_row_stride, void* hi, void* lo, int64_t out_row_stride, int64_t rows,
+                        int32_t D, void* stream) {
+  return split_bf16(x, in_row_stride, hi, lo, out_row_stride, rows, D, (cudaStream_t)stream);
+}
+
+int gava_patch_gather_split_fwd(const float* video, void* hi, void* lo, int32_t B, int32_t T, int32_t H, int32_t W,
+                                int32_t P, int32_t Kpad, void* stream) {
+  return patch_gather_split(video, hi, lo, B, T, H, W, P, Kpad, (cudaStream_t)stream);
+}
+
+int gava_embed_assemble_fwd(const float* tmp, float* x, const float* pos_embed, const float* time_embed, int32_t BT,
+                            int32_t T, int32_t Np, int32_t D, void* stream) {
+  return embed_assemble(tmp, x, pos_embed, time_embed, BT, T, Np, D, (cudaStream_t)stream);
+}
+
+int gava_quickgelu_f32_fwd(float* x, int64_t n, void* stream) { return quickgelu_f32(x, n, (cudaStream_t)stream); }
+
+int gava_attention_f32_fwd(const float* qkv, const float* kv_aux, float* out, int32_t B, int32_t T, int32_t N0,
+                           int32_t G, int32_t H, int32_t n_q, void* stream) {
+  return attention_f32(qkv, kv_aux, out, B, T, N0, G, H, n_q, (cudaStream_t)stream);
+}
+
+int gava_prompt_rows_f32_fwd(const float* global_prompts, const float* local_prompts, const float* cls_proj_out,
+                             const float* summary, const float* ln_weight, const float* ln_bias, float* out, int32_t G,
+                             int32_t B, int32_t T, int32_t D, float eps, void* stream) {
+  return prompt_rows_f32(global_prompts, local_prompts, cls_proj_out, summary, ln_weight, ln_bias, out, G, B, T, D, eps,
+                         (cudaStream_t)stream);
+}
+
 }  // extern "C"

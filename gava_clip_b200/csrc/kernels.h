@@ -47,4 +47,18 @@ int head(const float* frame_feat, const float* summary_tok, const float* text_ha
          float* video_features, float* summary_out, float* logits, int B, int T, int E, int D, int n_cls, float scale,
          float logit_bias, cudaStream_t stream);
 
+// ---- fp32-accuracy path (precise.cu)
+int split_bf16(const float* x, long long in_row_stride, void* hi, void* lo, long long out_row_stride, long long rows,
+               int D, cudaStream_t stream);
+int patch_gather_split(const float* video, void* hi, void* lo, int B, int T, int H, int W, int P, int Kpad,
+                       cudaStream_t stream);
+int embed_assemble(const float* tmp, float* x, const float* pos, const float* time_embed, int BT, int T, int Np, int D,
+                   cudaStream_t stream);
+int quickgelu_f32(float* x, long long n, cudaStream_t stream);
+int attention_f32(const float* qkv, const float* kv_aux, float* out, int B, int T, int N0, int G, int H, int n_q,
+                  cudaStream_t stream);
+int prompt_rows_f32(const float* global_prompts, const float* local_prompts, const float* cls_proj_out,
+                    const float* summary, const float* ln_w, const float* ln_b, float* out, int G, int B, int T, int D,
+                    float eps, cudaStream_t stream);
+
 }  // namespace gava

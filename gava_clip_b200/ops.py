@@ -187,3 +187,82 @@ def head(frame_feat: Tensor, summary_tok: Optional[Tensor], text_hat: Tensor, cl
                                    logits.data_ptr(), B, T, E, D, n_cls, scale, logit_bias, _stream())
     _lib.check(rc, "gava_head_fwd")
     return logits
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fp32-accuracy path: hi/lo bf16 operand split + 3-term tensor-core products, fp32 glue kernels (csrc/precise.cu)
+def split_bf16(x: Tensor, hi: Tensor, lo: Tensor, *, rows: int, D: int, in_row_stride: Optional[int] = None) -> None:
+    """hi = bf16(x), lo = bf16(x - hi) for `rows` rows of width D; x rows at pitch in_row_stride floats."""
+    _req(x, torch.float32, "split x"); _req(hi, torch.bfloat16, "split hi"); _req(lo, torch.bfloat16, "split lo")
+    in_row_stride = D if in_row_stride is None else in_row_stride
+    assert hi.is_contiguous() and lo.is_contiguous() and hi.numel() >= rows * D and lo.numel() >= rows * D
+    assert x.numel() >= (rows - 1) * in_row_stride + D
+    rc = _lib.load().gava_split_bf16_fwd(x.data_ptr(), in_row_stride, hi.data_ptr(), lo.data_ptr(), D, rows, D, _stream())
+    _lib.check(rc, "gava_split_bf16_fwd")
+
+
+def patch_gather_split(video: Tensor, hi: Tensor, lo: Tensor, patch: int) -> None:
+    _req(video, torch.float32, "patch_gather_split video"); _req(hi, torch.bfloat16, "hi"); _req(lo, torch.bfloat16, "lo")
+    assert video.is_contiguous() and hi.is_contiguous() and lo.is_contiguous() and hi.shape == lo.shape
+    B, _, T, H, W = video.shape
+    assert hi.shape[0] == B * T * (H // patch) * (W // patch)
+    rc = _lib.load().gava_patch_gather_split_fwd(video.data_ptr(), hi.data_ptr(), lo.data_ptr(), B, T, H, W, patch,
+                                                 hi.shape[1], _stream())
+    _lib.check(rc, "gava_patch_gather_split_fwd")
+
+
+def embed_assemble(tmp: Tensor, x: Tensor, pos_embed: Tensor, time_embed: Tensor, BT: int, T: int, Np: int) -> None:
+    for t in (tmp, x, pos_embed, time_embed):
+        _req(t, torch.float32, "embed_assemble"); assert t.is_contiguous()
+    D = tmp.shape[1]
+    assert tmp.shape[0] == BT * Np and x.numel() >= BT * (Np + 1) * D and pos_embed.shape == (Np + 1, D)
+    rc = _lib.load().gava_embed_assemble_fwd(tmp.data_ptr(), x.data_ptr(), pos_embed.data_ptr(), time_embed.data_ptr(),
+                                             BT, T, Np, D, _stream())
+    _lib.check(rc, "gava_embed_assemble_fwd")
+
+
+def quickgelu_f32(x: Tensor) -> Tensor:
+    _req(x, torch.float32, "quickgelu x"); assert x.is_contiguous()
+    rc = _lib.load().gava_quickgelu_f32_fwd(x.data_ptr(), x.numel(), _stream())
+    _lib.check(rc, "gava_quickgelu_f32_fwd")
+    return x
+
+
+def attention_f32(qkv: Tensor, kv_aux: Optional[Tensor], out: Tensor, *, B: int, T: int, N0: int, G: int, H: int,
+                  n_q: Optional[int] = None) -> Tensor:
+    _req(qkv, torch.float32, "attention_f32 qkv"); _req(out, torch.float32, "attention_f32 out")
+    D = H * 64
+    assert qkv.is_contiguous() and out.is_contiguous() and qkv.shape == (B * T * N0, 3 * D) and out.shape == (B * T * N0, D)
+    if kv_aux is not None:
+        _req(kv_aux, torch.float32, "attention_f32 kv_aux")
+        assert kv_aux.is_contiguous() and kv_aux.shape == (G + 2 * B * T, 2 * D)
+    rc = _lib.load().gava_attention_f32_fwd(qkv.data_ptr(), _ptr(kv_aux), out.data_ptr(), B, T, N0, G, H,
+                                            N0 if n_q is None else n_q, _stream())
+    _lib.check(rc, "gava_attention_f32_fwd")
+    return out
+
+
+def prompt_rows_f32(global_prompts: Tensor, local_prompts: Tensor, cls_proj_out: Tensor, summary: Tensor, ln_w: Tensor,
+                    ln_b: Tensor, out: Tensor, B: int, T: int, eps: float = 1e-5) -> Tensor:
+    for t in (global_prompts, local_prompts, cls_proj_out, summary, ln_w, ln_b, out):
+        _req(t, torch.float32, "prompt_rows_f32"); assert t.is_contiguous()
+    G, D = global_prompts.shape
+    assert out.shape == (G + 2 * B * T, D)
+    rc = _lib.load().gava_prompt_rows_f32_fwd(global_prompts.data_ptr(), local_prompts.data_ptr(), cls_proj_out.data_ptr(),
+                                              summary.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(), out.data_ptr(),
+                                              G, B, T, D, eps, _stream())
+    _lib.check(rc, "gava_prompt_rows_f32_fwd")
+    return out
+
+
+def gemm3(a_hi: Tensor, a_lo: Tensor, w_hi: Tensor, w_lo: Tensor, out: Tensor, *, bias: Optional[Tensor] = None,
+          resid: Optional[Tensor] = None) -> Tensor:
+    """fp32-accuracy product: out(f32) = [resid +] a @ w.T + bias with a = a_hi + a_lo, w = w_hi + w_lo (bf16 pairs),
+    evaluated as three tensor-core GEMMs accumulating in fp32 (the a_lo @ w_lo term, ~2^-18 relative, is dropped)."""
+    if resid is not None:
+        gemm(a_hi, w_hi, out, mode=EPI_BIAS_RESID_F32, bias=bias, resid=resid)
+    else:
+        gemm(a_hi, w_hi, out, mode=EPI_BIAS_F32, bias=bias)
+    gemm(a_hi, w_lo, out, mode=EPI_BIAS_RESID_F32, resid=out)
+    gemm(a_lo, w_hi, out, mode=EPI_BIAS_RESID_F32, resid=out)
+    return out

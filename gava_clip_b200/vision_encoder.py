@@ -184,6 +184,39 @@ class TowerEngine:
         self.signature = sig
         self.graphs.clear()  # captured graphs hold pointers into the old packed tensors
 
+    def pack_precise(self) -> Dict[str, Tensor]:
+        """hi/lo bf16 pairs of every GEMM weight for the fp32-accuracy path (w = hi + lo up to 2^-17)."""
+        if getattr(self, "_precise_sig", None) == self.signature and hasattr(self, "packed_lo"):
+            return self.packed_lo
+        e, dev = self.enc, self.device
+        D = e.feature_dim
+
+        def pair(w32: Tensor, name: str, out: Dict[str, Tensor]):
+            w32 = w32.detach().to(dev, torch.float32).contiguous()
+            hi = w32.to(torch.bfloat16)
+            out[name] = (hi, (w32 - hi.float()).to(torch.bfloat16))
+
+        Q: Dict[str, Tuple[Tensor, Tensor]] = {}
+        w = e.patch_embed.proj.weight.detach().reshape(D, -1).to(dev, torch.float32)
+        wp = torch.zeros(D, _ceil_to(w.shape[1], 64), device=dev)
+        wp[:, : w.shape[1]] = w
+        pair(wp, "patch.w", Q)
+        pj = torch.zeros(_ceil_to(e.embed_dim, 128), D, device=dev)
+        pj[: e.embed_dim] = e.proj.detach().t().to(dev, torch.float32)
+        pair(pj, "proj.wT", Q)
+        for i, blk in enumerate(e.blocks):
+            k = f"b{i}."
+            a, sa = blk.attn, blk.summary_attn_layer
+            pair(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0), k + "qkv.w", Q)
+            pair(a.out_proj.weight, k + "out.w", Q)
+            pair(blk.mlp.fc1.weight, k + "fc1.w", Q)
+            pair(blk.mlp.fc2.weight, k + "fc2.w", Q)
+            pair(blk.cls_proj.weight, k + "cls.w", Q)
+            pair(torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0), k + "sqkv.w", Q)
+            pair(sa.out_proj.weight, k + "sout.w", Q)
+        self.packed_lo, self._precise_sig = Q, self.signature
+        return Q
+
     def time_embed_for(self, T: int) -> Tensor:
         """nearest-neighbour resize when T differs from the trained length (vision_encoder.py:91-97)."""
         te = self.packed["time_embed"]
@@ -240,6 +273,11 @@ class TowerEngine:
 
     def run(self, video: Tensor) -> Tuple[Tensor, Tensor]:
         """encode_frames, replayed from a CUDA graph per clip shape (launch-bound inner loop: ~190 launches)."""
+        if self.enc.precision == "fp32":
+            n0 = ops.launch_count()
+            out = self.encode_frames_precise(video)
+            self.launches_last_call = ops.launch_count() - n0
+            return out
         if not self.use_graph or torch.cuda.is_current_stream_capturing():
             n0 = ops.launch_count()
             out = self.encode_frames(video)
@@ -351,8 +389,94 @@ class TowerEngine:
         return W["frame_feat"], W["summary"]
 
 
+    # ------------------------------------------------------------------ fp32-accuracy schedule
+    def _ws_precise(self, B: int, T: int) -> Dict[str, Tensor]:
+        key = ("precise", B, T)
+        if key in self.ws:
+            return self.ws[key]
+        e, dev = self.enc, self.device
+        D, N0, G = e.feature_dim, int(e.num_patches), e.num_global_prompts
+        BT, M = B * T, B * T * int(e.num_patches)
+        Dm = e.blocks[0].mlp.fc1.out_features
+        kp = _ceil_to(3 * e.patch_embed.patch_size ** 2, 64)
+        wide = max(Dm, kp)
+        bf, f32 = torch.bfloat16, torch.float32
+        z = lambda *s, dt: torch.empty(*s, device=dev, dtype=dt)
+        W = {"hi": z(M * wide, dt=bf), "lo": z(M * wide, dt=bf),            # operand split scratch (largest: [M, 4D])
+             "x": z(M, D, dt=f32), "t": z(M, D, dt=f32), "qkv": z(M, 3 * D, dt=f32), "att": z(M, D, dt=f32),
+             "h": z(M, Dm, dt=f32), "ptmp": z(BT * (N0 - 1), D, dt=f32),
+             "cls": z(BT, D, dt=f32), "cls_proj": z(BT, D, dt=f32), "sum_n": z(BT, D, dt=f32), "sqkv": z(BT, 3 * D, dt=f32),
+             "smix": z(BT, D, dt=f32), "summary": z(BT, D, dt=f32), "aux_n": z(G + 2 * BT, D, dt=f32),
+             "kvaux": z(G + 2 * BT, 2 * D, dt=f32), "x_cls": z(BT, D, dt=f32), "hc": z(BT, Dm, dt=f32),
+             "frame_feat": z(BT, self.packed["proj.wT"].shape[0], dt=f32)}
+        self.ws[key] = W
+        return W
+
+    def encode_frames_precise(self, video: Tensor) -> Tuple[Tensor, Tensor]:
+        """Same schedule as encode_frames with fp32 activations; every contraction is a 3-term split-bf16 product."""
+        e, P = self.enc, self.packed
+        Q = self.pack_precise()
+        B, _, T, _, _ = video.shape
+        D, N0, G, H = e.feature_dim, int(e.num_patches), e.num_global_prompts, e.num_heads
+        BT, M = B * T, B * T * N0
+        W = self._ws_precise(B, T)
+        te = self.time_embed_for(T)
+        x, t, qkv, att, h = W["x"], W["t"], W["qkv"], W["att"], W["h"]
+
+        def mm(a32: Tensor, rows: int, K: int, wname, out: Tensor, bias=None, resid=None, w_rows=None, in_row_stride=None):
+            """out = [resid +] a32[:rows, :K] @ w.T + bias, a32 fp32 (row pitch in_row_stride)."""
+            hi = W["hi"][: rows * K].view(rows, K)
+            lo = W["lo"][: rows * K].view(rows, K)
+            ops.split_bf16(a32, hi, lo, rows=rows, D=K, in_row_stride=in_row_stride)
+            w_hi, w_lo = Q[wname]
+            if w_rows is not None:
+                w_hi, w_lo = w_hi[w_rows], w_lo[w_rows]
+            ops.gemm3(hi, lo, w_hi, w_lo, out, bias=bias, resid=resid)
+
+        # patch embedding, cls rows, ln_pre
+        kp = Q["patch.w"][0].shape[1]
+        hi = W["hi"][: BT * (N0 - 1) * kp].view(-1, kp)
+        lo = W["lo"][: BT * (N0 - 1) * kp].view(-1, kp)
+        ops.patch_gather_split(video, hi, lo, e.patch_embed.patch_size)
+        ops.gemm3(hi, lo, *Q["patch.w"], W["ptmp"], bias=P["patch.b"])
+        ops.embed_assemble(W["ptmp"], x, P["pos_embed"], te, BT, T, N0 - 1)
+        ops.cls_rows(x, N0, P["cls_token"], P["pos_embed"], te, BT, T)
+        ops.layernorm(x, P["ln_pre.w"], P["ln_pre.b"], x, rows=M, in_row_stride=D)
+
+        L = len(e.blocks)
+        for i in range(L):
+            k = f"b{i}."
+            # temporal message (utils.py:160-188)
+            mm(x, BT, D, k + "cls.w", W["cls_proj"], bias=P[k + "cls.b"], in_row_stride=N0 * D)
+            ops.layernorm(W["cls_proj"], P[k + "summary_ln.w"], P[k + "summary_ln.b"], W["sum_n"], rows=BT, in_row_stride=D)
+            mm(W["sum_n"], BT, D, k + "sqkv.w", W["sqkv"], bias=P[k + "sqkv.b"])
+            ops.attention_f32(W["sqkv"], None, W["smix"], B=B, T=1, N0=T, G=0, H=H)
+            mm(W["smix"], BT, D, k + "sout.w", W["summary"], bias=P[k + "sout.b"], resid=W["cls_proj"])
+            ops.prompt_rows_f32(P["global_prompts"][i], P[k + "local"], W["cls_proj"], W["summary"], P[k + "norm1.w"],
+                                P[k + "norm1.b"], W["aux_n"], B, T, LN_EPS)
+            mm(W["aux_n"], G + 2 * BT, D, k + "qkv.w", W["kvaux"], bias=P[k + "qkv.b"][D:], w_rows=slice(D, 3 * D))
+            # x = x + attn(norm1(x))
+            ops.layernorm(x, P[k + "norm1.w"], P[k + "norm1.b"], t, rows=M, in_row_stride=D)
+            mm(t, M, D, k + "qkv.w", qkv, bias=P[k + "qkv.b"])
+            ops.attention_f32(qkv, W["kvaux"], att, B=B, T=T, N0=N0, G=G, H=H)
+            mm(att, M, D, k + "out.w", x, bias=P[k + "out.b"], resid=x)
+            # x = x + fc2(QuickGELU(fc1(norm2(x))))
+            ops.layernorm(x, P[k + "norm2.w"], P[k + "norm2.b"], t, rows=M, in_row_stride=D)
+            mm(t, M, D, k + "fc1.w", h, bias=P[k + "fc1.b"])
+            ops.quickgelu_f32(h)
+            mm(h, M, h.shape[1], k + "fc2.w", x, bias=P[k + "fc2.b"], resid=x)
+
+        ops.layernorm(x, P["ln_post.w"], P["ln_post.b"], W["cls"], rows=BT, in_row_stride=N0 * D)
+        mm(W["cls"], BT, D, "proj.wT", W["frame_feat"])
+        return W["frame_feat"], W["summary"]
+
+
 class CLIPVisionEncoder(nn.Module):
-    """Same constructor / parameters / outputs as the reference class (vision_encoder.py:18-132)."""
+    """Same constructor / parameters / outputs as the reference class (vision_encoder.py:18-132).
+
+    `precision` (attribute, default $GAVA_PRECISION or "bf16"): "bf16" = tensor-core bf16 operands, fp32 accumulation and
+    residual stream (logits within 2e-2 of the fp32 reference); "fp32" = split-bf16 3-term products + fp32 glue (within
+    1e-3; roughly 4x slower, a parity instrument)."""
 
     def __init__(self, input_size: Tuple[int, int] = (224, 224), num_frames: int = 8, feature_dim: int = 768,
                  patch_size: Tuple[int, int] = (16, 16), num_heads: int = 12, num_layers: int = 12,
@@ -388,6 +512,7 @@ class CLIPVisionEncoder(nn.Module):
         for p in (self.cls_token, self.pos_embed, self.time_embed):
             nn.init.normal_(p, std=0.02)
         self._engine: Optional[TowerEngine] = None
+        self.precision = os.environ.get("GAVA_PRECISION", "bf16")
 
     # -- engine plumbing ---------------------------------------------------------------------------
     def engine(self, device: torch.device) -> TowerEngine:

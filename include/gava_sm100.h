@@ -117,6 +117,40 @@ int gava_head_fwd(const float* frame_feat, const float* summary_tok, const float
                   const int32_t* class_offsets, float* video_features, float* summary_out, float* logits, int32_t B,
                   int32_t T, int32_t E, int32_t D, int32_t n_cls, float scale, float logit_bias, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * fp32-accuracy path (logits within 1e-3 of the fp32 reference).  Contractions still run on the tensor cores: an fp32
+ * operand x is split as hi + lo (two bf16 tensors, lo = bf16(x - hi)) and a product is evaluated as
+ * Ahi*Whi + Ahi*Wlo + Alo*Whi by three gava_gemm_bf16_fwd launches accumulating into an fp32 output
+ * (GAVA_EPI_BIAS_F32 first, then GAVA_EPI_BIAS_RESID_F32 with resid == out).  The entry points below are the glue. */
+
+/* hi[r, :] = bf16(x[r, :]), lo[r, :] = bf16(x[r, :] - hi[r, :]); x rows at pitch in_row_stride (f32 elements), hi/lo rows
+ * at pitch out_row_stride (bf16 elements).  D % 4 == 0. */
+int gava_split_bf16_fwd(const float* x, int64_t in_row_stride, void* hi, void* lo, int64_t out_row_stride, int64_t rows,
+                        int32_t D, void* stream);
+
+/* gava_patch_gather_fwd with a hi/lo bf16 pair as output (same row/column layout). */
+int gava_patch_gather_split_fwd(const float* video, void* hi, void* lo, int32_t B, int32_t T, int32_t H, int32_t W,
+                                int32_t P, int32_t Kpad, void* stream);
+
+/* x[f*(Np+1) + 1 + n, :] = tmp[f*Np + n, :] + pos_embed[1 + n, :] + time_embed[f % T, :]   (all f32)
+ * (the patch-embed epilogue of the bf16 path as a separate step; VitaCLIP_vision_encoder.py:108-111). */
+int gava_embed_assemble_fwd(const float* tmp, float* x, const float* pos_embed, const float* time_embed, int32_t BT,
+                            int32_t T, int32_t Np, int32_t D, void* stream);
+
+/* x <- x * sigmoid(1.702 x) in place, f32, n % 4 == 0   (VitaCLIP_vision_encoder_utils.py:18-20). */
+int gava_quickgelu_f32_fwd(float* x, int64_t n, void* stream);
+
+/* gava_attention_fwd in f32 on the CUDA cores: qkv f32 [B*T*N0, 3D], kv_aux f32 [G+2BT, 2D], out f32 [B*T*N0, D].
+ * kv_aux == NULL: plain self-attention over the N0 rows of each of the B*T groups (used for the summary-token
+ * attention with B*T = videos, N0 = frames). */
+int gava_attention_f32_fwd(const float* qkv, const float* kv_aux, float* out, int32_t B, int32_t T, int32_t N0,
+                           int32_t G, int32_t H, int32_t n_q, void* stream);
+
+/* gava_prompt_rows_fwd with f32 output. */
+int gava_prompt_rows_f32_fwd(const float* global_prompts, const float* local_prompts, const float* cls_proj_out,
+                             const float* summary, const float* ln_weight, const float* ln_bias, float* out, int32_t G,
+                             int32_t B, int32_t T, int32_t D, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

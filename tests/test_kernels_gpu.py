@@ -246,3 +246,76 @@ def test_head(cuda, n_kv):
     ref = (scale * vh @ txt.t()).view(B, n_cls, n_kv).mean(-1) - 0.5
     assert _rel(vf, v) < 1e-6 and _rel(so, st.view(B, T, D).mean(1)) < 1e-6
     assert _rel(lg, ref) < 1e-5
+
+
+# ---------------------------------------------------------------------------------- fp32-accuracy path kernels
+def test_split_and_gemm3_reach_fp32_accuracy(cuda):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(21)
+    M, N, K = 777, 768, 768
+    a = torch.randn(M, K, device=cuda, generator=g)
+    w = torch.randn(N, K, device=cuda, generator=g) * K ** -0.5
+    bias = torch.randn(N, device=cuda, generator=g)
+    resid = torch.randn(M, N, device=cuda, generator=g)
+    hi = torch.empty(M, K, device=cuda, dtype=torch.bfloat16); lo = torch.empty_like(hi)
+    ops.split_bf16(a, hi, lo, rows=M, D=K)
+    assert torch.equal(hi, a.bfloat16()) and _rel(hi.float() + lo.float(), a) < 2e-5
+    w_hi = w.bfloat16(); w_lo = (w - w_hi.float()).bfloat16()
+    out = torch.empty(M, N, device=cuda)
+    ops.gemm3(hi, lo, w_hi, w_lo, out, bias=bias, resid=resid)
+    ref = (resid.double() + a.double() @ w.double().t() + bias.double()).float()
+    assert _rel(out, ref) < 2e-5
+
+
+def test_quickgelu_f32_and_embed_assemble(cuda):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(22)
+    x = torch.randn(1000, 512, device=cuda, generator=g) * 3
+    ref = x * torch.sigmoid(1.702 * x)
+    ops.quickgelu_f32(x)
+    assert _rel(x, ref) < 1e-6
+    BT, T, Np, D = 6, 3, 196, 768
+    tmp = torch.randn(BT * Np, D, device=cuda, generator=g); pos = torch.randn(Np + 1, D, device=cuda, generator=g)
+    te = torch.randn(T, D, device=cuda, generator=g)
+    xs = torch.zeros(BT * (Np + 1), D, device=cuda)
+    ops.embed_assemble(tmp, xs, pos, te, BT, T, Np)
+    want = tmp.view(BT, Np, D) + pos[1:] + te[torch.arange(BT, device=cuda) % T][:, None]
+    assert torch.allclose(xs.view(BT, Np + 1, D)[:, 1:], want, atol=1e-6) and (xs.view(BT, Np + 1, D)[:, 0] == 0).all()
+
+
+@pytest.mark.parametrize("T,N0,H", [(8, 197, 12), (3, 50, 2)])
+def test_attention_f32(cuda, T, N0, H):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(23 + T)
+    B, G = 2, 8
+    D = H * 64
+    qkv = torch.randn(B * T * N0, 3 * D, device=cuda, generator=g)
+    kv_aux = torch.randn(G + 2 * B * T, 2 * D, device=cuda, generator=g)
+    out = torch.zeros(B * T * N0, D, device=cuda)
+    ops.attention_f32(qkv, kv_aux, out, B=B, T=T, N0=N0, G=G, H=H)
+    assert _rel(out, _attention_ref(qkv, kv_aux, B, T, N0, G, H)) < 1e-5
+    # summary form: plain self-attention over the T tokens of every video
+    sq = torch.randn(B * T, 3 * D, device=cuda, generator=g)
+    so = torch.zeros(B * T, D, device=cuda)
+    ops.attention_f32(sq, None, so, B=B, T=1, N0=T, G=0, H=H)
+    q, k, v = sq.view(B, T, 3, H, 64).unbind(2)
+    aff = torch.einsum("nqhc,nkhc->nqkh", q / 8.0, k).softmax(dim=-2)
+    assert _rel(so, torch.einsum("nqlh,nlhc->nqhc", aff, v).reshape(B * T, D)) < 1e-5
+
+
+def test_prompt_rows_f32_and_patch_gather_split(cuda):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(24)
+    B, T, G, D = 3, 8, 8, 768
+    gp = torch.randn(G, D, device=cuda, generator=g); lp = torch.randn(1, T, D, device=cuda, generator=g)
+    cp = torch.randn(B * T, D, device=cuda, generator=g); sm = torch.randn(B * T, D, device=cuda, generator=g)
+    w = torch.randn(D, device=cuda, generator=g); b = torch.randn(D, device=cuda, generator=g)
+    out = torch.empty(G + 2 * B * T, D, device=cuda)
+    ops.prompt_rows_f32(gp, lp, cp, sm, w, b, out, B, T)
+    rows = torch.cat([gp, (lp.expand(B, -1, -1) + cp.view(B, T, D)).reshape(B * T, D), sm])
+    assert _rel(out, F.layer_norm(rows, (D,), w, b, 1e-5)) < 1e-5
+    v = torch.randn(2, 3, 3, 56, 56, device=cuda, generator=g)
+    hi = torch.full((2 * 3 * 16, 640), 7.0, device=cuda, dtype=torch.bfloat16); lo = torch.full_like(hi, 7.0)
+    ops.patch_gather_split(v, hi, lo, 14)
+    ref = F.unfold(v.permute(0, 2, 1, 3, 4).flatten(0, 1), kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+    assert _rel(hi[:, :588].float() + lo[:, :588].float(), ref) < 2e-5 and (hi[:, 588:] == 0).all() and (lo[:, 588:] == 0).all()

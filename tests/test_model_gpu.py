@@ -124,3 +124,23 @@ def test_clip_streamer_matches_direct_calls(cuda):
     for a, b in zip(streamed, direct):
         assert torch.equal(a, b)
     assert st.h2d_bytes == sum(b.numel() * 4 for b in batches)
+
+
+@pytest.mark.parametrize("name", ["tiny", "b16_t8", "kapt_b16_t8"])
+def test_fp32_path_matches_reference(cuda, name):
+    """fp32-accuracy path (split-bf16 3-term tensor-core products, fp32 glue): logits within 1e-3 relative of the fp32
+    reference (BASELINE.json north_star), identical top-1."""
+    g = load_golden(name)
+    model, kw, B = build_model(name, device=cuda)
+    model.visual.precision = "fp32"
+    inp = {k: v.to(cuda) for k, v in fx.make_inputs(name).items()}
+    with torch.no_grad():
+        logits, logits_mt, logits_vm = model(inp["video"], memory=inp.get("memory"), video_nte=inp.get("video_nte"))
+    err = rel_err(logits, g["logits"])
+    print(f"\n[{name} fp32 path] logits rel err {err:.3e}; video_features rel-L2 {rel_l2(model.video_features, g['video_features']):.3e}")
+    assert err < 1e-3
+    assert rel_l2(model.video_features, g["video_features"]) < 1e-3
+    assert rel_l2(model.summary, g["summary"]) < 1e-3
+    assert torch.equal(logits.argmax(-1).cpu(), g["logits"].argmax(-1))
+    if g["logits_vm"] is not None:
+        assert rel_err(logits_vm, g["logits_vm"]) < 1e-3
