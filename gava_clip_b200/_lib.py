@@ -56,6 +56,7 @@ SIGNATURES = {
     "gava_embed_assemble_fwd": [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p],
     "gava_quickgelu_f32_fwd": [_p, _i64, _p],
     "gava_attention_f32_fwd": [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p],
+    "gava_causal_attention_f32_fwd": [_p, _p, _i32, _i32, _i32, _p],
     "gava_prompt_rows_f32_fwd": [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p],
 }
 _RESTYPES = {"gava_last_error_string": C.c_char_p}

@@ -109,6 +109,10 @@ int gava_attention_f32_fwd(const float* qkv, const float* kv_aux, float* out, in
   return attention_f32(qkv, kv_aux, out, B, T, N0, G, H, n_q, (cudaStream_t)stream);
 }
 
+int gava_causal_attention_f32_fwd(const float* qkv, float* out, int32_t n_seq, int32_t L, int32_t H, void* stream) {
+  return causal_attention_f32(qkv, out, n_seq, L, H, (cudaStream_t)stream);
+}
+
 int gava_prompt_rows_f32_fwd(const float* global_prompts, const float* local_prompts, const float* cls_proj_out,
                              const float* summary, const float* ln_weight, const float* ln_bias, float* out, int32_t G,
                              int32_t B, int32_t T, int32_t D, float eps, void* stream) {

@@ -57,6 +57,7 @@ int embed_assemble(const float* tmp, float* x, const float* pos, const float* ti
 int quickgelu_f32(float* x, long long n, cudaStream_t stream);
 int attention_f32(const float* qkv, const float* kv_aux, float* out, int B, int T, int N0, int G, int H, int n_q,
                   cudaStream_t stream);
+int causal_attention_f32(const float* qkv, float* out, int n_seq, int L, int H, cudaStream_t stream);
 int prompt_rows_f32(const float* global_prompts, const float* local_prompts, const float* cls_proj_out,
                     const float* summary, const float* ln_w, const float* ln_b, float* out, int G, int B, int T, int D,
                     float eps, cudaStream_t stream);

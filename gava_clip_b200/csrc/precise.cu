@@ -139,6 +139,7 @@ struct AttnF32Args {
   const float* kv_aux;   // [G + 2 BT, 2D] or null
   float* out;            // [rows, D]
   int T, N0, G, H, n_q, BT, S;
+  int causal;            // 1: query q attends keys 0..q only (text transformer); needs kv_aux == NULL
 };
 
 __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32Args p) {
@@ -173,8 +174,9 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32Args p)
     sQ[warp * 64 + lane] = qsrc[lane] * 0.125f;        // q / sqrt(dh), dh = 64 (exact: power of two)
     sQ[warp * 64 + 32 + lane] = qsrc[32 + lane] * 0.125f;
     __syncwarp();
+    const int Sq = p.causal ? q + 1 : S;      // keys visible to this query
     float mx = -INFINITY;
-    for (int j = lane; j < S; j += 32) {
+    for (int j = lane; j < Sq; j += 32) {
       float acc = 0.f;
 #pragma unroll 16
       for (int d = 0; d < 64; ++d) acc = fmaf(sQ[warp * 64 + d], sK[j * 65 + d], acc);
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32Args p)
     }
     mx = warp_max(mx);
     float sum = 0.f;
-    for (int j = lane; j < S; j += 32) {
+    for (int j = lane; j < Sq; j += 32) {
       const float e = expf(sP[warp * S + j] - mx);
       sP[warp * S + j] = e;
       sum += e;
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32Args p)
     sum = warp_sum(sum);
     __syncwarp();
     float o0 = 0.f, o1 = 0.f;
-    for (int j = 0; j < S; ++j) {
+    for (int j = 0; j < Sq; ++j) {
       const float pj = sP[warp * S + j];
       o0 = fmaf(pj, sV[j * 65 + lane], o0);
       o1 = fmaf(pj, sV[j * 65 + 32 + lane], o1);
@@ -203,13 +205,27 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32Args p)
   }
 }
 
+static int attention_f32_impl(const float* qkv, const float* kv_aux, float* out, int B, int T, int N0, int G, int H,
+                              int n_q, int causal, cudaStream_t stream);
+
 int attention_f32(const float* qkv, const float* kv_aux, float* out, int B, int T, int N0, int G, int H, int n_q,
                   cudaStream_t stream) {
-  if (!qkv || !out || B <= 0 || T <= 0 || N0 <= 0 || G < 0 || H <= 0 || n_q <= 0 || n_q > N0) {
+  return attention_f32_impl(qkv, kv_aux, out, B, T, N0, G, H, n_q, 0, stream);
+}
+
+// causal self-attention over n_seq sequences of L tokens (CLIP text transformer, VitaCLIP_text_encoder.py:67-88)
+int causal_attention_f32(const float* qkv, float* out, int n_seq, int L, int H, cudaStream_t stream) {
+  return attention_f32_impl(qkv, nullptr, out, n_seq, 1, L, 0, H, L, 1, stream);
+}
+
+static int attention_f32_impl(const float* qkv, const float* kv_aux, float* out, int B, int T, int N0, int G, int H,
+                              int n_q, int causal, cudaStream_t stream) {
+  if (!qkv || !out || B <= 0 || T <= 0 || N0 <= 0 || G < 0 || H <= 0 || n_q <= 0 || n_q > N0 || (causal && kv_aux)) {
     set_error("attention_f32: bad arguments");
     return GAVA_ERR_ARG;
   }
   AttnF32Args a;
+  a.causal = causal;
   a.qkv = qkv; a.kv_aux = kv_aux; a.out = out;
   a.T = T; a.N0 = N0; a.G = G; a.H = H; a.n_q = n_q; a.BT = B * T;
   a.S = kv_aux ? N0 + G + T + 1 : N0;       // kv_aux == NULL: plain self-attention over the N0 rows (summary attention)

@@ -266,3 +266,13 @@ def gemm3(a_hi: Tensor, a_lo: Tensor, w_hi: Tensor, w_lo: Tensor, out: Tensor, *
     gemm(a_hi, w_lo, out, mode=EPI_BIAS_RESID_F32, resid=out)
     gemm(a_lo, w_hi, out, mode=EPI_BIAS_RESID_F32, resid=out)
     return out
+
+
+def causal_attention_f32(qkv: Tensor, out: Tensor, *, n_seq: int, L: int, H: int) -> Tensor:
+    """causal self-attention core of the text transformer: qkv f32 [n_seq*L, 3D] -> out f32 [n_seq*L, D]."""
+    _req(qkv, torch.float32, "causal_attention qkv"); _req(out, torch.float32, "causal_attention out")
+    D = H * 64
+    assert qkv.is_contiguous() and out.is_contiguous() and qkv.shape == (n_seq * L, 3 * D) and out.shape == (n_seq * L, D)
+    rc = _lib.load().gava_causal_attention_f32_fwd(qkv.data_ptr(), out.data_ptr(), n_seq, L, H, _stream())
+    _lib.check(rc, "gava_causal_attention_f32_fwd")
+    return out

@@ -5,8 +5,9 @@ Interface and state_dict keys mirror the reference
 so checkpoints load unchanged.  The class text features do not depend on the video, so `TextTower`
 evaluates ALL description rows of ALL classes in one batched pass and caches the result per parameter
 version (the reference re-runs the 12-layer transformer once per class on every forward,
-VitaCLIP_model.py:282-290).  This producer is plain PyTorch on the GPU (library GEMMs): it is row
-(f)-1 "next" of SURVEY.md section 8, not part of the per-clip hot path.
+VitaCLIP_model.py:282-290).  On a CUDA device the transformer itself runs on the sm_100a kernels
+(`TextTower._encode_sm100`: LayerNorm, split-bf16 3-term tcgen05 GEMMs, fp32 causal attention, fp32 QuickGELU; row (f)-1
+of SURVEY.md section 8); only prompt assembly (concatenation, the tiny KAPT projector) stays in PyTorch.
 """
 from __future__ import annotations
 
@@ -174,6 +175,77 @@ class TextTower:
         ps = list(self.textual.parameters()) + list(self.prompt_learner.parameters())
         return (str(device), self.prompt_learner._embed_version) + tuple((p.data_ptr(), p._version) for p in ps)
 
+    # ------------------------------------------------------------------ sm_100a path
+    def _pack(self, device) -> dict:
+        """hi/lo bf16 pairs of the text transformer's GEMM weights (fp32-accuracy products: the features are computed
+        once per parameter version, so the 3x GEMM cost is irrelevant and the logits keep their full error budget)."""
+        key = tuple((p.data_ptr(), p._version) for p in self.textual.parameters())
+        if getattr(self, "_pack_key", None) == (key, str(device)):
+            return self._packed
+        t = self.textual
+
+        def pair(w):
+            w = w.detach().to(device, torch.float32).contiguous()
+            hi = w.to(torch.bfloat16)
+            return hi, (w - hi.float()).to(torch.bfloat16)
+
+        f32 = lambda v: v.detach().to(device, torch.float32).contiguous()
+        P = {"blocks": [], "pos": f32(t.positional_embedding), "lnf": (f32(t.ln_final.weight), f32(t.ln_final.bias)),
+             "proj": pair(t.text_projection.t())}
+        for blk in t.transformer.resblocks:
+            P["blocks"].append({
+                "ln1": (f32(blk.ln_1.weight), f32(blk.ln_1.bias)), "ln2": (f32(blk.ln_2.weight), f32(blk.ln_2.bias)),
+                "in": pair(blk.attn.in_proj_weight), "in_b": f32(blk.attn.in_proj_bias),
+                "out": pair(blk.attn.out_proj.weight), "out_b": f32(blk.attn.out_proj.bias),
+                "fc": pair(blk.mlp.c_fc.weight), "fc_b": f32(blk.mlp.c_fc.bias),
+                "pj": pair(blk.mlp.c_proj.weight), "pj_b": f32(blk.mlp.c_proj.bias)})
+        self._packed, self._pack_key = P, (key, str(device))
+        return P
+
+    def _encode_sm100(self, prompts: Tensor, tokenized: Tensor) -> Tensor:
+        """CLIPTextEncoder.forward (text_encoder.py:154-171) for all R description rows at once on the sm_100a kernels:
+        LayerNorm, split-bf16 3-term tcgen05 GEMMs, fp32 causal attention, fp32 QuickGELU."""
+        from . import ops
+        t = self.textual
+        R, L, Wd = prompts.shape
+        H = t.transformer.resblocks[0].n_head
+        if Wd // H != 64 or Wd % 128 != 0:
+            raise NotImplementedError("text tower kernels are specialised for head_dim 64 and width % 128 == 0")
+        dev = prompts.device
+        P = self._pack(dev)
+        M = R * L
+        x = (prompts + P["pos"]).reshape(M, Wd).contiguous()
+        z = lambda *s, dt=torch.float32: torch.empty(*s, device=dev, dtype=dt)
+        tn, qkv, att, h = z(M, Wd), z(M, 3 * Wd), z(M, Wd), z(M, 4 * Wd)
+        hi, lo = z(M * 4 * Wd, dt=torch.bfloat16), z(M * 4 * Wd, dt=torch.bfloat16)
+
+        def mm(a32, rows, K, w, out, bias=None, resid=None):
+            ah, al = hi[: rows * K].view(rows, K), lo[: rows * K].view(rows, K)
+            ops.split_bf16(a32, ah, al, rows=rows, D=K)
+            ops.gemm3(ah, al, w[0], w[1], out, bias=bias, resid=resid)
+
+        for b in P["blocks"]:
+            ops.layernorm(x, b["ln1"][0], b["ln1"][1], tn, rows=M, in_row_stride=Wd)
+            mm(tn, M, Wd, b["in"], qkv, bias=b["in_b"])
+            ops.causal_attention_f32(qkv, att, n_seq=R, L=L, H=H)
+            mm(att, M, Wd, b["out"], x, bias=b["out_b"], resid=x)
+            ops.layernorm(x, b["ln2"][0], b["ln2"][1], tn, rows=M, in_row_stride=Wd)
+            mm(tn, M, Wd, b["fc"], h, bias=b["fc_b"])
+            ops.quickgelu_f32(h)
+            mm(h, M, 4 * Wd, b["pj"], x, bias=b["pj_b"], resid=x)
+        eot = torch.where(tokenized == t.vocab_size - 1)[-1]                     # :169 (un-shifted ids: KAPT quirk kept)
+        rows = x.view(R, L, Wd)[torch.arange(R, device=dev), eot].contiguous()    # gather: memory plumbing
+        rn = z(R, Wd)
+        ops.layernorm(rows, P["lnf"][0], P["lnf"][1], rn, rows=R, in_row_stride=Wd)
+        E = t.text_projection.shape[1]
+        ep = (E + 127) // 128 * 128
+        w_hi, w_lo = P["proj"]
+        if ep != E:
+            w_hi = torch.cat([w_hi, w_hi.new_zeros(ep - E, Wd)]); w_lo = torch.cat([w_lo, w_lo.new_zeros(ep - E, Wd)])
+        out = z(R, ep)
+        mm(rn, R, Wd, (w_hi, w_lo), out)
+        return out[:, :E].contiguous()
+
     def features(self, device: torch.device, need_grad: bool = False):
         """-> (t_hat (R,E) L2-normalised rows, class_offsets int32 (n_cls+1), text_features (n_cls,E), counts)."""
         sig = self._signature(device)
@@ -183,7 +255,10 @@ class TextTower:
             prompts = self.prompt_learner()
             counts = [p.shape[0] for p in prompts]
             tok = torch.cat([t.to(device) for t in self.prompt_learner.tokenized_prompts], dim=0)
-            raw = self.textual(torch.cat(prompts, dim=0).to(device), tok).float()
+            if device.type == "cuda" and not need_grad:
+                raw = self._encode_sm100(torch.cat(prompts, dim=0).to(device).float(), tok)
+            else:       # host-side tests / autograd: the module's own PyTorch forward
+                raw = self.textual(torch.cat(prompts, dim=0).to(device), tok).float()
             t_hat = raw / raw.norm(dim=-1, keepdim=True)
             offs = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32, device=device)
             means = torch.stack([c.mean(0) for c in t_hat.split(counts, dim=0)])

@@ -146,6 +146,11 @@ int gava_quickgelu_f32_fwd(float* x, int64_t n, void* stream);
 int gava_attention_f32_fwd(const float* qkv, const float* kv_aux, float* out, int32_t B, int32_t T, int32_t N0,
                            int32_t G, int32_t H, int32_t n_q, void* stream);
 
+/* Causal multi-head self-attention core of the CLIP text transformer in f32: qkv f32 [n_seq*L, 3D] (packed in_proj
+ * output), out f32 [n_seq*L, D]; query t attends tokens 0..t of its sequence; dh = 64.
+ * Replaces nn.MultiheadAttention's core with the causal mask, VitaCLIP_text_encoder.py:83-88,146-152. */
+int gava_causal_attention_f32_fwd(const float* qkv, float* out, int32_t n_seq, int32_t L, int32_t H, void* stream);
+
 /* gava_prompt_rows_fwd with f32 output. */
 int gava_prompt_rows_f32_fwd(const float* global_prompts, const float* local_prompts, const float* cls_proj_out,
                              const float* summary, const float* ln_weight, const float* ln_bias, float* out, int32_t G,

@@ -144,3 +144,43 @@ def test_fp32_path_matches_reference(cuda, name):
     assert torch.equal(logits.argmax(-1).cpu(), g["logits"].argmax(-1))
     if g["logits_vm"] is not None:
         assert rel_err(logits_vm, g["logits_vm"]) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["tiny", "b16_t8", "kapt_b16_t8"])
+def test_text_tower_kernels_match_module_forward(cuda, name):
+    """sm_100a text tower (TextTower._encode_sm100) == the module's own PyTorch forward, and == the reference's
+    text_features golden, to fp32 accuracy."""
+    g = load_golden(name)
+    model, kw, B = build_model(name, device=cuda)
+    tt = model._text_tower
+    with torch.no_grad():
+        prompts = torch.cat(model.prompt_learner(), dim=0).to(cuda).float()
+        tok = torch.cat([t.to(cuda) for t in model.tokenized_prompts], dim=0)
+        ours = tt._encode_sm100(prompts, tok)
+        ref = model.textual(prompts, tok)
+        t_hat, offs, text_features, counts = tt.features(cuda)
+    assert rel_err(ours, ref) < 1e-4
+    assert rel_err(text_features, g["text_features"]) < 1e-4
+
+
+def test_long_clip_recipe_shape_against_oracle(cuda):
+    """T = 70 frames (the shipped UPDRS recipe, train_scripts/updrs_3cls_train_tulip.sh:21): 276 keys per frame, i.e. the
+    mma.sync attention fallback and the long summary attention.  No golden exists for it: checked against the CPU oracle."""
+    from gava_clip_b200 import VitaCLIP, tokenizer
+    from oracle import vita_oracle as vo
+    tokenizer.register_tokens(fx.load_tokens())
+    kw, _ = fx.case_kwargs("b16_t8")
+    kw.update(num_frames=70, num_layers=2)                     # 2 layers keep the CPU oracle fast; shapes are what matter
+    model = VitaCLIP(**kw)
+    fx.fill_params_(model.state_dict().items(), seed=1)
+    model.prompt_learner.refresh_token_embeddings(model.textual)
+    model.eval()
+    video = torch.randn(1, 3, 70, 224, 224, generator=torch.Generator().manual_seed(7))
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    ref = vo.vita_forward(sd, video, model.tokenized_prompts, num_frames=70, num_heads=12, num_layers=2, n_ctx=8)
+    model = model.to(cuda)
+    with torch.no_grad():
+        logits = model(video.to(cuda))[0]
+    assert rel_err(logits, ref["logits"]) < TOL
+    assert rel_l2(model.video_features, ref["video_features"]) < TOL
+    assert rel_l2(model.summary, ref["summary"]) < TOL
