@@ -313,6 +313,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         const int f = item / p.H, h = item - f * p.H;
         { ATC_T0(); mbar_wait(&s_full[w], it_ph); ATC_ACC(d_sfull); }
         tc_fence_after();
+        if (w * 128 + quarter * 32 >= p.n_q) {
+          // All 32 query rows of this warp lie beyond n_q (e.g. rows 224..255 of a 197-row frame): nothing to compute.
+          // MMA rows are independent, so the garbage left in these P/O rows never reaches a stored row; the warp only
+          // keeps the barrier protocol going (named barrier with its partner warps, p_ready, s_free).
+          asm volatile("bar.sync %0, 256;" ::"r"(1 + w) : "memory");
+          mbar_arrive(&p_ready[w]);
+          mbar_wait(&o_full[w], it_ph);
+          mbar_arrive(&s_free[w]);
+          it_ph ^= 1u;
+          continue;
+        }
         // ---- pass 1: maximum over this thread's half of the keys, then exchange with the partner thread
         float mx = -INFINITY;
         {
