@@ -46,6 +46,7 @@ SIGNATURES = {
     "gava_gemm_bf16_fwd": [_p, _i64, _p, _i64, _i64, _i64, _i64, C.POINTER(GemmEpilogue), _p],
     "gava_layernorm_fwd": [_p, _i64, _p, _p, _p, _i64, _i32, _i64, _i32, _f32, _p],
     "gava_patch_gather_fwd": [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p],
+    "gava_patch_gather_u8_fwd": [_p, _p, _p, C.POINTER(C.c_float), C.POINTER(C.c_float), _i32, _i32, _i32, _i32, _i32, _i32, _p],
     "gava_cls_rows_fwd": [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _p],
     "gava_temporal_attention_fwd": [_p, _p, _i32, _i32, _i32, _p],
     "gava_prompt_rows_fwd": [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p],

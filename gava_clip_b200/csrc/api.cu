@@ -59,6 +59,11 @@ int gava_patch_gather_fwd(const float* video, void* A, int32_t B, int32_t T, int
   return patch_gather(video, A, B, T, H, W, P, Kpad, (cudaStream_t)stream);
 }
 
+int gava_patch_gather_u8_fwd(const uint8_t* frames, void* hi, void* lo, const float* mean, const float* std, int32_t B,
+                             int32_t T, int32_t H, int32_t W, int32_t P, int32_t Kpad, void* stream) {
+  return patch_gather_u8(frames, hi, lo, mean, std, B, T, H, W, P, Kpad, (cudaStream_t)stream);
+}
+
 int gava_cls_rows_fwd(float* x, int32_t tokens_per_frame, const float* cls_token, const float* pos_embed,
                       const float* time_embed, int32_t BT, int32_t T, int32_t D, void* stream) {
   return cls_rows(x, tokens_per_frame, cls_token, pos_embed, time_embed, BT, T, D, (cudaStream_t)stream);

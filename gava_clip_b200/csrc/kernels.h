@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda.h>
+#include <stdint.h>
 #include "../../include/gava_sm100.h"
 
 namespace gava {
@@ -26,6 +27,10 @@ int layernorm(const float* x, long long in_row_stride, const float* w, const flo
               long long out_row_stride, int out_bf16, long long rows, int D, float eps, cudaStream_t stream);
 
 int patch_gather(const float* video, void* A, int B, int T, int H, int W, int P, int Kpad, cudaStream_t stream);
+
+// mean/std are HOST arrays of 3 floats (passed by value to the kernel); lo may be null
+int patch_gather_u8(const uint8_t* frames, void* hi, void* lo, const float* mean, const float* std, int B, int T, int H,
+                    int W, int P, int Kpad, cudaStream_t stream);
 
 int cls_rows(float* x, int tokens_per_frame, const float* cls_token, const float* pos_embed, const float* time_embed,
              int BT, int T, int D, cudaStream_t stream);

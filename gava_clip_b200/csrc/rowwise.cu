@@ -153,6 +153,93 @@ int patch_gather(const float* video, void* A, int B, int T, int H, int W, int P,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Input stage fused into the patch gather: decoder output uint8 [B,T,H,W,3] (HWC) ->
+// (u/255 - mean[c]) / std[c] (video_dataset/dataset.py:117-121, fp32, true divisions) -> bf16 patch rows.
+// One thread moves 8 pixels x 3 channels (24 contiguous input bytes -> three 16-byte stores).
+__global__ void __launch_bounds__(256) patch_gather_u8_vec8_kernel(const uint8_t* __restrict__ frames,
+                                                                   __nv_bfloat16* __restrict__ A, float m0, float m1,
+                                                                   float m2, float s0, float s1, float s2, int B, int T,
+                                                                   int H, int W, int P, int Kpad) {
+  const int w8n = W >> 3;
+  const long long total = (long long)B * T * H * w8n;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int w8 = (int)(idx % w8n);
+  long long r = idx / w8n;
+  const int y = (int)(r % H); r /= H;            // r = b*T + t
+  const uint2* src = reinterpret_cast<const uint2*>(frames + idx * 24);
+  const uint2 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2);
+  const uint32_t wds[6] = {q0.x, q0.y, q1.x, q1.y, q2.x, q2.y};
+  float v[3][8];
+  const float mean[3] = {m0, m1, m2}, sd[3] = {s0, s1, s2};
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    const float u = (float)((wds[i >> 2] >> (8 * (i & 3))) & 0xffu);
+    v[i % 3][i / 3] = __fdiv_rn(__fdiv_rn(u, 255.0f) - mean[i % 3], sd[i % 3]);
+  }
+  const int x = w8 * 8;
+  const int gw = W / P, gh = H / P;
+  const long long arow = (r * gh + y / P) * gw + x / P;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    uint4 o;
+    o.x = pack_bf16x2(v[c][0], v[c][1]); o.y = pack_bf16x2(v[c][2], v[c][3]);
+    o.z = pack_bf16x2(v[c][4], v[c][5]); o.w = pack_bf16x2(v[c][6], v[c][7]);
+    *reinterpret_cast<uint4*>(A + arow * Kpad + c * P * P + (y % P) * P + (x % P)) = o;
+  }
+}
+// any patch size; optional lo output (fp32-accuracy path)
+__global__ void __launch_bounds__(256) patch_gather_u8_scalar_kernel(const uint8_t* __restrict__ frames,
+                                                                     __nv_bfloat16* __restrict__ hi,
+                                                                     __nv_bfloat16* __restrict__ lo, float m0, float m1,
+                                                                     float m2, float s0, float s1, float s2, int B, int T,
+                                                                     int H, int W, int P, int Kpad) {
+  const long long total = (long long)B * T * H * W * 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % 3);
+  long long r = idx / 3;
+  const int x = (int)(r % W); r /= W;
+  const int y = (int)(r % H); r /= H;
+  const int gw = W / P, gh = H / P;
+  if (y >= gh * P || x >= gw * P) return;
+  const float mean = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+  const float v = __fdiv_rn(__fdiv_rn((float)frames[idx], 255.0f) - mean, sd);
+  const long long off = ((r * gh + y / P) * gw + x / P) * Kpad + c * P * P + (y % P) * P + (x % P);
+  const __nv_bfloat16 h = __float2bfloat16(v);
+  hi[off] = h;
+  if (lo != nullptr) lo[off] = __float2bfloat16(v - __bfloat162float(h));
+}
+
+int patch_gather_u8(const uint8_t* frames, void* hi, void* lo, const float* mean, const float* std, int B, int T, int H,
+                    int W, int P, int Kpad, cudaStream_t stream) {
+  if (!frames || !hi || !mean || !std || B <= 0 || T <= 0 || P <= 0 || H < P || W < P || Kpad < 3 * P * P) {
+    set_error("patch_gather_u8: bad arguments");
+    return GAVA_ERR_ARG;
+  }
+  for (int c = 0; c < 3; ++c)
+    if (!(std[c] > 0.f)) { set_error("patch_gather_u8: std must be positive"); return GAVA_ERR_ARG; }
+  const long long rows = (long long)B * T * (H / P) * (W / P);
+  if (Kpad > 3 * P * P) {
+    cudaError_t e = cudaMemsetAsync(hi, 0, (size_t)rows * Kpad * 2, stream);
+    if (e == cudaSuccess && lo) e = cudaMemsetAsync(lo, 0, (size_t)rows * Kpad * 2, stream);
+    if (e != cudaSuccess) { set_error("patch_gather_u8 memset: %s", cudaGetErrorString(e)); return (int)e; }
+  }
+  if (!lo && P % 8 == 0 && W % 8 == 0 && H % P == 0 && W % P == 0 && Kpad % 8 == 0 &&
+      (reinterpret_cast<uintptr_t>(frames) & 7u) == 0) {
+    const long long total = (long long)B * T * H * (W / 8);
+    patch_gather_u8_vec8_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+        frames, reinterpret_cast<__nv_bfloat16*>(hi), mean[0], mean[1], mean[2], std[0], std[1], std[2], B, T, H, W, P, Kpad);
+  } else {
+    const long long total = (long long)B * T * H * W * 3;
+    patch_gather_u8_scalar_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+        frames, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), mean[0], mean[1], mean[2],
+        std[0], std[1], std[2], B, T, H, W, P, Kpad);
+  }
+  return check_launch("patch_gather_u8");
+}
+
+// ------------------------------------------------------------------------------------------------
 // cls rows: x[f*tpf] = cls_token + pos_embed[0] + time_embed[f % T]   (VitaCLIP_vision_encoder.py:108-111)
 __global__ void __launch_bounds__(256) cls_rows_kernel(float* __restrict__ x, int tpf, const float* __restrict__ cls,
                                                        const float* __restrict__ pos, const float* __restrict__ te,

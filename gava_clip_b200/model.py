@@ -185,6 +185,8 @@ class VitaCLIP(nn.Module):
 
     # ------------------------------------------------------------------ forward (reference :241-401)
     def forward(self, x: Tensor, memory=None, video_nte=None, desc_wise=False):
+        """x: fp32 clip (B,3,T,H,W) as in the reference, or -- after self.visual.set_input_norm(mean, std) -- the
+        decoder's uint8 frames (B,T,H,W,3), normalised on the fly inside the patch gather."""
         ff, st, B, T = self.visual.frames_forward(x)
         dev = ff.device
         if self.use_text_prompt_learning:

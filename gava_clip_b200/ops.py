@@ -276,3 +276,17 @@ def causal_attention_f32(qkv: Tensor, out: Tensor, *, n_seq: int, L: int, H: int
     rc = _lib.load().gava_causal_attention_f32_fwd(qkv.data_ptr(), out.data_ptr(), n_seq, L, H, _stream())
     _lib.check(rc, "gava_causal_attention_f32_fwd")
     return out
+
+
+def patch_gather_u8(frames: Tensor, hi: Tensor, lo: Optional[Tensor], mean, std, patch: int) -> None:
+    """uint8 frames [B,T,H,W,3] -> normalised bf16 patch rows (input stage fused into the gather); mean/std: 3 floats."""
+    _req(frames, torch.uint8, "patch_gather_u8 frames"); _req(hi, torch.bfloat16, "patch_gather_u8 hi")
+    assert frames.is_contiguous() and frames.dim() == 5 and frames.shape[-1] == 3 and hi.is_contiguous()
+    B, T, H, W, _ = frames.shape
+    assert hi.shape[0] == B * T * (H // patch) * (W // patch)
+    if lo is not None:
+        _req(lo, torch.bfloat16, "patch_gather_u8 lo"); assert lo.is_contiguous() and lo.shape == hi.shape
+    m = (C.c_float * 3)(*[float(v) for v in mean]); s = (C.c_float * 3)(*[float(v) for v in std])
+    rc = _lib.load().gava_patch_gather_u8_fwd(frames.data_ptr(), hi.data_ptr(), _ptr(lo), m, s, B, T, H, W, patch,
+                                              hi.shape[1], _stream())
+    _lib.check(rc, "gava_patch_gather_u8_fwd")

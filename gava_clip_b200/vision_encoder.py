@@ -119,6 +119,15 @@ def _ceil_to(v: int, m: int) -> int:
     return (v + m - 1) // m * m
 
 
+def _clip_dims(video: Tensor) -> Tuple[int, int, int, int]:
+    """(B, T, H, W) of a float clip (B,3,T,H,W) or a uint8 decoder-layout clip (B,T,H,W,3)."""
+    if video.dtype == torch.uint8:
+        B, T, H, W, _ = video.shape
+    else:
+        B, _, T, H, W = video.shape
+    return B, T, H, W
+
+
 class TowerEngine:
     """Packed weights + workspaces + kernel schedule for one CLIPVisionEncoder on one GPU."""
 
@@ -262,14 +271,14 @@ class TowerEngine:
         return W
 
     # ------------------------------------------------------------------ CUDA-graph replay
-    def input_buffer(self, shape) -> Tensor:
-        """Static fp32 clip buffer of the captured graph for this shape: callers that fill it directly (e.g. an
+    def input_buffer(self, shape, dtype=torch.float32) -> Tensor:
+        """Static clip buffer of the captured graph for this shape: callers that fill it directly (e.g. an
         H2D copy from pinned memory) and then pass it to forward() skip the staging copy."""
         key = tuple(shape)
         ent = self.graphs.get(key)
         if ent is not None:
             return ent[1]
-        return torch.empty(*shape, device=self.device, dtype=torch.float32)
+        return torch.empty(*shape, device=self.device, dtype=dtype)
 
     def run(self, video: Tensor) -> Tuple[Tensor, Tensor]:
         """encode_frames, replayed from a CUDA graph per clip shape (launch-bound inner loop: ~190 launches)."""
@@ -300,7 +309,8 @@ class TowerEngine:
             static_in.copy_(video)
         g.replay()
         self.launches_last_call = n_launch
-        W = self.ws[(video.shape[0], video.shape[2])]
+        B, T, _, _ = _clip_dims(video)
+        W = self.ws[(B, T)]
         return W["frame_feat"], W["summary"]
 
     # ------------------------------------------------------------------ schedule
@@ -310,7 +320,7 @@ class TowerEngine:
         Everything up to (not including) the temporal mean of vision_encoder.py:128-130.
         """
         e, P = self.enc, self.packed
-        B, _, T, Hh, Ww = video.shape
+        B, T, Hh, Ww = _clip_dims(video)
         D, N0, G, H = e.feature_dim, int(e.num_patches), e.num_global_prompts, e.num_heads
         BT = B * T
         M = BT * N0
@@ -319,7 +329,10 @@ class TowerEngine:
         x, xn, qkv, h = W["x"], W["xn"], W["qkv"], W["h"]
 
         # patch embedding (+bias +pos +time), cls rows, ln_pre          vision_encoder.py:105-113
-        ops.patch_gather(video, W["patches"], e.patch_embed.patch_size)
+        if video.dtype == torch.uint8:     # input stage fused into the gather
+            ops.patch_gather_u8(video, W["patches"], None, e.input_norm[0], e.input_norm[1], e.patch_embed.patch_size)
+        else:
+            ops.patch_gather(video, W["patches"], e.patch_embed.patch_size)
         ops.gemm(W["patches"], P["patch.w"], x, mode=ops.EPI_PATCH_F32, bias=P["patch.b"], pos=P["pos_embed"],
                  time_embed=te, group=N0 - 1, group_stride=N0, row_offset=1, T=T)
         ops.cls_rows(x, N0, P["cls_token"], P["pos_embed"], te, BT, T)
@@ -416,7 +429,7 @@ class TowerEngine:
         """Same schedule as encode_frames with fp32 activations; every contraction is a 3-term split-bf16 product."""
         e, P = self.enc, self.packed
         Q = self.pack_precise()
-        B, _, T, _, _ = video.shape
+        B, T, _, _ = _clip_dims(video)
         D, N0, G, H = e.feature_dim, int(e.num_patches), e.num_global_prompts, e.num_heads
         BT, M = B * T, B * T * N0
         W = self._ws_precise(B, T)
@@ -437,7 +450,10 @@ class TowerEngine:
         kp = Q["patch.w"][0].shape[1]
         hi = W["hi"][: BT * (N0 - 1) * kp].view(-1, kp)
         lo = W["lo"][: BT * (N0 - 1) * kp].view(-1, kp)
-        ops.patch_gather_split(video, hi, lo, e.patch_embed.patch_size)
+        if video.dtype == torch.uint8:
+            ops.patch_gather_u8(video, hi, lo, e.input_norm[0], e.input_norm[1], e.patch_embed.patch_size)
+        else:
+            ops.patch_gather_split(video, hi, lo, e.patch_embed.patch_size)
         ops.gemm3(hi, lo, *Q["patch.w"], W["ptmp"], bias=P["patch.b"])
         ops.embed_assemble(W["ptmp"], x, P["pos_embed"], te, BT, T, N0 - 1)
         ops.cls_rows(x, N0, P["cls_token"], P["pos_embed"], te, BT, T)
@@ -513,6 +529,16 @@ class CLIPVisionEncoder(nn.Module):
             nn.init.normal_(p, std=0.02)
         self._engine: Optional[TowerEngine] = None
         self.precision = os.environ.get("GAVA_PRECISION", "bf16")
+        # (mean[3], std[3]) of the input stage; when set, forward() also accepts the decoder's uint8 (B,T,H,W,3) clips
+        # and normalises them on the fly (video_dataset/dataset.py:117-122; dataloader defaults 0.45 / 0.225)
+        self.input_norm = None
+
+    def set_input_norm(self, mean, std) -> None:
+        mean, std = [float(v) for v in mean], [float(v) for v in std]
+        if len(mean) == 1:
+            mean, std = mean * 3, std * 3
+        assert len(mean) == 3 and len(std) == 3 and all(v > 0 for v in std)
+        self.input_norm = (mean, std)
 
     # -- engine plumbing ---------------------------------------------------------------------------
     def engine(self, device: torch.device) -> TowerEngine:
@@ -527,24 +553,31 @@ class CLIPVisionEncoder(nn.Module):
         return self._engine
 
     def _check_input(self, x: Tensor) -> Tensor:
-        if x.dim() != 5 or x.shape[1] != 3:
+        u8 = x.dtype == torch.uint8
+        if u8:
+            if x.dim() != 5 or x.shape[-1] != 3:
+                raise ValueError(f"expected uint8 clip of shape (B,T,H,W,3), got {tuple(x.shape)}")
+            if self.input_norm is None:
+                raise RuntimeError("uint8 clips need set_input_norm(mean, std) first")
+        elif x.dim() != 5 or x.shape[1] != 3:
             raise ValueError(f"expected video of shape (B,3,T,H,W), got {tuple(x.shape)}")
         if not x.is_cuda:
             raise RuntimeError("gava_clip_b200 runs on sm_100a only: move the clip to a CUDA device "
                                "(there is no CPU fallback)")
-        if x.shape[2] != self.num_frames:
+        if x.shape[1 if u8 else 2] != self.num_frames:
             # the reference blocks hard-code num_frames (utils.py:161): other lengths mis-shape its views
-            raise ValueError(f"clip has T={x.shape[2]} frames but the encoder was built with num_frames={self.num_frames}")
+            raise ValueError(f"clip has T={x.shape[1 if u8 else 2]} frames but the encoder was built with num_frames={self.num_frames}")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
             raise NotImplementedError("backward kernels are not part of this build: call under torch.no_grad() / eval()")
-        return x.contiguous().float()
+        return x.contiguous() if u8 else x.contiguous().float()
 
     def frames_forward(self, x: Tensor) -> Tuple[Tensor, Tensor, int, int]:
         """per-frame projected cls features [BT, E(+pad)] and summary tokens [BT, D] (workspace views)."""
         x = self._check_input(x)
         eng = self.engine(x.device)
         ff, st = eng.run(x)
-        return ff, st, x.shape[0], x.shape[2]
+        B, T, _, _ = _clip_dims(x)
+        return ff, st, B, T
 
     def forward(self, x: Tensor):
         ff, st, B, T = self.frames_forward(x)

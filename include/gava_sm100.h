@@ -75,6 +75,13 @@ int gava_layernorm_fwd(const float* x, int64_t in_row_stride, const float* weigh
 int gava_patch_gather_fwd(const float* video, void* A, int32_t B, int32_t T, int32_t H, int32_t W, int32_t P,
                           int32_t Kpad, void* stream);
 
+/* Input stage fused into the patch gather: decoder output uint8 [B,T,H,W,3] (HWC, as PyAV's to_ndarray) ->
+ * (u/255 - mean[c]) / std[c] in f32 -> bf16 patch rows `hi` (and, if lo != NULL, the bf16 remainder for the fp32 path).
+ * mean/std: HOST pointers to 3 floats each.  Replaces `frames.float()/255; (frames-mean)/std; permute`
+ * video_dataset/dataset.py:117-122 plus gava_patch_gather_fwd. */
+int gava_patch_gather_u8_fwd(const uint8_t* frames, void* hi, void* lo, const float* mean, const float* std, int32_t B,
+                             int32_t T, int32_t H, int32_t W, int32_t P, int32_t Kpad, void* stream);
+
 /* cls rows of the embedded stream: x[f*tokens_per_frame + 0, :] = cls_token + pos_embed[0] + time_embed[f % T].
  * Replaces the cls concat + broadcasts, VitaCLIP_vision_encoder.py:108-111. */
 int gava_cls_rows_fwd(float* x, int32_t tokens_per_frame, const float* cls_token, const float* pos_embed,

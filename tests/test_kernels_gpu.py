@@ -319,3 +319,24 @@ def test_prompt_rows_f32_and_patch_gather_split(cuda):
     ops.patch_gather_split(v, hi, lo, 14)
     ref = F.unfold(v.permute(0, 2, 1, 3, 4).flatten(0, 1), kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
     assert _rel(hi[:, :588].float() + lo[:, :588].float(), ref) < 2e-5 and (hi[:, 588:] == 0).all() and (lo[:, 588:] == 0).all()
+
+
+@pytest.mark.parametrize("P,H,Kpad", [(16, 224, 768), (14, 56, 640)])
+def test_patch_gather_u8(cuda, P, H, Kpad):
+    """uint8 HWC frames -> (u/255 - mean)/std -> bf16 patch rows, bit-identical to normalising on the host in fp32."""
+    from gava_clip_b200 import ops
+    g = torch.Generator().manual_seed(P)
+    B, T = 2, 3
+    u8 = torch.randint(0, 256, (B, T, H, H, 3), dtype=torch.uint8, generator=g).to(cuda)
+    mean, std = [0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711]
+    gh = H // P
+    hi = torch.full((B * T * gh * gh, Kpad), 7.0, device=cuda, dtype=torch.bfloat16)
+    ops.patch_gather_u8(u8, hi, None, mean, std, P)
+    x = (u8.float() / 255.0 - torch.tensor(mean, device=cuda)) / torch.tensor(std, device=cuda)      # (B,T,H,W,3)
+    frames = x.permute(0, 1, 4, 2, 3).flatten(0, 1)
+    ref = F.unfold(frames, kernel_size=P, stride=P).transpose(1, 2).reshape(-1, 3 * P * P)
+    assert torch.equal(hi[:, :3 * P * P], ref.bfloat16())
+    lo = torch.empty_like(hi); hi2 = torch.empty_like(hi)
+    ops.patch_gather_u8(u8, hi2, lo, mean, std, P)                                                   # hi/lo (fp32 path)
+    assert torch.equal(hi2[:, :3 * P * P], ref.bfloat16())
+    assert _rel(hi2[:, :3 * P * P].float() + lo[:, :3 * P * P].float(), ref) < 2e-5

@@ -184,3 +184,39 @@ def test_long_clip_recipe_shape_against_oracle(cuda):
     assert rel_err(logits, ref["logits"]) < TOL
     assert rel_l2(model.video_features, ref["video_features"]) < TOL
     assert rel_l2(model.summary, ref["summary"]) < TOL
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_uint8_input_stage(cuda, precision):
+    """uint8 (B,T,H,W,3) clips normalised inside the patch gather == the float path fed the host-normalised clip
+    (video_dataset/dataset.py:117-122), for both the vectorised and the hi/lo gather kernels; also vs the CPU oracle."""
+    from oracle import vita_oracle as vo
+    model, kw, B = build_model("tiny", device=cuda)
+    model.visual.precision = precision
+    mean, std = [0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711]
+    model.visual.set_input_norm(mean, std)
+    u8 = torch.randint(0, 256, (3, 3, 64, 64, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(3))
+    clip = ((u8.float() / 255.0 - torch.tensor(mean)) / torch.tensor(std)).permute(0, 4, 1, 2, 3).contiguous()
+    with torch.no_grad():
+        a = model(u8.to(cuda))[0].clone()
+        b = model(clip.to(cuda))[0].clone()
+    assert torch.allclose(a, b, atol=1e-5, rtol=0)
+    cpu = build_model("tiny")[0]
+    sd = {k: v.detach() for k, v in cpu.state_dict().items()}
+    ref = vo.vita_forward(sd, clip, cpu.tokenized_prompts, num_frames=3, num_heads=2, num_layers=2, text_heads=2,
+                          text_layers=2, n_ctx=8)["logits"]
+    assert rel_err(a, ref) < (TOL if precision == "bf16" else 1e-3)
+
+
+def test_clip_streamer_uint8(cuda):
+    from gava_clip_b200 import ClipStreamer
+    model, kw, B = build_model("tiny", device=cuda)
+    model.visual.set_input_norm([0.45], [0.225])
+    g = torch.Generator().manual_seed(5)
+    batches = [torch.randint(0, 256, (4, 3, 64, 64, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(3)]
+    with torch.no_grad():
+        direct = [model(b.to(cuda))[0].cpu().clone() for b in batches]
+    st = ClipStreamer(model)
+    for a, b in zip([o.clone() for o in st.run(batches)], direct):
+        assert torch.equal(a, b)
+    assert st.h2d_bytes == sum(b.numel() for b in batches)
