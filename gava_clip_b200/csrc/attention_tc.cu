@@ -61,49 +61,6 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-      "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-// ---- softmax building blocks; a chunk is 32 keys of one query row (the thread's row)
-template <bool MASK>
-__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int j0, int v0, int v1, int v2, float mx) {
-  float m0 = mx, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < 32; j += 4) {
-    float a0 = __uint_as_float(v[j]), a1 = __uint_as_float(v[j + 1]), a2 = __uint_as_float(v[j + 2]), a3 = __uint_as_float(v[j + 3]);
-    if (MASK) {
-      const int k = j0 + j;
-      if (!(k < v0 || (k >= v1 && k <= v2))) a0 = -INFINITY;
-      if (!(k + 1 < v0 || (k + 1 >= v1 && k + 1 <= v2))) a1 = -INFINITY;
-      if (!(k + 2 < v0 || (k + 2 >= v1 && k + 2 <= v2))) a2 = -INFINITY;
-      if (!(k + 3 < v0 || (k + 3 >= v1 && k + 3 <= v2))) a3 = -INFINITY;
-    }
-    m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1); m2 = fmaxf(m2, a2); m3 = fmaxf(m3, a3);
-  }
-  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-}
-template <bool MASK>
-__device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], uint32_t (&pk)[16], int j0, int v0, int v1, int v2,
-                                           float c, float mc) {
-  float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    float p0 = exp2f(fmaf(__uint_as_float(v[j]), c, -mc));
-    float p1 = exp2f(fmaf(__uint_as_float(v[j + 1]), c, -mc));
-    if (MASK) {
-      const int k = j0 + j;
-      if (!(k < v0 || (k >= v1 && k <= v2))) p0 = 0.f;
-      if (!(k + 1 < v0 || (k + 1 >= v1 && k + 1 <= v2))) p1 = 0.f;
-    }
-    s0 += p0; s1 += p1;
-    pk[j >> 1] = pack_bf16x2(p0, p1);
-  }
-  return s0 + s1;
-}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // MN-major (rows = K index, 64 contiguous N elements per 128-byte row) smem descriptor, 128-byte swizzle:

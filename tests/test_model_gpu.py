@@ -220,3 +220,27 @@ def test_clip_streamer_uint8(cuda):
     for a, b in zip([o.clone() for o in st.run(batches)], direct):
         assert torch.equal(a, b)
     assert st.h2d_bytes == sum(b.numel() for b in batches)
+
+
+def test_full_size_config2_properties(cuda):
+    """BASELINE.json configs[1] at full size (ViT-B/16, 8 frames, batch 64): size-independent properties.
+    (i) the two golden clips placed inside the 64-batch reproduce the reference logits; (ii) duplicated clips give
+    bit-identical rows (clips are independent, no cross-batch arithmetic); (iii) a 2-clip call returns exactly the rows of
+    the 64-clip call (per-element reduction order does not depend on the batch size); (iv) replay is deterministic."""
+    g = load_golden("b16_t8")
+    model, kw, B = build_model("b16_t8", device=cuda)
+    gold = fx.make_inputs("b16_t8")["video"]
+    gen = torch.Generator().manual_seed(99)
+    batch = torch.randn(64, 3, 8, 224, 224, generator=gen)
+    batch[10], batch[41] = gold[0], gold[1]
+    batch[63] = batch[7]
+    batch = batch.to(cuda)
+    with torch.no_grad():
+        full = model(batch)[0].clone()
+        again = model(batch)[0].clone()
+        pair = model(batch[[10, 41]].contiguous())[0].clone()
+    assert torch.isfinite(full).all()
+    assert rel_err(full[[10, 41]], g["logits"]) < TOL
+    assert torch.equal(full[63], full[7])
+    assert torch.equal(pair, full[[10, 41]])
+    assert torch.equal(full, again)
