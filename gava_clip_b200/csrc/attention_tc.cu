@@ -7,7 +7,7 @@
 //                P_w (bf16, unnormalised probabilities) overwrites S_w in place, each key-column half inside its own
 //                columns (keys [0,NK/2) -> cols [0,NK/4), keys [NK/2,NK) -> cols [NK/2, 3NK/4));
 //                O_w = P_w V (128 x 64 fp32) lives at columns +192..+255 of the same region
-//   roles      : warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 3-18 softmax/output:
+//   roles      : warp 0 TMA producer, warps 1/2 MMA issuers of query tile 0/1 (warp 2 also allocates TMEM), warps 3-18 softmax/output:
 //                8 warps per query tile, TWO threads per query row (each owns one half of the key columns; row max and
 //                row sum are exchanged through shared memory), so four independent softmax streams hide the
 //                TMEM-load / MUFU latency chains
@@ -150,7 +150,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], n_units);   // one tcgen05.commit per query tile
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], 256);
       mbar_init(&o_full[i], 1);
@@ -197,9 +197,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers: warp 1 drives query tile 0, warp 2 query tile 1 =====================
+    // One in-order issuer for both tiles would couple them (S of tile 0 for the next item could not be issued while the
+    // issuer waits for tile 1's probabilities); with one issuer per tile the two softmax groups run fully decoupled.
+    const int w = warp - 1;
+    if (lane == 0 && w < n_units) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, NK);
       constexpr uint32_t idesc_o = make_idesc_bf16_bmn(128, 64);
       int st = 0;
@@ -212,36 +215,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         uint8_t* sK = sQ + 2 * ATC_QTILE_BYTES;
         uint8_t* sV = sK + kKVBytes;
         { ATC_T0(); mbar_wait(&kv_full[st], ph); ATC_ACC(d_kv); }
+        { ATC_T0(); mbar_wait(&s_free[w], it_ph ^ 1u); ATC_ACC(d_sfree); }
         tc_fence_after();
         const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK));
-        for (int w = 0; w < n_units; ++w) {
-          { ATC_T0(); mbar_wait(&s_free[w], it_ph ^ 1u); ATC_ACC(d_sfree); }
-          tc_fence_after();
-          const uint64_t dq = make_sw128_kmajor_desc(smem_u32(sQ + w * ATC_QTILE_BYTES));
+        const uint64_t dq = make_sw128_kmajor_desc(smem_u32(sQ + w * ATC_QTILE_BYTES));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16_ss(tmem_base + (uint32_t)(w * 256), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
-          umma_commit(&s_full[w]);
-        }
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_ss(tmem_base + (uint32_t)(w * 256), dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
+        umma_commit(&s_full[w]);
         const uint64_t dv = make_sw128_mnmajor_desc(smem_u32(sV), (uint32_t)kKVBytes);
-        for (int w = 0; w < n_units; ++w) {
-          { ATC_T0(); mbar_wait(&p_ready[w], it_ph); ATC_ACC(d_pready); }
-          tc_fence_after();
+        { ATC_T0(); mbar_wait(&p_ready[w], it_ph); ATC_ACC(d_pready); }
+        tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < NK / 16; ++k) {  // 16 keys per MMA; V advances 16 rows (2048 B); P of key half 0 sits at
-            // columns 8k, P of key half 1 at NK/2 + 8(k - NK/32) (each half writes P inside its own S columns)
-            const int pcol = k < NK / 32 ? 8 * k : NK / 2 + 8 * (k - NK / 32);
-            umma_bf16_ts(tmem_base + (uint32_t)(w * 256 + 192), tmem_base + (uint32_t)(w * 256 + pcol),
-                         dv + (uint64_t)(128 * k), idesc_o, (uint32_t)(k != 0));
-          }
-          umma_commit(&o_full[w]);
+        for (int k = 0; k < NK / 16; ++k) {  // 16 keys per MMA; V advances 16 rows (2048 B); P of key half 0 sits at
+          // columns 8k, P of key half 1 at NK/2 + 8(k - NK/32) (each half writes P inside its own S columns)
+          const int pcol = k < NK / 32 ? 8 * k : NK / 2 + 8 * (k - NK / 32);
+          umma_bf16_ts(tmem_base + (uint32_t)(w * 256 + 192), tmem_base + (uint32_t)(w * 256 + pcol),
+                       dv + (uint64_t)(128 * k), idesc_o, (uint32_t)(k != 0));
         }
-        umma_commit(&kv_empty[st]);
+        umma_commit(&o_full[w]);
+        umma_commit(&kv_empty[st]);   // one arrival per tile: the stage is free once both tiles' MMAs have retired
         it_ph ^= 1u;
         if (++st == 2) { st = 0; ph ^= 1u; }
       }
 #if GAVA_ATTN_DEBUG
-      if (blockIdx.x == 3) printf("[attn mma] total %lld: wait kv_full %lld, s_free %lld, p_ready %lld\n", clock64() - d_start, d_kv, d_sfree, d_pready);
+      if (blockIdx.x == 3) printf("[attn mma %d] total %lld: wait kv_full %lld, s_free %lld, p_ready %lld\n", w, clock64() - d_start, d_kv, d_sfree, d_pready);
 #endif
     }
     __syncwarp();
@@ -283,18 +281,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         }
         // ---- pass 1: maximum over this thread's half of the keys, then exchange with the partner thread
         float mx = -INFINITY;
-        {
-          uint32_t va[16], vb[16];
+        {   // the reduction per chunk is ~16 instructions, far shorter than a TMEM load: keep THREE loads in flight
+          uint32_t va[16], vb[16], vc[16];
+          constexpr int NCH = HALF / 16;
           tmem_ld_32x16(t_mine, va);
+          if (NCH > 1) tmem_ld_32x16(t_mine + 16u, vb);
+          if (NCH > 2) tmem_ld_32x16(t_mine + 32u, vc);
 #pragma unroll
-          for (int ch = 0; ch < HALF / 16; ++ch) {
-            tmem_ld_wait();
-            uint32_t (&cur)[16] = (ch & 1) ? vb : va;
-            uint32_t (&nxt)[16] = (ch & 1) ? va : vb;
-            if (ch + 1 < HALF / 16) tmem_ld_32x16(t_mine + (uint32_t)((ch + 1) * 16), nxt);
+          for (int ch = 0; ch < NCH; ++ch) {
+            // tcgen05.wait::ld waits for ALL outstanding loads of the thread, so loads are issued in groups of three
+            if (ch % 3 == 0) tmem_ld_wait();
+            uint32_t (&cur)[16] = (ch % 3 == 0) ? va : ((ch % 3 == 1) ? vb : vc);
             const int j0 = hh * HALF + ch * 16;
             if (j0 + 16 <= v0) mx = chunk16_max<false>(cur, j0, v0, v1, v2, mx);
             else mx = chunk16_max<true>(cur, j0, v0, v1, v2, mx);
+            if (ch % 3 == 2 && ch + 1 < NCH) {   // group consumed: issue the next three
+              tmem_ld_32x16(t_mine + (uint32_t)((ch + 1) * 16), va);
+              if (ch + 2 < NCH) tmem_ld_32x16(t_mine + (uint32_t)((ch + 2) * 16), vb);
+              if (ch + 3 < NCH) tmem_ld_32x16(t_mine + (uint32_t)((ch + 3) * 16), vc);
+            }
           }
         }
         *my_max = mx;
