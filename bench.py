@@ -211,9 +211,12 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the sm_100a path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    saved_stdout = None
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"       # keep stdout to the single JSON line (no "NCCL version ..." banner)
+        # NCCL prints a "NCCL version ..." banner on the C-level stdout: park fd 1 on stderr until the JSON line is due
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().gava_init(), "gava_init")
 
@@ -339,6 +342,9 @@ def run_ours(args):
         cps, sec, cores = cpu_port_clips_per_s(T, 5, 1)
         line["cpu_baseline"] = {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port",
                                 "sample": f"5 forwards of 1 clip ({T}x224x224, fp32, config 1) after 1 warm-up, median {sec:.3f} s"}
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
