@@ -630,11 +630,16 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
   }
   const int bn = (N % 256 == 0) ? 256 : 128;
   static const bool use_pair = [] { const char* e = getenv("GAVA_GEMM_PAIR"); return !(e && e[0] == '0'); }();
-  const bool pair = use_pair && bn == 256;   // CTA-pair kernel for every N % 256 == 0 shape
+  // CTA-pair kernel for every N % 256 == 0 shape; the handful-of-tiles GEMMs of the temporal-message chain (M = B*T rows)
+  // are latency-bound and spread over more SMs with the single-CTA 128x128 tiles (GAVA_SMALL_M: row threshold)
+  static const long long small_m = [] { const char* e = getenv("GAVA_SMALL_M"); return e ? atoll(e) : 2048LL; }();
+  const bool small = M <= small_m;
+  const bool pair = use_pair && bn == 256 && !small;
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16(&ta, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = make_tmap_bf16(&tb, W, N, K, ldw, pair ? 128 : bn);
+  const int bn_eff = small ? 128 : bn;
+  rc = make_tmap_bf16(&tb, W, N, K, ldw, pair ? 128 : bn_eff);
   if (rc) return rc;
   GemmArgs a;
   a.M = (int)M; a.N = (int)N; a.K = (int)K;
@@ -643,7 +648,7 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
   a.group = epi->group; a.group_stride = epi->group_stride; a.row_offset = epi->row_offset;
   a.pos = epi->pos; a.time_embed = epi->time_embed; a.T = epi->T;
   if (pair) return dispatch_mode2(epi->mode, ta, tb, a, stream);
-  return bn == 256 ? dispatch_mode<256>(epi->mode, ta, tb, a, stream) : dispatch_mode<128>(epi->mode, ta, tb, a, stream);
+  return bn_eff == 256 ? dispatch_mode<256>(epi->mode, ta, tb, a, stream) : dispatch_mode<128>(epi->mode, ta, tb, a, stream);
 }
 
 }  // namespace gava

@@ -238,10 +238,21 @@ class TowerEngine:
         return self.packed[key]
 
     # ------------------------------------------------------------------ workspace
+    MAX_SHAPES = 4    # workspaces / graphs kept alive (an eval loop sees the full batch size and one ragged tail)
+
+    def _evict(self) -> None:
+        """Drop the oldest clip shapes (2.3 GB of workspace each at config 2) once more than MAX_SHAPES were seen."""
+        while len(self.ws) > self.MAX_SHAPES:
+            old = next(iter(self.ws))
+            del self.ws[old]
+            for k in [k for k, v in self.graphs.items() if _clip_dims(v[1])[:2] == old[-2:]]:
+                del self.graphs[k]
+
     def workspace(self, B: int, T: int) -> Dict[str, Tensor]:
         key = (B, T)
         if key in self.ws:
             return self.ws[key]
+        self._evict()
         e, dev = self.enc, self.device
         D, N0, G = e.feature_dim, int(e.num_patches), e.num_global_prompts
         BT = B * T

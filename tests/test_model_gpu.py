@@ -244,3 +244,17 @@ def test_full_size_config2_properties(cuda):
     assert torch.equal(full[63], full[7])
     assert torch.equal(pair, full[[10, 41]])
     assert torch.equal(full, again)
+
+
+def test_many_batch_shapes_are_evicted(cuda):
+    """An eval loop with ragged batch sizes must not accumulate workspaces/graphs without bound."""
+    model, kw, B = build_model("tiny", device=cuda)
+    g = torch.Generator().manual_seed(1)
+    outs = {}
+    with torch.no_grad():
+        for b in (1, 2, 3, 4, 5, 6, 7, 2, 1):
+            v = torch.randn(b, 3, 3, 64, 64, generator=g).to(cuda)
+            outs[b] = model(v)[0].clone()
+            assert outs[b].shape == (b, 3) and torch.isfinite(outs[b]).all()
+    eng = model.visual._engine
+    assert len(eng.ws) <= eng.MAX_SHAPES + 1 and len(eng.graphs) <= eng.MAX_SHAPES + 1
