@@ -148,6 +148,12 @@ class VitaCLIP(nn.Module):
             if not any(k in name for k in ('summary', 'local', 'global', 'time_embed')):
                 p.requires_grad = False
 
+    def freeze_visual(self) -> None:
+        """Freeze the WHOLE video tower, prompts included (not a reference method): enables the text-side-only fine-tune
+        mode of this build, see _forward_text_finetune."""
+        for p in self.visual.parameters():
+            p.requires_grad = False
+
     def _freeze_textual(self):
         for p in self.textual.parameters():
             p.requires_grad = False
@@ -183,12 +189,41 @@ class VitaCLIP(nn.Module):
         ops.head(ff, st, t_hat, offs, vf, so, logits, B=B, T=T, scale=self._scale(), logit_bias=0.0)
         return logits, vf, so
 
+    # ------------------------------------------------------------------ restricted fine-tune mode (text side only)
+    def _text_side_needs_grad(self) -> bool:
+        if not (self.training and torch.is_grad_enabled()):
+            return False
+        return self.logit_scale.requires_grad or any(p.requires_grad for p in self.prompt_learner.parameters())
+
+    def _forward_text_finetune(self, ff: Tensor, st: Tensor, B: int, T: int, memory, video_nte):
+        """Training-mode forward with a FULLY FROZEN video tower (every `visual.*` parameter requires_grad=False; the
+        tower refuses to run otherwise): the video features come from the sm_100a kernels as constants, the text side
+        (prompt learner / KAPT projector -> text transformer -> cosine logits, VitaCLIP_model.py:257-293) runs in PyTorch so
+        that autograd yields the gradients of prompt_learner.*, logit_scale and the memory/NTE heads.  This covers prompt
+        tuning of the text side only; gradients into the visual prompts need the backward kernels (not built)."""
+        dev = ff.device
+        E = self.visual.embed_dim
+        with torch.no_grad():
+            vf = ff[:, :E].reshape(B, T, E).mean(dim=1)
+            summary = st.reshape(B, T, -1).mean(dim=1)
+            v_hat = vf / vf.norm(dim=-1, keepdim=True)
+        t_hat, offs, text_features, counts = self._text_tower.features(dev, need_grad=True)
+        scale = self.logit_scale.exp()
+        logits = torch.cat([(scale * v_hat @ t.t()).mean(-1, keepdim=True) for t in t_hat.split(counts, dim=0)], dim=-1)
+        self.text_features = text_features
+        self.video_features, self.summary = vf, summary
+        if self.logit_bias is not None:
+            logits = logits + self.logit_bias
+        return logits, self._memory_logits(memory), self._nte_logits(summary, video_nte)
+
     # ------------------------------------------------------------------ forward (reference :241-401)
     def forward(self, x: Tensor, memory=None, video_nte=None, desc_wise=False):
         """x: fp32 clip (B,3,T,H,W) as in the reference, or -- after self.visual.set_input_norm(mean, std) -- the
         decoder's uint8 frames (B,T,H,W,3), normalised on the fly inside the patch gather."""
         ff, st, B, T = self.visual.frames_forward(x)
         dev = ff.device
+        if self.use_text_prompt_learning and self._text_side_needs_grad():
+            return self._forward_text_finetune(ff, st, B, T, memory, video_nte)
         if self.use_text_prompt_learning:
             t_hat, offs, text_features, counts = self._text_tower.features(dev)
             if desc_wise:
@@ -213,31 +248,36 @@ class VitaCLIP(nn.Module):
             else:
                 logits = logits + self.logit_bias
 
-        logits_vm = None
-        if self.add_nte and video_nte is not None:                 # reference :311-343
-            sp = self.sum_proj(summary)
-            sp = sp / sp.norm(dim=-1, keepdim=True)
-            with torch.no_grad():
-                valid = (video_nte.sum(dim=-1).sum(dim=-1) != 0).float()
-                valid_mat = valid.unsqueeze(1) * valid.unsqueeze(0)
-            nte = video_nte / video_nte.norm(dim=-1, keepdim=True)
-            sim = torch.bmm(sp.unsqueeze(0).expand(NUM_COMB, -1, -1), nte.permute(1, 2, 0)).mean(0)
-            mat = self.logit_scale_vm * (sim * valid_mat)
-            logits_vm = F.log_softmax(mat, dim=-1) + F.log_softmax(mat, dim=-2)
+        return logits, self._memory_logits(memory), self._nte_logits(summary, video_nte)
 
-        logits_mt = None
-        if self.use_support_memory and memory is not None:         # reference :347-391
-            tfeat = self.text_features.detach() if self.detach_features else self.text_features
-            mem = memory.mean(dim=1)
-            cols = []
-            for cid, mproj in enumerate(self.memory_project):
-                tf = self.tf_project(tfeat[cid])
-                tf = tf / tf.norm(dim=-1, keepdim=True)
-                m = mproj(mem)
-                m = m / m.norm(dim=-1, keepdim=True)
-                cols.append((self.logit_scale_mt * m @ tf.t()).unsqueeze(-1))
-            logits_mt = F.log_softmax(torch.cat(cols, dim=1), dim=-1)
-            if self.logit_bias_mt is not None:
-                logits_mt = logits_mt + self.logit_bias_mt
+    def _nte_logits(self, summary: Tensor, video_nte):
+        """video <-> numeric-text-embedding contrastive head (reference :311-343); tiny, PyTorch."""
+        if not (self.add_nte and video_nte is not None):
+            return None
+        sp = self.sum_proj(summary)
+        sp = sp / sp.norm(dim=-1, keepdim=True)
+        with torch.no_grad():
+            valid = (video_nte.sum(dim=-1).sum(dim=-1) != 0).float()
+            valid_mat = valid.unsqueeze(1) * valid.unsqueeze(0)
+        nte = video_nte / video_nte.norm(dim=-1, keepdim=True)
+        sim = torch.bmm(sp.unsqueeze(0).expand(NUM_COMB, -1, -1), nte.permute(1, 2, 0)).mean(0)
+        mat = self.logit_scale_vm * (sim * valid_mat)
+        return F.log_softmax(mat, dim=-1) + F.log_softmax(mat, dim=-2)
 
-        return logits, logits_mt, logits_vm
+    def _memory_logits(self, memory):
+        """support-memory head (reference :347-391); tiny, PyTorch."""
+        if not (self.use_support_memory and memory is not None):
+            return None
+        tfeat = self.text_features.detach() if self.detach_features else self.text_features
+        mem = memory.mean(dim=1)
+        cols = []
+        for cid, mproj in enumerate(self.memory_project):
+            tf = self.tf_project(tfeat[cid])
+            tf = tf / tf.norm(dim=-1, keepdim=True)
+            m = mproj(mem)
+            m = m / m.norm(dim=-1, keepdim=True)
+            cols.append((self.logit_scale_mt * m @ tf.t()).unsqueeze(-1))
+        logits_mt = F.log_softmax(torch.cat(cols, dim=1), dim=-1)
+        if self.logit_bias_mt is not None:
+            logits_mt = logits_mt + self.logit_bias_mt
+        return logits_mt

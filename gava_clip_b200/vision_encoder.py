@@ -579,7 +579,9 @@ class CLIPVisionEncoder(nn.Module):
             # the reference blocks hard-code num_frames (utils.py:161): other lengths mis-shape its views
             raise ValueError(f"clip has T={x.shape[1 if u8 else 2]} frames but the encoder was built with num_frames={self.num_frames}")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("backward kernels are not part of this build: call under torch.no_grad() / eval()")
+            raise NotImplementedError(
+                "backward kernels for the video tower are not part of this build: run under torch.no_grad()/eval(), or "
+                "freeze every visual parameter (VitaCLIP.freeze_visual()) to fine-tune the text side only")
         return x.contiguous() if u8 else x.contiguous().float()
 
     def frames_forward(self, x: Tensor) -> Tuple[Tensor, Tensor, int, int]:

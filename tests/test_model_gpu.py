@@ -258,3 +258,35 @@ def test_many_batch_shapes_are_evicted(cuda):
             assert outs[b].shape == (b, 3) and torch.isfinite(outs[b]).all()
     eng = model.visual._engine
     assert len(eng.ws) <= eng.MAX_SHAPES + 1 and len(eng.graphs) <= eng.MAX_SHAPES + 1
+
+
+def test_text_side_finetune_gradients(cuda):
+    """Restricted fine-tune mode: frozen video tower on the sm_100a kernels, text side under autograd.  Gradients of the
+    class-specific context and of logit_scale match the CPU oracle (same formulas, fp32 video features)."""
+    import torch.nn.functional as Fn
+    from oracle import vita_oracle as vo
+    model, kw, B = build_model("tiny", device=cuda)
+    video = fx.make_inputs("tiny")["video"]
+    labels = torch.tensor([2, 0])
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model(video.to(cuda))                                  # visual prompts still trainable -> refused, loudly
+    model.freeze_visual()
+    logits = model(video.to(cuda))[0]
+    assert logits.requires_grad
+    Fn.cross_entropy(logits, labels.to(cuda)).backward()
+    g_ctx, g_ls = model.prompt_learner.ctx.grad.cpu(), model.logit_scale.grad.cpu()
+    assert all(p.grad is None for p in model.visual.parameters())
+    # oracle gradients
+    cpu = build_model("tiny")[0]
+    sd = {k: v.detach().clone() for k, v in cpu.state_dict().items()}
+    sd["prompt_learner.ctx"].requires_grad_(True); sd["logit_scale"].requires_grad_(True)
+    with torch.no_grad():
+        v, _ = vo.vision_encoder(sd, video, num_frames=3, num_heads=2, num_layers=2)
+    prompts = vo.assemble_prompts(sd, cpu.tokenized_prompts, 8, kapt=False)
+    tfs = [vo.text_encoder(sd, p, t, heads=2, layers=2) for p, t in zip(prompts, cpu.tokenized_prompts)]
+    ref_logits, _ = vo.logit_head(v, tfs, sd["logit_scale"])
+    Fn.cross_entropy(ref_logits, labels).backward()
+    assert rel_err(logits.detach(), ref_logits.detach()) < TOL
+    assert rel_err(g_ctx, sd["prompt_learner.ctx"].grad) < 3e-2
+    assert rel_err(g_ls, sd["logit_scale"].grad) < 3e-2
