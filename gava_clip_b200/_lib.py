@@ -16,6 +16,7 @@ EPI_BIAS_GELU_BF16 = 1
 EPI_BIAS_RESID_F32 = 2
 EPI_BIAS_F32 = 3
 EPI_PATCH_F32 = 4
+EPI_DGELU_BF16 = 5
 
 
 class GemmEpilogue(C.Structure):
@@ -33,6 +34,8 @@ class GemmEpilogue(C.Structure):
         ("T", C.c_int32),
         ("pos", C.c_void_p),
         ("time_embed", C.c_void_p),
+        ("aux", C.c_void_p),
+        ("ld_aux", C.c_int64),
     ]
 
 
@@ -59,6 +62,14 @@ SIGNATURES = {
     "gava_attention_f32_fwd": [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p],
     "gava_causal_attention_f32_fwd": [_p, _p, _i32, _i32, _i32, _p],
     "gava_prompt_rows_f32_fwd": [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p],
+    "gava_layernorm_bwd": [_p, _i64, _i32, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _f32, _p],
+    "gava_attention_bwd": [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p],
+    "gava_temporal_attention_bwd": [_p, _p, _p, _i32, _i32, _i32, _p],
+    "gava_prompt_rows_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p],
+    "gava_group_sum": [_p, _i64, _i32, _p, _i32, _i32, _i32, _i32, _p],
+    "gava_transpose_bf16": [_p, _i64, _i32, _p, _i32, _i32, _i32, _p],
+    "gava_quickgelu_bf16_fwd": [_p, _p, _i64, _p],
+    "gava_adamw_step": [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _p],
 }
 _RESTYPES = {"gava_last_error_string": C.c_char_p}
 
@@ -80,8 +91,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing -> loud
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.gava_version() != 1:
-        raise RuntimeError(f"libgava_sm100 ABI version {lib.gava_version()} != 1")
+    if lib.gava_version() != 2:
+        raise RuntimeError(f"libgava_sm100 ABI version {lib.gava_version()} != 2")
     _lib = lib
     return lib
 

@@ -125,4 +125,50 @@ int gava_prompt_rows_f32_fwd(const float* global_prompts, const float* local_pro
                          (cudaStream_t)stream);
 }
 
+int gava_layernorm_bwd(const void* dy, int64_t dy_stride, int32_t dy_bf16, const float* x, int64_t x_stride,
+                       const float* weight, const float* add1, int64_t add1_stride, const float* add2,
+                       int64_t add2_stride, float* dx_out, int64_t dx_stride, void* dx_bf16, int64_t dxb_stride,
+                       float* dw, float* db, int64_t rows, int32_t D, float eps, void* stream) {
+  return layernorm_bwd(dy, dy_stride, dy_bf16, x, x_stride, weight, add1, add1_stride, add2, add2_stride, dx_out,
+                       dx_stride, dx_bf16, dxb_stride, dw, db, rows, D, eps, (cudaStream_t)stream);
+}
+
+int gava_attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, void* dqkv,
+                       float* dkv_aux, int32_t B, int32_t T, int32_t N0, int32_t G, int32_t H, void* stream) {
+  return attention_bwd(qkv, kv_aux, out, dout, dqkv, dkv_aux, B, T, N0, G, H, (cudaStream_t)stream);
+}
+
+int gava_temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int32_t B, int32_t T, int32_t H,
+                                void* stream) {
+  return temporal_attention_bwd(qkv, dout, dqkv, B, T, H, (cudaStream_t)stream);
+}
+
+int gava_prompt_rows_bwd(const void* d_rows_n, const float* global_prompts, const float* local_prompts,
+                         const float* cls_proj_out, const float* summary, const float* ln_weight, float* d_global,
+                         float* d_local_cp, float* d_summary, const float* d_summary_ext, int32_t G, int32_t B, int32_t T,
+                         int32_t D, float eps, void* stream) {
+  return prompt_rows_bwd(d_rows_n, global_prompts, local_prompts, cls_proj_out, summary, ln_weight, d_global, d_local_cp,
+                         d_summary, d_summary_ext, G, B, T, D, eps, (cudaStream_t)stream);
+}
+
+int gava_group_sum(const void* in, int64_t ld, int32_t in_bf16, float* out, int32_t outer, int32_t J, int32_t inner,
+                   int32_t D, void* stream) {
+  return group_sum(in, ld, in_bf16, out, outer, J, inner, D, (cudaStream_t)stream);
+}
+
+int gava_transpose_bf16(const void* in, int64_t ld, int32_t in_bf16, void* out, int32_t R, int32_t C, int32_t Rpad,
+                        void* stream) {
+  return transpose_bf16(in, ld, in_bf16, out, R, C, Rpad, (cudaStream_t)stream);
+}
+
+int gava_quickgelu_bf16_fwd(const void* a, void* h, int64_t n, void* stream) {
+  return quickgelu_bf16(a, h, n, (cudaStream_t)stream);
+}
+
+int gava_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream) {
+  return adamw_step(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale,
+                    (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -224,4 +224,12 @@ __device__ __forceinline__ float quick_gelu(float x) {
   return fmaf(h, t, h);
 }
 
+// d/dx [x sigmoid(1.702 x)] = s (1 + 1.702 x (1 - s)), s = sigmoid(1.702 x) = 0.5 (1 + tanh(0.851 x))
+__device__ __forceinline__ float quick_gelu_grad(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+  const float s = fmaf(0.5f, t, 0.5f);
+  return s * fmaf(1.702f * x, 1.0f - s, 1.0f);
+}
+
 }  // namespace gava

@@ -51,6 +51,8 @@ struct GemmArgs {
   const float* pos;     // [group+1, N]
   const float* time_embed;  // [T, N]
   int T;
+  const __nv_bfloat16* aux;  // EPI_DGELU_BF16: fc1 pre-activations bf16 [M, ld_aux]
+  long long ld_aux;
 };
 
 // ---- epilogue: TMEM -> registers (one row per thread) -> swizzled smem staging -> transposed, coalesced global access.
@@ -58,11 +60,19 @@ struct GemmArgs {
 // rows per warp instruction (measured: l1tex 77 % busy, tensor pipe 64 %).  Each warp therefore transposes its
 // 32x32 block through a private 4 KB staging buffer (XOR-swizzled 16-byte chunks: conflict-free both ways) so that
 // every warp-level global load/store covers whole 64/128-byte row segments.
+// (dy0, dy1) * QuickGELU'(a0, a1) on packed bf16 pairs; g'(a) = s (1 + 1.702 a (1 - s)), s = sigmoid(1.702 a)
+__device__ __forceinline__ uint32_t dgelu_mul2(uint32_t dy2, uint32_t a2) {
+  const __nv_bfloat162 d = *reinterpret_cast<const __nv_bfloat162*>(&dy2);
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&a2);
+  return pack_bf16x2(__bfloat162float(d.x) * quick_gelu_grad(__bfloat162float(a.x)),
+                     __bfloat162float(d.y) * quick_gelu_grad(__bfloat162float(a.y)));
+}
+
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage, int row0, int col0,
                                                const uint32_t (&v)[32], const float4 (&resid)[8], const float* bias_s,
                                                int lane) {
-  if constexpr (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16) {
+  if constexpr (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16 || MODE == EPI_DGELU_BF16) {
     float acc[32];
     {  // bias of this chunk from shared memory (staged per tile before the accumulator wait; broadcast LDS.128)
       const float4* b4 = reinterpret_cast<const float4*>(bias_s);
@@ -93,7 +103,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int r = 8 * i + (lane >> 2);
-      const uint4 w = *reinterpret_cast<const uint4*>(stage + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+      uint4 w = *reinterpret_cast<const uint4*>(stage + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+      if constexpr (MODE == EPI_DGELU_BF16) {   // dgrad through QuickGELU: multiply by g'(a1), a1 read coalesced (row segments)
+        if (row0 + r < p.M) {
+          const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.aux + (long long)(row0 + r) * p.ld_aux + col0 + 8 * c));
+          w.x = dgelu_mul2(w.x, a.x); w.y = dgelu_mul2(w.y, a.y); w.z = dgelu_mul2(w.z, a.z); w.w = dgelu_mul2(w.w, a.w);
+        }
+      }
       if (row0 + r < p.M) *reinterpret_cast<uint4*>(obase + (long long)(row0 + r) * p.ldo) = w;
     }
     __syncwarp();
@@ -141,7 +157,7 @@ template <int MODE, int NCH>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage, float* bias_s, uint64_t* tmem_full_bar,
                                               uint32_t full_phase, uint32_t t_addr, int row0, int col_base, int lane,
                                               long long& dbg_wait) {
-  if constexpr (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16) {
+  if constexpr (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16 || MODE == EPI_DGELU_BF16) {
     static_assert(NCH * 32 <= 128, "one float4 per lane covers the warp's columns");
     if (lane < NCH * 8) {
       const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col_base) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -598,6 +614,7 @@ static int dispatch_mode2(int mode, const CUtensorMap& ta, const CUtensorMap& tb
     case EPI_BIAS_RESID_F32: return launch_gemm2<EPI_BIAS_RESID_F32>(ta, tb, a, s);
     case EPI_BIAS_F32: return launch_gemm2<EPI_BIAS_F32>(ta, tb, a, s);
     case EPI_PATCH_F32: return launch_gemm2<EPI_PATCH_F32>(ta, tb, a, s);
+    case EPI_DGELU_BF16: return launch_gemm2<EPI_DGELU_BF16>(ta, tb, a, s);
   }
   set_error("gemm: unknown epilogue mode %d", mode);
   return GAVA_ERR_ARG;
@@ -611,6 +628,7 @@ static int dispatch_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tb,
     case EPI_BIAS_RESID_F32: return launch_gemm<BN, EPI_BIAS_RESID_F32>(ta, tb, a, s);
     case EPI_BIAS_F32: return launch_gemm<BN, EPI_BIAS_F32>(ta, tb, a, s);
     case EPI_PATCH_F32: return launch_gemm<BN, EPI_PATCH_F32>(ta, tb, a, s);
+    case EPI_DGELU_BF16: return launch_gemm<BN, EPI_DGELU_BF16>(ta, tb, a, s);
   }
   set_error("gemm: unknown epilogue mode %d", mode);
   return GAVA_ERR_ARG;
@@ -628,6 +646,7 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
     set_error("gemm: patch epilogue needs pos/time_embed/group/T");
     return GAVA_ERR_ARG;
   }
+  if (epi->mode == EPI_DGELU_BF16 && (!epi->aux || (epi->ld_aux & 7))) { set_error("gemm: dgelu epilogue needs aux (pitch %% 8 == 0)"); return GAVA_ERR_ARG; }
   const int bn = (N % 256 == 0) ? 256 : 128;
   static const bool use_pair = [] { const char* e = getenv("GAVA_GEMM_PAIR"); return !(e && e[0] == '0'); }();
   // CTA-pair kernel for every N % 256 == 0 shape; the handful-of-tiles GEMMs of the temporal-message chain (M = B*T rows)
@@ -647,6 +666,7 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
   a.out = epi->out; a.ldo = epi->ldo;
   a.group = epi->group; a.group_stride = epi->group_stride; a.row_offset = epi->row_offset;
   a.pos = epi->pos; a.time_embed = epi->time_embed; a.T = epi->T;
+  a.aux = reinterpret_cast<const __nv_bfloat16*>(epi->aux); a.ld_aux = epi->ld_aux;
   if (pair) return dispatch_mode2(epi->mode, ta, tb, a, stream);
   return bn_eff == 256 ? dispatch_mode<256>(epi->mode, ta, tb, a, stream) : dispatch_mode<128>(epi->mode, ta, tb, a, stream);
 }

@@ -13,6 +13,7 @@ enum : int {
   EPI_BIAS_RESID_F32 = GAVA_EPI_BIAS_RESID_F32,
   EPI_BIAS_F32 = GAVA_EPI_BIAS_F32,
   EPI_PATCH_F32 = GAVA_EPI_PATCH_F32,
+  EPI_DGELU_BF16 = GAVA_EPI_DGELU_BF16,
 };
 
 int num_sms();
@@ -66,5 +67,24 @@ int causal_attention_f32(const float* qkv, float* out, int n_seq, int L, int H, 
 int prompt_rows_f32(const float* global_prompts, const float* local_prompts, const float* cls_proj_out,
                     const float* summary, const float* ln_w, const float* ln_b, float* out, int G, int B, int T, int D,
                     float eps, cudaStream_t stream);
+
+// ---- fine-tune step: backward + optimizer (backward.cu, attention_bwd.cu)
+int layernorm_bwd(const void* dy, long long dy_stride, int dy_bf16, const float* x, long long x_stride, const float* w,
+                  const float* add1, long long add1_stride, const float* add2, long long add2_stride, float* dx_out,
+                  long long dx_stride, void* dx_bf16, long long dxb_stride, float* dw, float* db, long long rows, int D,
+                  float eps, cudaStream_t stream);
+int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, void* dqkv, float* dkv_aux,
+                  int B, int T, int N0, int G, int H, cudaStream_t stream);
+int temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int B, int T, int H, cudaStream_t stream);
+int prompt_rows_bwd(const void* d_rows_n, const float* global_prompts, const float* local_prompts,
+                    const float* cls_proj_out, const float* summary, const float* ln_w, float* d_global,
+                    float* d_local_cp, float* d_summary, const float* d_summary_ext, int G, int B, int T, int D, float eps,
+                    cudaStream_t stream);
+int group_sum(const void* in, long long ld, int in_bf16, float* out, int outer, int J, int inner, int D,
+              cudaStream_t stream);
+int transpose_bf16(const void* in, long long ld, int in_bf16, void* out, int R, int C, int Rpad, cudaStream_t stream);
+int quickgelu_bf16(const void* a, void* h, long long n, cudaStream_t stream);
+int adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+               float weight_decay, int step, float grad_scale, cudaStream_t stream);
 
 }  // namespace gava

@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_PATCH_F32,
+from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_DGELU_BF16, EPI_PATCH_F32,
                    GemmEpilogue)
 
 Tensor = torch.Tensor
@@ -45,14 +45,14 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
 
 def gemm(a: Tensor, w: Tensor, out: Tensor, *, mode: int, bias: Optional[Tensor] = None,
          resid: Optional[Tensor] = None, pos: Optional[Tensor] = None, time_embed: Optional[Tensor] = None,
-         group: int = 0, group_stride: int = 0, row_offset: int = 0, T: int = 0) -> Tensor:
+         group: int = 0, group_stride: int = 0, row_offset: int = 0, T: int = 0, aux: Optional[Tensor] = None) -> Tensor:
     """out = epilogue(a @ w.T).  a: bf16 [M,K] (row stride free), w: bf16 [N,K], fp32 bias [N]."""
     _req(a, torch.bfloat16, "gemm a"); _req(w, torch.bfloat16, "gemm w")
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K, (a.shape, w.shape)
-    want = torch.bfloat16 if mode in (EPI_BIAS_BF16, EPI_BIAS_GELU_BF16) else torch.float32
+    want = torch.bfloat16 if mode in (EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_DGELU_BF16) else torch.float32
     _req(out, want, "gemm out")
     assert out.dim() == 2 and out.stride(1) == 1 and out.shape[1] >= N
     if bias is not None:
@@ -74,6 +74,10 @@ def gemm(a: Tensor, w: Tensor, out: Tensor, *, mode: int, bias: Optional[Tensor]
         assert M % group == 0 and out.shape[0] >= (M // group) * group_stride
         epi.pos = pos.data_ptr(); epi.time_embed = time_embed.data_ptr()
         epi.group, epi.group_stride, epi.row_offset, epi.T = group, group_stride, row_offset, T
+    elif mode == EPI_DGELU_BF16:
+        _req(aux, torch.bfloat16, "gemm aux")
+        assert aux.dim() == 2 and aux.stride(1) == 1 and aux.shape[0] >= M and aux.shape[1] >= N and out.shape[0] >= M
+        epi.aux = aux.data_ptr(); epi.ld_aux = aux.stride(0)
     else:
         assert out.shape[0] >= M
     rc = _lib.load().gava_gemm_bf16_fwd(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K,
@@ -290,3 +294,118 @@ def patch_gather_u8(frames: Tensor, hi: Tensor, lo: Optional[Tensor], mean, std,
     rc = _lib.load().gava_patch_gather_u8_fwd(frames.data_ptr(), hi.data_ptr(), _ptr(lo), m, s, B, T, H, W, patch,
                                               hi.shape[1], _stream())
     _lib.check(rc, "gava_patch_gather_u8_fwd")
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# fine-tune step: backward + optimizer kernels (csrc/backward.cu, csrc/attention_bwd.cu)
+def layernorm_bwd(dy: Tensor, x: Tensor, weight: Tensor, dx_out: Tensor, *, rows: int, D: int,
+                  dy_stride: Optional[int] = None, x_stride: Optional[int] = None, dx_stride: Optional[int] = None,
+                  add1: Optional[Tensor] = None, add1_stride: Optional[int] = None, add2: Optional[Tensor] = None,
+                  add2_stride: Optional[int] = None, dx_bf16: Optional[Tensor] = None, dxb_stride: Optional[int] = None,
+                  dw: Optional[Tensor] = None, db: Optional[Tensor] = None, eps: float = 1e-5) -> Tensor:
+    """dx_out = [add1] + [add2] + LayerNorm-backward(dy; x, weight); optional bf16 copy and dw/db accumulation.
+    Strides are row pitches in elements (default D): lets callers address e.g. the cls rows of the stream."""
+    assert dy.dtype in (torch.bfloat16, torch.float32) and dy.is_cuda
+    _req(x, torch.float32, "layernorm_bwd x"); _req(weight, torch.float32, "layernorm_bwd weight")
+    _req(dx_out, torch.float32, "layernorm_bwd dx_out")
+    for t in (add1, add2):
+        if t is not None:
+            _req(t, torch.float32, "layernorm_bwd add")
+    if dx_bf16 is not None:
+        _req(dx_bf16, torch.bfloat16, "layernorm_bwd dx_bf16")
+    if dw is not None:
+        _req(dw, torch.float32, "layernorm_bwd dw"); _req(db, torch.float32, "layernorm_bwd db")
+        assert dw.numel() == D and db.numel() == D
+    st = lambda v: D if v is None else v
+    for t, sd in ((dy, st(dy_stride)), (x, st(x_stride)), (dx_out, st(dx_stride))):
+        assert t.numel() >= (rows - 1) * sd + D
+    rc = _lib.load().gava_layernorm_bwd(dy.data_ptr(), st(dy_stride), 1 if dy.dtype == torch.bfloat16 else 0, x.data_ptr(),
+                                        st(x_stride), weight.data_ptr(), _ptr(add1), st(add1_stride), _ptr(add2),
+                                        st(add2_stride), dx_out.data_ptr(), st(dx_stride), _ptr(dx_bf16), st(dxb_stride),
+                                        _ptr(dw), _ptr(db), rows, D, eps, _stream())
+    _lib.check(rc, "gava_layernorm_bwd")
+    return dx_out
+
+
+def attention_bwd(qkv: Tensor, kv_aux: Tensor, out: Tensor, dout: Tensor, dqkv: Tensor, dkv_aux: Tensor, *, B: int,
+                  T: int, N0: int, G: int, H: int) -> None:
+    for t in (qkv, kv_aux, out, dout, dqkv):
+        _req(t, torch.bfloat16, "attention_bwd"); assert t.is_contiguous()
+    _req(dkv_aux, torch.float32, "attention_bwd dkv_aux")
+    D = H * 64
+    assert qkv.shape == (B * T * N0, 3 * D) and dqkv.shape == qkv.shape and out.shape == (B * T * N0, D)
+    assert dout.shape == out.shape and kv_aux.shape == (G + 2 * B * T, 2 * D) and dkv_aux.shape == kv_aux.shape
+    assert dkv_aux.is_contiguous()
+    rc = _lib.load().gava_attention_bwd(qkv.data_ptr(), kv_aux.data_ptr(), out.data_ptr(), dout.data_ptr(), dqkv.data_ptr(),
+                                        dkv_aux.data_ptr(), B, T, N0, G, H, _stream())
+    _lib.check(rc, "gava_attention_bwd")
+
+
+def temporal_attention_bwd(qkv: Tensor, dout: Tensor, dqkv: Tensor, B: int, T: int, H: int) -> Tensor:
+    for t in (qkv, dout, dqkv):
+        _req(t, torch.bfloat16, "temporal_attention_bwd"); assert t.is_contiguous()
+    D = H * 64
+    assert qkv.shape == (B * T, 3 * D) and dqkv.shape == qkv.shape and dout.shape == (B * T, D)
+    rc = _lib.load().gava_temporal_attention_bwd(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, T, H, _stream())
+    _lib.check(rc, "gava_temporal_attention_bwd")
+    return dqkv
+
+
+def prompt_rows_bwd(d_rows_n: Tensor, global_prompts: Tensor, local_prompts: Tensor, cls_proj_out: Tensor, summary: Tensor,
+                    ln_w: Tensor, d_global: Tensor, d_local_cp: Tensor, d_summary: Tensor, d_summary_ext: Optional[Tensor],
+                    B: int, T: int, eps: float = 1e-5) -> None:
+    _req(d_rows_n, torch.bfloat16, "prompt_rows_bwd d_rows_n")
+    for t in (global_prompts, local_prompts, cls_proj_out, summary, ln_w, d_global, d_local_cp, d_summary):
+        _req(t, torch.float32, "prompt_rows_bwd"); assert t.is_contiguous()
+    G, D = global_prompts.shape
+    assert d_rows_n.is_contiguous() and d_rows_n.shape == (G + 2 * B * T, D)
+    assert d_global.shape == (G, D) and d_local_cp.shape == (B * T, D) and d_summary.shape == (B * T, D)
+    if d_summary_ext is not None:
+        _req(d_summary_ext, torch.float32, "prompt_rows_bwd ext"); assert d_summary_ext.is_contiguous() and d_summary_ext.shape == (B * T, D)
+    rc = _lib.load().gava_prompt_rows_bwd(d_rows_n.data_ptr(), global_prompts.data_ptr(), local_prompts.data_ptr(),
+                                          cls_proj_out.data_ptr(), summary.data_ptr(), ln_w.data_ptr(), d_global.data_ptr(),
+                                          d_local_cp.data_ptr(), d_summary.data_ptr(), _ptr(d_summary_ext), G, B, T, D, eps,
+                                          _stream())
+    _lib.check(rc, "gava_prompt_rows_bwd")
+
+
+def group_sum(x: Tensor, out: Tensor, *, outer: int, J: int, inner: int, ld: Optional[int] = None) -> Tensor:
+    """out[j] = sum_{o<outer, n<inner} x[(o*J + j)*inner + n]  (rows of width D = out.shape[-1], pitch ld)."""
+    assert x.dtype in (torch.float32, torch.bfloat16) and x.is_cuda
+    _req(out, torch.float32, "group_sum out"); assert out.is_contiguous()
+    D = out.shape[-1]
+    ld = D if ld is None else ld
+    assert out.numel() == J * D and x.numel() >= (outer * J * inner - 1) * ld + D
+    rc = _lib.load().gava_group_sum(x.data_ptr(), ld, 1 if x.dtype == torch.bfloat16 else 0, out.data_ptr(), outer, J, inner,
+                                    D, _stream())
+    _lib.check(rc, "gava_group_sum")
+    return out
+
+
+def transpose_bf16(x: Tensor, out: Tensor) -> Tensor:
+    """out bf16 [C, Rpad] = x[R, C]^T, zero-padded along R (x: f32 or bf16, row stride free)."""
+    assert x.dtype in (torch.float32, torch.bfloat16) and x.is_cuda and x.dim() == 2 and x.stride(1) == 1
+    _req(out, torch.bfloat16, "transpose out"); assert out.is_contiguous() and out.dim() == 2
+    R, Cc = x.shape
+    assert out.shape[0] == Cc and out.shape[1] >= R
+    rc = _lib.load().gava_transpose_bf16(x.data_ptr(), x.stride(0), 1 if x.dtype == torch.bfloat16 else 0, out.data_ptr(),
+                                         R, Cc, out.shape[1], _stream())
+    _lib.check(rc, "gava_transpose_bf16")
+    return out
+
+
+def quickgelu_bf16(a: Tensor, h: Tensor) -> Tensor:
+    _req(a, torch.bfloat16, "quickgelu a"); _req(h, torch.bfloat16, "quickgelu h")
+    assert a.is_contiguous() and h.is_contiguous() and a.numel() == h.numel()
+    rc = _lib.load().gava_quickgelu_bf16_fwd(a.data_ptr(), h.data_ptr(), a.numel(), _stream())
+    _lib.check(rc, "gava_quickgelu_bf16_fwd")
+    return h
+
+
+def adamw_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, *, lr: float, beta1: float = 0.9, beta2: float = 0.999,
+               eps: float = 1e-8, weight_decay: float = 0.01, step: int = 1, grad_scale: float = 1.0) -> None:
+    for t in (p, g, m, v):
+        _req(t, torch.float32, "adamw"); assert t.is_contiguous() and t.numel() == p.numel()
+    rc = _lib.load().gava_adamw_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr, beta1, beta2,
+                                     eps, weight_decay, step, grad_scale, _stream())
+    _lib.check(rc, "gava_adamw_step")

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define GAVA_ABI_VERSION 1
+#define GAVA_ABI_VERSION 2
 
 /* epilogue modes of gava_gemm_bf16_fwd */
 enum gava_epilogue_mode {
@@ -30,8 +30,9 @@ enum gava_epilogue_mode {
   GAVA_EPI_BIAS_GELU_BF16 = 1, /* out(bf16) = QuickGELU(acc + bias)                       (mlp.fc1 + act)  */
   GAVA_EPI_BIAS_RESID_F32 = 2, /* out(f32)  = resid + acc + bias  (out may alias resid)   (out_proj, fc2)  */
   GAVA_EPI_BIAS_F32 = 3,       /* out(f32)  = acc + bias                                  (cls_proj, proj) */
-  GAVA_EPI_PATCH_F32 = 4       /* out(f32)[(r/group)*group_stride + r%group + row_offset]
+  GAVA_EPI_PATCH_F32 = 4,      /* out(f32)[(r/group)*group_stride + r%group + row_offset]
                                     = acc + bias + pos[1 + r%group] + time_embed[(r/group)%T] (patch embed) */
+  GAVA_EPI_DGELU_BF16 = 5      /* out(bf16) = acc * QuickGELU'(aux[r, c])   (dgrad through mlp.act; aux = fc1 pre-activations) */
 };
 
 typedef struct gava_gemm_epilogue {
@@ -47,6 +48,8 @@ typedef struct gava_gemm_epilogue {
   int32_t T;               /* PATCH: frames per clip */
   const float* pos;        /* PATCH: f32 [group+1, N]  (visual.pos_embed) */
   const float* time_embed; /* PATCH: f32 [T, N]        (visual.time_embed, already resized to T) */
+  const void* aux;         /* DGELU: bf16 [M, ld_aux] */
+  int64_t ld_aux;
 } gava_gemm_epilogue;
 
 int gava_version(void);
@@ -162,6 +165,56 @@ int gava_causal_attention_f32_fwd(const float* qkv, float* out, int32_t n_seq, i
 int gava_prompt_rows_f32_fwd(const float* global_prompts, const float* local_prompts, const float* cls_proj_out,
                              const float* summary, const float* ln_weight, const float* ln_bias, float* out, int32_t G,
                              int32_t B, int32_t T, int32_t D, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fine-tune step: backward through the frozen backbone to the trainable prompt / summary parameters
+ * (VitaCLIP_model.py:230-235), replacing autograd of the ops above, plus the optimizer update (train.py:351,485).
+ * Dense input gradients dX = dY * W reuse gava_gemm_bf16_fwd with W^T packed as the [N,K] operand; the small weight
+ * gradients dW = dY^T X reuse it on operands transposed by gava_transpose_bf16. */
+
+/* LayerNorm input gradient.  Row r: dy at dy + r*dy_stride (bf16 if dy_bf16 else f32), x at x + r*x_stride (the forward
+ * INPUT, f32).  dx_out[r] = (add1 ? add1[r] : 0) + (add2 ? add2[r] : 0) + dLN(dy[r]); dx_out may alias add1.
+ * dx_bf16 (optional): bf16 copy of dx_out (operand of the next dgrad GEMM).  dw/db (optional, both or neither): f32 [D],
+ * atomically accumulated weight / bias gradients (caller zeroes them). */
+int gava_layernorm_bwd(const void* dy, int64_t dy_stride, int32_t dy_bf16, const float* x, int64_t x_stride,
+                       const float* weight, const float* add1, int64_t add1_stride, const float* add2,
+                       int64_t add2_stride, float* dx_out, int64_t dx_stride, void* dx_bf16, int64_t dxb_stride,
+                       float* dw, float* db, int64_t rows, int32_t D, float eps, void* stream);
+
+/* Backward of gava_attention_fwd (all N0 query rows).  out/dout: bf16 [B*T*N0, D] forward output and its gradient.
+ * dqkv: bf16 [B*T*N0, 3D] = [dq | dk | dv] of the live rows; dkv_aux: f32 [G + 2*B*T, 2D] = [dk | dv] of the K/V-only rows
+ * (zeroed and atomically accumulated inside: global rows collect all frames, local rows the T frames of a video). */
+int gava_attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, void* dqkv,
+                       float* dkv_aux, int32_t B, int32_t T, int32_t N0, int32_t G, int32_t H, void* stream);
+
+/* Backward of gava_temporal_attention_fwd: qkv bf16 [B*T, 3D], dout bf16 [B*T, D] -> dqkv bf16 [B*T, 3D].  T <= 128. */
+int gava_temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int32_t B, int32_t T, int32_t H,
+                                void* stream);
+
+/* Backward of gava_prompt_rows_fwd.  d_rows_n: bf16 [G + 2*B*T, D] gradient of the normalised rows.  Outputs (f32):
+ * d_global [G, D]; d_local_cp [B*T, D] (gradient of local_prompts[t] + cls_proj_out[f], per frame);
+ * d_summary [B*T, D] (+ d_summary_ext[f] if given: the gradient arriving at the encoder's summary output). */
+int gava_prompt_rows_bwd(const void* d_rows_n, const float* global_prompts, const float* local_prompts,
+                         const float* cls_proj_out, const float* summary, const float* ln_weight, float* d_global,
+                         float* d_local_cp, float* d_summary, const float* d_summary_ext, int32_t G, int32_t B, int32_t T,
+                         int32_t D, float eps, void* stream);
+
+/* out[j, :] = sum_{o<outer} sum_{n<inner} in[((o*J + j)*inner + n)*ld + :]; in f32 or bf16 (in_bf16), out f32 [J, D]
+ * (time_embed gradient: outer=B, J=T, inner=N0; local_prompts: outer=B, J=T, inner=1; bias: outer=rows, J=1, inner=1). */
+int gava_group_sum(const void* in, int64_t ld, int32_t in_bf16, float* out, int32_t outer, int32_t J, int32_t inner,
+                   int32_t D, void* stream);
+
+/* out bf16 [C, Rpad] = in[R, C]^T (in: f32 or bf16, row pitch ld), columns R..Rpad-1 zero (K padding of a wgrad GEMM). */
+int gava_transpose_bf16(const void* in, int64_t ld, int32_t in_bf16, void* out, int32_t R, int32_t C, int32_t Rpad,
+                        void* stream);
+
+/* h = QuickGELU(a), bf16 -> bf16, n % 8 == 0 (training forward keeps the fc1 pre-activations for the DGELU epilogue). */
+int gava_quickgelu_bf16_fwd(const void* a, void* h, int64_t n, void* stream);
+
+/* Fused AdamW on a flat f32 buffer (torch.optim.AdamW semantics: decoupled decay, bias correction with `step` >= 1);
+ * gradients are multiplied by grad_scale first (1/world_size after a SUM all-reduce).  n % 4 == 0. */
+int gava_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }
