@@ -149,8 +149,8 @@ class VitaCLIP(nn.Module):
                 p.requires_grad = False
 
     def freeze_visual(self) -> None:
-        """Freeze the WHOLE video tower, prompts included (not a reference method): enables the text-side-only fine-tune
-        mode of this build, see _forward_text_finetune."""
+        """Freeze the WHOLE video tower, prompts included (not a reference method): text-side-only fine-tuning; the tower
+        then runs its inference schedule (CUDA-graph replay) inside the training step."""
         for p in self.visual.parameters():
             p.requires_grad = False
 
@@ -189,28 +189,33 @@ class VitaCLIP(nn.Module):
         ops.head(ff, st, t_hat, offs, vf, so, logits, B=B, T=T, scale=self._scale(), logit_bias=0.0)
         return logits, vf, so
 
-    # ------------------------------------------------------------------ restricted fine-tune mode (text side only)
+    # ------------------------------------------------------------------ fine-tune mode
     def _text_side_needs_grad(self) -> bool:
         if not (self.training and torch.is_grad_enabled()):
             return False
+        if not self.use_text_prompt_learning:
+            return self.logit_scale.requires_grad
         return self.logit_scale.requires_grad or any(p.requires_grad for p in self.prompt_learner.parameters())
 
-    def _forward_text_finetune(self, ff: Tensor, st: Tensor, B: int, T: int, memory, video_nte):
-        """Training-mode forward with a FULLY FROZEN video tower (every `visual.*` parameter requires_grad=False; the
-        tower refuses to run otherwise): the video features come from the sm_100a kernels as constants, the text side
-        (prompt learner / KAPT projector -> text transformer -> cosine logits, VitaCLIP_model.py:257-293) runs in PyTorch so
-        that autograd yields the gradients of prompt_learner.*, logit_scale and the memory/NTE heads.  This covers prompt
-        tuning of the text side only; gradients into the visual prompts need the backward kernels (not built)."""
+    def _forward_finetune(self, ff: Tensor, st: Tensor, B: int, T: int, memory, video_nte):
+        """Training-mode forward (train.py:441-443).  The video tower ran on the sm_100a kernels; when any of its trainable
+        parameters requires grad, `ff`/`st` come from train_engine.TowerFunction and loss.backward() drives the backward
+        kernels.  The head -- temporal mean, cosine logits (VitaCLIP_model.py:248-293) -- and the text side (prompt learner
+        / KAPT projector -> text transformer, R description rows) are a few MFLOP..GFLOP and run under PyTorch autograd,
+        which yields the gradients of prompt_learner.*, logit_scale and the memory / NTE heads."""
         dev = ff.device
         E = self.visual.embed_dim
-        with torch.no_grad():
-            vf = ff[:, :E].reshape(B, T, E).mean(dim=1)
-            summary = st.reshape(B, T, -1).mean(dim=1)
-            v_hat = vf / vf.norm(dim=-1, keepdim=True)
-        t_hat, offs, text_features, counts = self._text_tower.features(dev, need_grad=True)
+        vf = ff[:, :E].reshape(B, T, E).mean(dim=1)
+        summary = st.reshape(B, T, -1).mean(dim=1)
+        v_hat = vf / vf.norm(dim=-1, keepdim=True)
         scale = self.logit_scale.exp()
-        logits = torch.cat([(scale * v_hat @ t.t()).mean(-1, keepdim=True) for t in t_hat.split(counts, dim=0)], dim=-1)
-        self.text_features = text_features
+        if self.use_text_prompt_learning:
+            t_hat, offs, text_features, counts = self._text_tower.features(dev, need_grad=self._text_side_needs_grad())
+            logits = torch.cat([(scale * v_hat @ t.t()).mean(-1, keepdim=True) for t in t_hat.split(counts, dim=0)], dim=-1)
+            self.text_features = text_features
+        else:
+            t_hat, _ = self._zeroshot_operand(dev)
+            logits = scale * v_hat @ t_hat.t()
         self.video_features, self.summary = vf, summary
         if self.logit_bias is not None:
             logits = logits + self.logit_bias
@@ -222,8 +227,9 @@ class VitaCLIP(nn.Module):
         decoder's uint8 frames (B,T,H,W,3), normalised on the fly inside the patch gather."""
         ff, st, B, T = self.visual.frames_forward(x)
         dev = ff.device
-        if self.use_text_prompt_learning and self._text_side_needs_grad():
-            return self._forward_text_finetune(ff, st, B, T, memory, video_nte)
+        if self.training and torch.is_grad_enabled() and (ff.requires_grad or self._text_side_needs_grad()):
+            assert not desc_wise
+            return self._forward_finetune(ff, st, B, T, memory, video_nte)
         if self.use_text_prompt_learning:
             t_hat, offs, text_features, counts = self._text_tower.features(dev)
             if desc_wise:

@@ -1,0 +1,303 @@
+"""Fine-tune step of the video tower on the sm_100a kernels (reference: training/train.py:441-494).
+
+The backbone is frozen (VitaCLIP_model.py:230-235): gradients flow THROUGH it (input gradients only, "dgrad") and are
+collected for the parameters the reference leaves trainable -- names containing `summary`, `local`, `global`,
+`time_embed`: visual.time_embed, visual.global_prompts, blocks.{i}.local_prompts, blocks.{i}.summary_ln.*,
+blocks.{i}.summary_attn_layer.{q,k,v,out}_proj.*.
+
+`TowerTrainer` extends the inference `TowerEngine` (vision_encoder.py):
+  * forward_train(video): the same kernel schedule with every layer's activations kept on a tape in HBM (x_in, x_mid fp32;
+    qkv, kv_aux, attention output, fc1 pre-activations bf16; the small temporal-message tensors);
+  * backward(d_frame_feat, d_summary): dgrad GEMMs on pre-transposed frozen weights (tcgen05 GEMM, DGELU epilogue through
+    the MLP), flash-style attention backward, LayerNorm backward kernels, and for the trainable tensors the small wgrad
+    GEMMs (dY^T X on transposed operands), row reductions and the prompt-row scatter.  All gradients land in ONE flat
+    fp32 buffer (`grad_flat`), the unit of the NCCL all-reduce and of the fused AdamW kernel (finetune.py).
+`TowerFunction` exposes the pair to torch.autograd so that the drop-in VitaCLIP.forward -> loss.backward() works unchanged
+(also under DistributedDataParallel, whose hooks fire on the parameters' .grad accumulation).
+
+There is no PyTorch fallback: every arithmetic op of the tower's forward and backward is a kernel behind the C ABI.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .vision_encoder import LN_EPS, TowerEngine, _ceil_to, _clip_dims
+
+Tensor = torch.Tensor
+TRAINABLE_KEYS = ("summary", "local", "global", "time_embed")      # VitaCLIP_model.py:230-235
+
+
+def is_trainable_name(name: str) -> bool:
+    return any(k in name for k in TRAINABLE_KEYS)
+
+
+class TowerTrainer(TowerEngine):
+    # ------------------------------------------------------------------ parameters / gradients
+    def trainable_named(self) -> List[Tuple[str, torch.nn.Parameter]]:
+        """(name, parameter) of the tensors this build can produce gradients for, in named_parameters() order."""
+        return [(n, p) for n, p in self.enc.named_parameters() if is_trainable_name(n)]
+
+    def check_trainable(self) -> None:
+        bad = [n for n, p in self.enc.named_parameters() if p.requires_grad and not is_trainable_name(n)]
+        if bad:
+            raise NotImplementedError(
+                "the sm_100a backward covers the reference's fine-tune recipe (frozen backbone; trainable: names containing "
+                f"{TRAINABLE_KEYS}); these parameters also require grad: {bad[:4]}{'...' if len(bad) > 4 else ''}")
+
+    def _alloc_grads(self) -> None:
+        """One flat fp32 buffer; q/k/v of a summary attention layer are adjacent so one wgrad GEMM fills all three."""
+        if getattr(self, "grad_flat", None) is not None:
+            return
+        e, dev = self.enc, self.device
+        D, L, G, T = e.feature_dim, len(e.blocks), e.num_global_prompts, e.num_frames
+        layout: List[Tuple[str, Tuple[int, ...]]] = [("time_embed", (T, D)), ("global_prompts", (L, G, D))]
+        for i in range(L):
+            k = f"blocks.{i}."
+            layout += [(k + "local_prompts", (1, T, D)), (k + "summary_ln.weight", (D,)), (k + "summary_ln.bias", (D,)),
+                       (k + "sqkv.weight", (3 * D, D)), (k + "sqkv.bias", (3 * D,)),
+                       (k + "summary_attn_layer.out_proj.weight", (D, D)), (k + "summary_attn_layer.out_proj.bias", (D,))]
+        total = sum(int(torch.Size(s).numel()) for _, s in layout)
+        self.grad_flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grads: Dict[str, Tensor] = {}
+        off = 0
+        for name, shape in layout:
+            n = int(torch.Size(shape).numel())
+            self.grads[name] = self.grad_flat[off: off + n].view(shape)
+            off += n
+        for i in range(L):       # per-parameter views of the fused q|k|v blocks
+            k = f"blocks.{i}."
+            w, b = self.grads[k + "sqkv.weight"], self.grads[k + "sqkv.bias"]
+            for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
+                self.grads[k + f"summary_attn_layer.{nm}.weight"] = w[j * D:(j + 1) * D]
+                self.grads[k + f"summary_attn_layer.{nm}.bias"] = b[j * D:(j + 1) * D]
+
+    def grad_of(self, name: str) -> Tensor:
+        return self.grads[name]
+
+    # ------------------------------------------------------------------ transposed frozen weights (dgrad operands)
+    def pack_train(self) -> None:
+        """W^T copies: dX[M,K] = dY[M,N] W[N,K] runs as the forward GEMM with W^T [K,N] as its [N', K'] operand."""
+        self.pack()
+        e, P = self.enc, self.packed
+        vers = self.__dict__.setdefault("_t_versions", {})
+
+        def put_t(name: str, src: Tensor) -> None:
+            key = (src.data_ptr(), src._version)
+            if name in P and vers.get(name) == key:
+                return
+            val = src.detach().t().to(self.device, torch.bfloat16).contiguous()
+            if name in P and P[name].shape == val.shape:
+                P[name].copy_(val)
+            else:
+                P[name] = val
+            vers[name] = key
+
+        D = e.feature_dim
+        if "proj.w" not in P or vers.get("proj.w") != (e.proj.data_ptr(), e.proj._version):
+            pw = torch.zeros(D, _ceil_to(e.embed_dim, 128), device=self.device, dtype=torch.bfloat16)
+            pw[:, : e.embed_dim] = e.proj.detach().to(self.device, torch.bfloat16)
+            P["proj.w"] = pw
+            vers["proj.w"] = (e.proj.data_ptr(), e.proj._version)
+        for i in range(len(e.blocks)):
+            k = f"b{i}."
+            for nm in ("qkv", "out", "fc1", "fc2", "cls", "sqkv", "sout"):
+                put_t(k + nm + ".wT", P[k + nm + ".w"])
+
+    # ------------------------------------------------------------------ tape + scratch
+    def train_ws(self, B: int, T: int) -> Dict[str, object]:
+        key = ("train", B, T)
+        if key in self.ws:
+            return self.ws[key]
+        e, dev = self.enc, self.device
+        D, N0, G, L = e.feature_dim, int(e.num_patches), e.num_global_prompts, len(e.blocks)
+        BT, M = B * T, B * T * N0
+        Dm = e.blocks[0].mlp.fc1.out_features
+        R = G + 2 * BT
+        BTp = _ceil_to(BT, 64)
+        Ep = self.packed["proj.wT"].shape[0]
+        bf, f32 = torch.bfloat16, torch.float32
+        z = lambda *s, dt: torch.empty(*s, device=dev, dtype=dt)
+        per_layer = lambda *s, dt: [z(*s, dt=dt) for _ in range(L)]
+        W: Dict[str, object] = {
+            # ---- tape
+            "x0_pre": z(M, D, dt=f32), "x_in": [z(M, D, dt=f32) for _ in range(L + 1)], "x_mid": per_layer(M, D, dt=f32),
+            "qkv": per_layer(M, 3 * D, dt=bf), "kvaux": per_layer(R, 2 * D, dt=bf), "o": per_layer(M, D, dt=bf),
+            "a1": per_layer(M, Dm, dt=bf), "cls_proj": per_layer(BT, D, dt=f32), "summary": per_layer(BT, D, dt=f32),
+            "sum_n": per_layer(BT, D, dt=bf), "sqkv": per_layer(BT, 3 * D, dt=bf), "smix": per_layer(BT, D, dt=bf),
+            # ---- forward scratch
+            "patches": z(BT * (N0 - 1), self.packed["patch.w"].shape[1], dt=bf), "xn": z(M, D, dt=bf), "h": z(M, Dm, dt=bf),
+            "cls_bf": z(BT, D, dt=bf), "aux_n": z(R, D, dt=bf), "frame_feat": z(BT, Ep, dt=f32),
+            # ---- backward scratch
+            "dx": z(M, D, dt=f32), "dxb": z(M, D, dt=bf), "g4": z(M, Dm, dt=bf), "gD": z(M, D, dt=bf),
+            "dqkv": z(M, 3 * D, dt=bf), "dkvaux": z(R, 2 * D, dt=f32), "dkvaux_bf": z(R, 2 * D, dt=bf),
+            "daux_n": z(R, D, dt=bf), "d_lcp": z(BT, D, dt=f32), "d_sum": z(BT, D, dt=f32), "d_sum_bf": z(BT, D, dt=bf),
+            "dsmix": z(BT, D, dt=bf), "dsqkv": z(BT, 3 * D, dt=bf), "dsn": z(BT, D, dt=bf), "d_cp": z(BT, D, dt=f32),
+            "d_cp_bf": z(BT, D, dt=bf), "tA": z(3 * D, BTp, dt=bf), "tB": z(D, BTp, dt=bf),
+            "dff_bf": z(BT, Ep, dt=bf), "dcls_n": z(BT, D, dt=bf), "dff": z(BT, Ep, dt=f32),
+        }
+        self.ws[key] = W
+        return W
+
+    # ------------------------------------------------------------------ forward with tape
+    def forward_train(self, video: Tensor) -> Tuple[Tensor, Tensor]:
+        """Same schedule as TowerEngine.encode_frames (all layers in full), activations kept for backward()."""
+        self.pack_train()
+        e, P = self.enc, self.packed
+        B, T, _, _ = _clip_dims(video)
+        D, N0, G, H = e.feature_dim, int(e.num_patches), e.num_global_prompts, e.num_heads
+        BT, M = B * T, B * T * N0
+        W = self.train_ws(B, T)
+        te = self.time_embed_for(T)
+        xn, h = W["xn"], W["h"]
+        n0 = ops.launch_count()
+
+        if video.dtype == torch.uint8:
+            ops.patch_gather_u8(video, W["patches"], None, e.input_norm[0], e.input_norm[1], e.patch_embed.patch_size)
+        else:
+            ops.patch_gather(video, W["patches"], e.patch_embed.patch_size)
+        x0 = W["x0_pre"]
+        ops.gemm(W["patches"], P["patch.w"], x0, mode=ops.EPI_PATCH_F32, bias=P["patch.b"], pos=P["pos_embed"],
+                 time_embed=te, group=N0 - 1, group_stride=N0, row_offset=1, T=T)
+        ops.cls_rows(x0, N0, P["cls_token"], P["pos_embed"], te, BT, T)
+        ops.layernorm(x0, P["ln_pre.w"], P["ln_pre.b"], W["x_in"][0], rows=M, in_row_stride=D)
+
+        L = len(e.blocks)
+        for i in range(L):
+            k = f"b{i}."
+            xin, xmid, xnext = W["x_in"][i], W["x_mid"][i], W["x_in"][i + 1]
+            cp, sm = W["cls_proj"][i], W["summary"][i]
+            # temporal message (utils.py:160-188)
+            ops.layernorm(xin, None, None, W["cls_bf"], rows=BT, in_row_stride=N0 * D)
+            ops.gemm(W["cls_bf"], P[k + "cls.w"], cp, mode=ops.EPI_BIAS_F32, bias=P[k + "cls.b"])
+            ops.layernorm(cp, P[k + "summary_ln.w"], P[k + "summary_ln.b"], W["sum_n"][i], rows=BT, in_row_stride=D)
+            ops.gemm(W["sum_n"][i], P[k + "sqkv.w"], W["sqkv"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "sqkv.b"])
+            ops.temporal_attention(W["sqkv"][i], W["smix"][i], B, T, H)
+            ops.gemm(W["smix"][i], P[k + "sout.w"], sm, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "sout.b"], resid=cp)
+            ops.prompt_rows(P["global_prompts"][i], P[k + "local"], cp, sm, P[k + "norm1.w"], P[k + "norm1.b"], W["aux_n"],
+                            B, T, LN_EPS)
+            ops.gemm(W["aux_n"], P[k + "qkv.w"][D:], W["kvaux"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:])
+            # x = x + attn(norm1(x))   (utils.py:190-191)
+            ops.layernorm(xin, P[k + "norm1.w"], P[k + "norm1.b"], xn, rows=M, in_row_stride=D)
+            ops.gemm(xn, P[k + "qkv.w"], W["qkv"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"])
+            ops.attention(W["qkv"][i], W["kvaux"][i], W["o"][i], B=B, T=T, N0=N0, G=G, H=H)
+            ops.gemm(W["o"][i], P[k + "out.w"], xmid, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "out.b"], resid=xin)
+            # x = x + fc2(QuickGELU(fc1(norm2(x))))   (utils.py:199); the pre-activations stay for the DGELU epilogue
+            ops.layernorm(xmid, P[k + "norm2.w"], P[k + "norm2.b"], xn, rows=M, in_row_stride=D)
+            ops.gemm(xn, P[k + "fc1.w"], W["a1"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "fc1.b"])
+            ops.quickgelu_bf16(W["a1"][i], h)
+            ops.gemm(h, P[k + "fc2.w"], xnext, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"], resid=xmid)
+
+        ops.layernorm(W["x_in"][L], P["ln_post.w"], P["ln_post.b"], W["cls_bf"], rows=BT, in_row_stride=N0 * D)
+        ops.gemm(W["cls_bf"], P["proj.wT"], W["frame_feat"], mode=ops.EPI_BIAS_F32)
+        self.launches_last_call = ops.launch_count() - n0
+        return W["frame_feat"], W["summary"][L - 1]
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, B: int, T: int, d_frame_feat: Optional[Tensor], d_summary: Optional[Tensor]) -> Dict[str, Tensor]:
+        """Gradients of the trainable tower parameters given d(frame_feat) [BT, E(+pad)] and d(summary tokens) [BT, D]
+        (either may be None = zero).  Returns self.grads (views into self.grad_flat); uses the tape of the last
+        forward_train call for this (B, T)."""
+        e, P = self.enc, self.packed
+        self._alloc_grads()
+        D, N0, G, H = e.feature_dim, int(e.num_patches), e.num_global_prompts, e.num_heads
+        BT, M = B * T, B * T * N0
+        R = G + 2 * BT
+        L = len(e.blocks)
+        W = self.train_ws(B, T)
+        g = self.grads
+        dx, dxb, gD = W["dx"], W["dxb"], W["gD"]
+        dx_cls = dx.view(BT, N0 * D)[:, :D]
+        n0 = ops.launch_count()
+
+        # ---- frame_feat = ln_post(x_cls) @ proj   (vision_encoder.py:126-127)
+        dx.zero_()
+        if d_frame_feat is not None:
+            Ep = W["dff"].shape[1]
+            dff = W["dff"]
+            if d_frame_feat.shape[1] != Ep:
+                dff.zero_()
+                dff[:, : d_frame_feat.shape[1]].copy_(d_frame_feat)
+            else:
+                dff.copy_(d_frame_feat)
+            ops.layernorm(dff, None, None, W["dff_bf"], rows=BT, in_row_stride=Ep)            # f32 -> bf16 cast
+            ops.gemm(W["dff_bf"], P["proj.w"], W["dcls_n"], mode=ops.EPI_BIAS_BF16)
+            ops.layernorm_bwd(W["dcls_n"], W["x_in"][L], P["ln_post.w"], dx, rows=BT, D=D, x_stride=N0 * D,
+                              dx_stride=N0 * D)
+        ext = None
+        if d_summary is not None:
+            ext = d_summary.contiguous().float()
+
+        for i in reversed(range(L)):
+            k, kb = f"b{i}.", f"blocks.{i}."
+            cp, sm = W["cls_proj"][i], W["summary"][i]
+            # ---- MLP: dx += dLN2( (dx W2 * g'(a1)) W1 )
+            ops.layernorm(dx, None, None, dxb, rows=M, in_row_stride=D)                        # cast
+            ops.gemm(dxb, P[k + "fc2.wT"], W["g4"], mode=ops.EPI_DGELU_BF16, aux=W["a1"][i])
+            ops.gemm(W["g4"], P[k + "fc1.wT"], gD, mode=ops.EPI_BIAS_BF16)
+            ops.layernorm_bwd(gD, W["x_mid"][i], P[k + "norm2.w"], dx, rows=M, D=D, add1=dx, dx_bf16=dxb)
+            # ---- attention: dO = dx Wo; (dq, dk, dv, d kv_aux); dx += dLN1(dqkv Wqkv)
+            ops.gemm(dxb, P[k + "out.wT"], gD, mode=ops.EPI_BIAS_BF16)
+            ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G, H=H)
+            ops.gemm(W["dqkv"], P[k + "qkv.wT"], gD, mode=ops.EPI_BIAS_BF16)
+            ops.layernorm_bwd(gD, W["x_in"][i], P[k + "norm1.w"], dx, rows=M, D=D, add1=dx)
+            # ---- K/V-only prompt rows: d kv_aux -> normalised rows -> global / local / summary / cls_proj gradients
+            ops.layernorm(W["dkvaux"].view(2 * R, D), None, None, W["dkvaux_bf"].view(2 * R, D), rows=2 * R, in_row_stride=D)
+            ops.gemm(W["dkvaux_bf"], P[k + "qkv.wT"][:, D:], W["daux_n"], mode=ops.EPI_BIAS_BF16)
+            ops.prompt_rows_bwd(W["daux_n"], P["global_prompts"][i], P[k + "local"], cp, sm, P[k + "norm1.w"],
+                                g["global_prompts"][i], W["d_lcp"], W["d_sum"], ext if i == L - 1 else None, B, T, LN_EPS)
+            ops.group_sum(W["d_lcp"], g[kb + "local_prompts"], outer=B, J=T, inner=1)
+            # ---- summary = cls_proj + out_proj(temporal_attention(qkv(summary_ln(cls_proj))))   (utils.py:168-170)
+            ops.layernorm(W["d_sum"], None, None, W["d_sum_bf"], rows=BT, in_row_stride=D)     # cast
+            ops.gemm(W["d_sum_bf"], P[k + "sout.wT"], W["dsmix"], mode=ops.EPI_BIAS_BF16)
+            self._wgrad(W, W["d_sum"], W["smix"][i], g[kb + "summary_attn_layer.out_proj.weight"])
+            ops.group_sum(W["d_sum"], g[kb + "summary_attn_layer.out_proj.bias"], outer=BT, J=1, inner=1)
+            ops.temporal_attention_bwd(W["sqkv"][i], W["dsmix"], W["dsqkv"], B, T, H)
+            ops.gemm(W["dsqkv"], P[k + "sqkv.wT"], W["dsn"], mode=ops.EPI_BIAS_BF16)
+            self._wgrad(W, W["dsqkv"], W["sum_n"][i], g[kb + "sqkv.weight"])
+            ops.group_sum(W["dsqkv"], g[kb + "sqkv.bias"], outer=BT, J=1, inner=1)
+            g[kb + "summary_ln.weight"].zero_(); g[kb + "summary_ln.bias"].zero_()
+            ops.layernorm_bwd(W["dsn"], cp, P[k + "summary_ln.w"], W["d_cp"], rows=BT, D=D, add1=W["d_lcp"],
+                              add2=W["d_sum"], dx_bf16=W["d_cp_bf"], dw=g[kb + "summary_ln.weight"],
+                              db=g[kb + "summary_ln.bias"])
+            # ---- cls_proj (frozen): dx[cls rows] += d_cp Wc
+            ops.gemm(W["d_cp_bf"], P[k + "cls.wT"], dx_cls, mode=ops.EPI_BIAS_RESID_F32, resid=dx_cls)
+
+        # ---- ln_pre and the embedding sum: d time_embed[t] = sum over videos and tokens   (vision_encoder.py:108-113)
+        ops.layernorm_bwd(dx, W["x0_pre"], P["ln_pre.w"], dx, rows=M, D=D)
+        ops.group_sum(dx, g["time_embed"], outer=B, J=T, inner=N0)
+        self.bwd_launches_last_call = ops.launch_count() - n0
+        return g
+
+    def _wgrad(self, W: Dict[str, object], dy: Tensor, x: Tensor, out: Tensor) -> None:
+        """out[N, K] (f32) = dy[rows, N]^T x[rows, K] on the tensor cores: both operands transposed to [*, rows_pad]."""
+        n, kk = dy.shape[1], x.shape[1]
+        tA = W["tA"][:n]
+        tB = W["tB"][:kk]
+        ops.transpose_bf16(dy, tA)
+        ops.transpose_bf16(x, tB)
+        ops.gemm(tA, tB, out, mode=ops.EPI_BIAS_F32)
+
+
+class TowerFunction(torch.autograd.Function):
+    """autograd bridge: (video, trainable tower parameters) -> (frame_feat [BT,E], summary tokens [BT,D])."""
+
+    @staticmethod
+    def forward(ctx, trainer: TowerTrainer, video: Tensor, E: int, *params: Tensor):
+        ff, st = trainer.forward_train(video)
+        B, T, _, _ = _clip_dims(video)
+        ctx.trainer, ctx.B, ctx.T, ctx.E = trainer, B, T, E
+        ctx.names = [n for n, _ in trainer.trainable_named()]
+        # clones: the workspace is overwritten by the next forward while autograd may still hold these outputs
+        return ff[:, :E].clone(), st.clone()
+
+    @staticmethod
+    def backward(ctx, d_ff: Optional[Tensor], d_st: Optional[Tensor]):
+        tr: TowerTrainer = ctx.trainer
+        grads = tr.backward(ctx.B, ctx.T, d_ff, d_st)
+        out = []
+        for (name, p), need in zip(tr.trainable_named(), ctx.needs_input_grad[3:]):
+            out.append(grads[name].view_as(p) if need else None)
+        return (None, None, None, *out)

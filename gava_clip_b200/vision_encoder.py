@@ -150,48 +150,84 @@ class TowerEngine:
         return tuple((p.data_ptr(), p._version) for p in self.enc.parameters())
 
     def pack(self) -> None:
-        """bf16 K-major copies of every GEMM weight; q|k|v concatenated to one [3D, D] operand."""
+        """bf16 K-major copies of every GEMM weight; q|k|v concatenated to one [3D, D] operand.
+
+        Re-packing after a parameter update (fine-tuning changes the prompt / summary parameters every step) copies
+        only the tensors whose source changed, IN PLACE, so captured CUDA graphs and TMA maps stay valid."""
         sig = self._sig()
         if sig == self.signature:
             return
         e, dev = self.enc, self.device
         bf = lambda t: t.detach().to(dev, torch.bfloat16).contiguous()
         f32 = lambda t: t.detach().to(dev, torch.float32).contiguous()
-        P: Dict[str, Tensor] = {}
+        P = self.packed
+        vers = getattr(self, "_src_versions", {})
+        moved = False
+
+        def put(name: str, srcs, make) -> None:
+            """packed[name] = make() unless none of the source parameters changed since the last pack."""
+            nonlocal moved
+            key = tuple((t.data_ptr(), t._version) for t in srcs)
+            if name in P and vers.get(name) == key:
+                return
+            val = make()
+            old = P.get(name)
+            if old is not None and old.shape == val.shape and old.dtype == val.dtype:
+                old.copy_(val)
+            else:
+                P[name] = val
+                moved = True
+            vers[name] = key
+
         D = e.feature_dim
-        w = e.patch_embed.proj.weight.detach().reshape(D, -1)
-        kpad = _ceil_to(w.shape[1], 64)
-        wp = torch.zeros(D, kpad, device=dev, dtype=torch.bfloat16)
-        wp[:, : w.shape[1]] = w.to(dev, torch.bfloat16)
-        P["patch.w"], P["patch.b"] = wp, f32(e.patch_embed.proj.bias)
-        P["cls_token"], P["pos_embed"] = f32(e.cls_token), f32(e.pos_embed)
-        P["time_embed"] = f32(e.time_embed)
+
+        def patch_w():
+            w = e.patch_embed.proj.weight.detach().reshape(D, -1)
+            wp = torch.zeros(D, _ceil_to(w.shape[1], 64), device=dev, dtype=torch.bfloat16)
+            wp[:, : w.shape[1]] = w.to(dev, torch.bfloat16)
+            return wp
+
+        def proj_wT():
+            pj = torch.zeros(_ceil_to(e.embed_dim, 128), D, device=dev, dtype=torch.bfloat16)   # proj^T, rows padded to the N tile
+            pj[: e.embed_dim] = e.proj.detach().t().to(dev, torch.bfloat16)
+            return pj
+
+        put("patch.w", [e.patch_embed.proj.weight], patch_w)
+        put("patch.b", [e.patch_embed.proj.bias], lambda: f32(e.patch_embed.proj.bias))
+        put("cls_token", [e.cls_token], lambda: f32(e.cls_token))
+        put("pos_embed", [e.pos_embed], lambda: f32(e.pos_embed))
+        put("time_embed", [e.time_embed], lambda: f32(e.time_embed))
         for n in ("ln_pre", "ln_post"):
-            P[n + ".w"], P[n + ".b"] = f32(getattr(e, n).weight), f32(getattr(e, n).bias)
-        ep = _ceil_to(e.embed_dim, 128)
-        pj = torch.zeros(ep, D, device=dev, dtype=torch.bfloat16)       # proj^T, rows padded to the N tile
-        pj[: e.embed_dim] = e.proj.detach().t().to(dev, torch.bfloat16)
-        P["proj.wT"] = pj
-        P["global_prompts"] = f32(e.global_prompts)
+            put(n + ".w", [getattr(e, n).weight], lambda n=n: f32(getattr(e, n).weight))
+            put(n + ".b", [getattr(e, n).bias], lambda n=n: f32(getattr(e, n).bias))
+        put("proj.wT", [e.proj], proj_wT)
+        put("global_prompts", [e.global_prompts], lambda: f32(e.global_prompts))
         for i, blk in enumerate(e.blocks):
             k = f"b{i}."
             a = blk.attn
-            P[k + "qkv.w"] = bf(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0))
-            P[k + "qkv.b"] = f32(torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0))
-            P[k + "out.w"], P[k + "out.b"] = bf(a.out_proj.weight), f32(a.out_proj.bias)
-            P[k + "fc1.w"], P[k + "fc1.b"] = bf(blk.mlp.fc1.weight), f32(blk.mlp.fc1.bias)
-            P[k + "fc2.w"], P[k + "fc2.b"] = bf(blk.mlp.fc2.weight), f32(blk.mlp.fc2.bias)
+            put(k + "qkv.w", [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight],
+                lambda a=a: bf(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0)))
+            put(k + "qkv.b", [a.q_proj.bias, a.k_proj.bias, a.v_proj.bias],
+                lambda a=a: f32(torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0)))
+            for nm, lin in (("out", a.out_proj), ("fc1", blk.mlp.fc1), ("fc2", blk.mlp.fc2), ("cls", blk.cls_proj),
+                            ("sout", blk.summary_attn_layer.out_proj)):
+                put(k + nm + ".w", [lin.weight], lambda lin=lin: bf(lin.weight))
+                put(k + nm + ".b", [lin.bias], lambda lin=lin: f32(lin.bias))
             for n in ("norm1", "norm2", "summary_ln"):
-                P[k + n + ".w"], P[k + n + ".b"] = f32(getattr(blk, n).weight), f32(getattr(blk, n).bias)
-            P[k + "cls.w"], P[k + "cls.b"] = bf(blk.cls_proj.weight), f32(blk.cls_proj.bias)
-            s = blk.summary_attn_layer
-            P[k + "sqkv.w"] = bf(torch.cat([s.q_proj.weight, s.k_proj.weight, s.v_proj.weight], 0))
-            P[k + "sqkv.b"] = f32(torch.cat([s.q_proj.bias, s.k_proj.bias, s.v_proj.bias], 0))
-            P[k + "sout.w"], P[k + "sout.b"] = bf(s.out_proj.weight), f32(s.out_proj.bias)
-            P[k + "local"] = f32(blk.local_prompts)
-        self.packed = P
+                put(k + n + ".w", [getattr(blk, n).weight], lambda blk=blk, n=n: f32(getattr(blk, n).weight))
+                put(k + n + ".b", [getattr(blk, n).bias], lambda blk=blk, n=n: f32(getattr(blk, n).bias))
+            sa = blk.summary_attn_layer
+            put(k + "sqkv.w", [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight],
+                lambda sa=sa: bf(torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0)))
+            put(k + "sqkv.b", [sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias],
+                lambda sa=sa: f32(torch.cat([sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias], 0)))
+            put(k + "local", [blk.local_prompts], lambda blk=blk: f32(blk.local_prompts))
+        for key in [key for key in P if key.startswith("time_embed@")]:
+            del P[key]                                  # resized copies are rebuilt on demand
+        self._src_versions = vers
         self.signature = sig
-        self.graphs.clear()  # captured graphs hold pointers into the old packed tensors
+        if moved:
+            self.graphs.clear()  # captured graphs hold pointers into the old packed tensors
 
     def pack_precise(self) -> Dict[str, Tensor]:
         """hi/lo bf16 pairs of every GEMM weight for the fp32-accuracy path (w = hi + lo up to 2^-17)."""
@@ -559,7 +595,8 @@ class CLIPVisionEncoder(nn.Module):
         if self.feature_dim // self.num_heads != 64:
             raise NotImplementedError("attention kernel is specialised for head_dim 64")
         if self._engine is None or self._engine.device != device:
-            self._engine = TowerEngine(self, device)
+            from .train_engine import TowerTrainer           # TowerEngine + tape / backward schedule
+            self._engine = TowerTrainer(self, device)
         self._engine.pack()
         return self._engine
 
@@ -578,18 +615,25 @@ class CLIPVisionEncoder(nn.Module):
         if x.shape[1 if u8 else 2] != self.num_frames:
             # the reference blocks hard-code num_frames (utils.py:161): other lengths mis-shape its views
             raise ValueError(f"clip has T={x.shape[1 if u8 else 2]} frames but the encoder was built with num_frames={self.num_frames}")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError(
-                "backward kernels for the video tower are not part of this build: run under torch.no_grad()/eval(), or "
-                "freeze every visual parameter (VitaCLIP.freeze_visual()) to fine-tune the text side only")
         return x.contiguous() if u8 else x.contiguous().float()
+
+    def _wants_grad(self) -> bool:
+        """training mode + grad enabled + a trainable tower parameter: the forward keeps a tape and is differentiable."""
+        return self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
     def frames_forward(self, x: Tensor) -> Tuple[Tensor, Tensor, int, int]:
         """per-frame projected cls features [BT, E(+pad)] and summary tokens [BT, D] (workspace views)."""
         x = self._check_input(x)
         eng = self.engine(x.device)
-        ff, st = eng.run(x)
         B, T, _, _ = _clip_dims(x)
+        if self._wants_grad():
+            if self.precision == "fp32":
+                raise NotImplementedError("the fine-tune step runs in the bf16 path (set precision='bf16')")
+            from .train_engine import TowerFunction
+            eng.check_trainable()
+            ff, st = TowerFunction.apply(eng, x, self.embed_dim, *[p for _, p in eng.trainable_named()])
+            return ff, st, B, T
+        ff, st = eng.run(x)
         return ff, st, B, T
 
     def forward(self, x: Tensor):

@@ -21,13 +21,13 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(lib, s), f"{s} declared in include/gava_sm100.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in gava_clip_b200/_lib.py"
     assert sorted(_lib.SIGNATURES) == syms
-    assert lib.gava_version() == 1
+    assert lib.gava_version() == 2
 
 
 def test_epilogue_struct_layout():
     from gava_clip_b200._lib import GemmEpilogue
-    # int32 mode (+4 pad), 2 ptr, i64, ptr, i64, 4 x i32, 2 ptr  -> 80 bytes on LP64
-    assert ctypes.sizeof(GemmEpilogue) == 80
+    # int32 mode (+4 pad), 2 ptr, i64, ptr, i64, 4 x i32, 2 ptr, ptr, i64  -> 96 bytes on LP64
+    assert ctypes.sizeof(GemmEpilogue) == 96 and GemmEpilogue.aux.offset == 80
     assert GemmEpilogue.out.offset == 32 and GemmEpilogue.group.offset == 48 and GemmEpilogue.pos.offset == 64
 
 
