@@ -62,11 +62,17 @@ class TowerTrainer(TowerEngine):
         total = sum(int(torch.Size(s).numel()) for _, s in layout)
         self.grad_flat = torch.zeros(total, device=dev, dtype=torch.float32)
         self.grads: Dict[str, Tensor] = {}
+        self.layer_slices: List[Tensor] = []          # contiguous per-layer ranges of grad_flat (all-reduce units)
         off = 0
         for name, shape in layout:
             n = int(torch.Size(shape).numel())
             self.grads[name] = self.grad_flat[off: off + n].view(shape)
+            if name.endswith("local_prompts"):
+                lo = off
+            if name.endswith("out_proj.bias"):
+                self.layer_slices.append(self.grad_flat[lo: off + n])
             off += n
+        self.head_slice = self.grad_flat[: T * D + L * G * D]       # time_embed + global_prompts
         for i in range(L):       # per-parameter views of the fused q|k|v blocks
             k = f"blocks.{i}."
             w, b = self.grads[k + "sqkv.weight"], self.grads[k + "sqkv.bias"]
@@ -210,6 +216,8 @@ class TowerTrainer(TowerEngine):
         g = self.grads
         dx, dxb, gD = W["dx"], W["dxb"], W["gD"]
         dx_cls = dx.view(BT, N0 * D)[:, :D]
+        hook = getattr(self, "grad_ready_hook", None)   # finetune.FineTuner: per-layer gradient all-reduce overlap
+        pending: List = []
         n0 = ops.launch_count()
 
         # ---- frame_feat = ln_post(x_cls) @ proj   (vision_encoder.py:126-127)
@@ -264,10 +272,17 @@ class TowerTrainer(TowerEngine):
                               db=g[kb + "summary_ln.bias"])
             # ---- cls_proj (frozen): dx[cls rows] += d_cp Wc
             ops.gemm(W["d_cp_bf"], P[k + "cls.wT"], dx_cls, mode=ops.EPI_BIAS_RESID_F32, resid=dx_cls)
+            if hook is not None:
+                pending.append(hook(self.layer_slices[i]))   # this layer's gradients are final: start their all-reduce now
 
         # ---- ln_pre and the embedding sum: d time_embed[t] = sum over videos and tokens   (vision_encoder.py:108-113)
         ops.layernorm_bwd(dx, W["x0_pre"], P["ln_pre.w"], dx, rows=M, D=D)
         ops.group_sum(dx, g["time_embed"], outer=B, J=T, inner=N0)
+        if hook is not None:
+            pending.append(hook(self.head_slice))
+            for h in pending:           # stream-level wait: autograd adds these buffers into the parameters' .grad next
+                if h is not None:
+                    h.wait()
         self.bwd_launches_last_call = ops.launch_count() - n0
         return g
 

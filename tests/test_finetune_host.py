@@ -1,0 +1,80 @@
+"""CPU tests of the fine-tune step's host logic: loss restatement vs the reference formula, flat parameter / gradient
+buffers, and (gloo, world_size 2) the bucketed gradient all-reduce.  The kernels themselves are covered on the GPU
+(tests/test_backward_kernels_gpu.py, tests/test_model_gpu.py)."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn.functional as F
+
+from gava_clip_b200.finetune import allreduce_flat, finetune_loss, flatten_parameters, focal_ordinal_weight
+
+
+def _ref_focal_ordinal(y_pred, y_true, gamma=2., alpha=.25, beta=0.2, scale=1.0):
+    """independent restatement of training/loss_utils.py:25-44 used as the checker"""
+    y_true = F.one_hot(y_true, num_classes=y_pred.shape[-1])
+    y_pred = y_pred.softmax(dim=-1)
+    ordinal_dist = torch.abs(torch.argmax(y_true, dim=-1) - torch.argmax(y_pred, dim=-1))
+    weights = (ordinal_dist / (y_pred.shape[-1] - 1)).float()
+    focal = alpha * torch.pow(1 - y_pred, gamma)
+    combined = (beta * weights.unsqueeze(-1).expand(-1, y_pred.shape[-1]) + focal) * y_true
+    return combined.sum(-1) * scale
+
+
+def test_loss_matches_reference_formula():
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(16, 3, generator=g, requires_grad=True)
+    labels = torch.randint(0, 3, (16,), generator=g)
+    mt = torch.randn(64, 3, generator=g).log_softmax(-1)
+    mtl = torch.randint(0, 3, (64,), generator=g)
+    w = focal_ordinal_weight(logits, labels)
+    assert torch.allclose(w, _ref_focal_ordinal(logits, labels), atol=1e-7)
+    loss = finetune_loss(logits, labels, mt, mtl)
+    ref = (F.cross_entropy(logits, labels, reduction="none") * _ref_focal_ordinal(logits, labels)).mean() \
+        + (0.1 * F.cross_entropy(mt, mtl, reduction="none")).mean()
+    assert torch.allclose(loss, ref, atol=1e-7)
+    loss.backward()
+    assert logits.grad is not None and torch.isfinite(logits.grad).all()
+
+
+def test_flatten_parameters_preserves_values_and_aliases():
+    g = torch.Generator().manual_seed(1)
+    ps = [torch.nn.Parameter(torch.randn(s, generator=g)) for s in [(3, 5), (7,), (), (2, 2, 2)]]
+    before = [p.detach().clone() for p in ps]
+    flat_p, flat_g = flatten_parameters(ps)
+    assert flat_p.numel() % 4 == 0 and flat_p.numel() >= sum(p.numel() for p in ps)
+    for p, b in zip(ps, before):
+        assert torch.equal(p.detach(), b) and p.requires_grad
+    flat_p.mul_(2.0)
+    for p, b in zip(ps, before):
+        assert torch.equal(p.detach(), 2 * b)              # parameters are views of the flat buffer
+    sum((p * p).sum() for p in ps).backward()
+    off = 0
+    for p in ps:                                            # autograd accumulated INTO the flat gradient buffer
+        assert torch.allclose(flat_g[off: off + p.numel()].view(p.shape), 2 * p.detach())
+        off += p.numel()
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+        allreduce_flat(flat, bucket_elems=256)                                   # 4 buckets, ragged tail
+        ret[rank] = bool(torch.equal(flat, torch.arange(1000, dtype=torch.float32) * 3))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_bucketed_gradient_allreduce():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ret.get(0) is True and ret.get(1) is True

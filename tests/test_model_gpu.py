@@ -347,3 +347,37 @@ def test_unsupported_trainable_parameter_is_refused(cuda):
     model.visual.blocks[0].mlp.fc1.weight.requires_grad_(True)        # backbone weight: no wgrad kernel for it
     with pytest.raises(NotImplementedError):
         model(fx.make_inputs("tiny")["video"].to(cuda))
+
+
+def test_finetuner_step_matches_torch_adamw(cuda):
+    """FineTuner (flat parameters + fused AdamW kernel) against torch.optim.AdamW on a twin model fed the same gradients;
+    the second step must see the updated weights (packed bf16 copies / cached text features are refreshed)."""
+    import torch.nn.functional as Fn
+    from gava_clip_b200.finetune import FineTuner, finetune_loss
+    video = fx.make_inputs("tiny")["video"].to(cuda)
+    labels = torch.tensor([2, 0], device=cuda)
+    a, _, _ = build_model("tiny", device=cuda)
+    b, _, _ = build_model("tiny", device=cuda)
+    a.train(); b.train()
+    keys_before = list(a.state_dict().keys())
+    tuner = FineTuner(a, lr=1e-3, weight_decay=0.2)
+    opt = torch.optim.AdamW([p for p in b.parameters() if p.requires_grad], lr=1e-3, weight_decay=0.2)
+    losses = []
+    for _ in range(3):
+        la = tuner.step(video, labels)
+        opt.zero_grad(set_to_none=True)
+        lb = finetune_loss(b(video)[0], labels)
+        lb.backward()
+        opt.step()
+        losses.append((float(la), float(lb)))
+    assert list(a.state_dict().keys()) == keys_before
+    assert abs(losses[0][0] - losses[0][1]) < 1e-5 * max(1.0, abs(losses[0][1]))
+    assert losses[2][0] != losses[0][0]                      # the weights moved and the forward saw it
+    for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        if pa.requires_grad:
+            # Adam normalises the update to ~lr per element, so atomics-order noise in tiny gradients can flip a few
+            # elements by a fraction of lr; compare against the step size
+            assert float((pa - pb).abs().max()) < 3 * 1e-3 * 0.35, n
+            assert rel_l2(pa, pb) < 2e-3, n
+    for la, lb in losses:
+        assert abs(la - lb) < 2e-2 * max(1e-3, abs(lb))
