@@ -1,0 +1,65 @@
+"""2-GPU fine-tune step over NCCL (skipped with < 2 GPUs; run with `gpurun --gpus 2`): two ranks, each on its half of
+the batch, must land on the same parameters as ONE process stepping on the whole batch (mean loss => averaged gradients),
+and both ranks must hold identical parameters afterwards."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.util import build_model, fx, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(dev):
+    g = torch.Generator().manual_seed(77)
+    video = torch.randn(4, 3, 3, 64, 64, generator=g).to(dev)          # "tiny" case shapes, 4 clips
+    labels = torch.tensor([2, 0, 1, 1], device=dev)
+    return video, labels
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from gava_clip_b200.finetune import FineTuner
+        model, _, _ = build_model("tiny", device=dev)
+        tuner = FineTuner(model, lr=1e-3, weight_decay=0.2, focal_ordinal=False)   # plain mean CE: shards average exactly
+        video, labels = _inputs(dev)
+        lo, hi = rank * 2, rank * 2 + 2
+        for _ in range(2):
+            tuner.step(video[lo:hi], labels[lo:hi])
+        torch.cuda.synchronize()
+        ret[rank] = {n: p.detach().cpu() for n, p in model.named_parameters() if p.requires_grad}
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_step_equals_single_process_full_batch(cuda):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    from gava_clip_b200.finetune import FineTuner
+    model, _, _ = build_model("tiny", device=cuda)
+    tuner = FineTuner(model, lr=1e-3, weight_decay=0.2, focal_ordinal=False)
+    video, labels = _inputs(cuda)
+    for _ in range(2):
+        tuner.step(video, labels)
+    ref = {n: p.detach().cpu() for n, p in model.named_parameters() if p.requires_grad}
+    for n in ref:
+        assert torch.equal(ret[0][n], ret[1][n]), f"ranks diverged on {n}"
+        if n.endswith("k_proj.bias"):
+            continue      # exact gradient is 0 (softmax shift invariance): Adam turns rounding noise into +-lr steps
+        assert rel_l2(ret[0][n], ref[n]) < 2e-3, n
