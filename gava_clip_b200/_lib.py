@@ -69,6 +69,8 @@ SIGNATURES = {
     "gava_group_sum": [_p, _i64, _i32, _p, _i32, _i32, _i32, _i32, _p],
     "gava_transpose_bf16": [_p, _i64, _i32, _p, _i32, _i32, _i32, _p],
     "gava_quickgelu_bf16_fwd": [_p, _p, _i64, _p],
+    "gava_preprocess_u8_fwd": [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32,
+                               C.POINTER(C.c_float), C.POINTER(C.c_float), _p],
     "gava_adamw_step": [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _p],
 }
 _RESTYPES = {"gava_last_error_string": C.c_char_p}

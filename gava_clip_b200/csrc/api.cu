@@ -171,4 +171,11 @@ int gava_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_
                     (cudaStream_t)stream);
 }
 
+int gava_preprocess_u8_fwd(const uint8_t* frames, float* out, int32_t T0, int32_t H0, int32_t W0, int32_t new_h, int32_t new_w,
+                           int32_t h_st, int32_t w_st, int32_t t_st, int32_t t_step, int32_t T, int32_t Sh, int32_t Sw,
+                           const float* mean, const float* std, void* stream) {
+  return preprocess_u8(frames, out, T0, H0, W0, new_h, new_w, h_st, w_st, t_st, t_step, T, Sh, Sw, mean, std,
+                       (cudaStream_t)stream);
+}
+
 }  // extern "C"

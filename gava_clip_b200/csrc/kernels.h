@@ -87,4 +87,8 @@ int quickgelu_bf16(const void* a, void* h, long long n, cudaStream_t stream);
 int adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                float weight_decay, int step, float grad_scale, cudaStream_t stream);
 
+// ---- input stage (input_stage.cu); mean/std: HOST arrays of 3 floats
+int preprocess_u8(const uint8_t* frames, float* out, int T0, int H0, int W0, int new_h, int new_w, int h_st, int w_st,
+                  int t_st, int t_step, int T, int Sh, int Sw, const float* mean, const float* std, cudaStream_t stream);
+
 }  // namespace gava

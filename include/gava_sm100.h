@@ -216,6 +216,16 @@ int gava_quickgelu_bf16_fwd(const void* a, void* h, int64_t n, void* stream);
 int gava_adamw_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
                     float beta2, float eps, float weight_decay, int32_t step, float grad_scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Evaluation input stage in one kernel: decoder frames uint8 [T0, H0, W0, 3] -> u/255 ->
+ * (x - mean[c]) / std[c] -> bilinear resize of every frame to (new_h, new_w) (align_corners = False, ATen weights) ->
+ * spatial crop [h_st, h_st+Sh) x [w_st, w_st+Sw) -> frames t_st + i*t_step (i < T; indices past the end repeat the last
+ * frame) -> out f32 [3, T, Sh, Sw].  mean/std: HOST pointers to 3 floats.
+ * Replaces video_dataset/dataset.py:117-139 (eval branch) and the crops of :160-196. */
+int gava_preprocess_u8_fwd(const uint8_t* frames, float* out, int32_t T0, int32_t H0, int32_t W0, int32_t new_h,
+                           int32_t new_w, int32_t h_st, int32_t w_st, int32_t t_st, int32_t t_step, int32_t T, int32_t Sh,
+                           int32_t Sw, const float* mean, const float* std, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -369,7 +369,7 @@ def test_finetuner_step_matches_torch_adamw(cuda):
         lb = finetune_loss(b(video)[0], labels)
         lb.backward()
         opt.step()
-        losses.append((float(la), float(lb)))
+        losses.append((float(la), float(lb.detach())))
     assert list(a.state_dict().keys()) == keys_before
     assert abs(losses[0][0] - losses[0][1]) < 1e-5 * max(1.0, abs(losses[0][1]))
     assert losses[2][0] != losses[0][0]                      # the weights moved and the forward saw it

@@ -61,3 +61,37 @@ def test_oracle_zeroshot_head_consistent():
     a = vo.zeroshot_head(v, tf, ls)
     b, _ = vo.logit_head(v, [t[None] for t in tf], ls)
     assert torch.allclose(a, b, atol=1e-6)
+
+
+def test_input_stage_oracle_matches_reference_dataset():
+    """oracle/input_oracle.py against the reference's own VideoDataset eval branch (oracle/make_golden_input.py)."""
+    import torch
+    from oracle import input_oracle as io
+    gold = torch.load(fx.GOLDEN / "input_stage.pt", map_location="cpu", weights_only=False)
+    for name, (T0, H0, W0, S, nf, rate, nsv, ntv) in io.INPUT_CASES.items():
+        views = io.eval_views(io.make_frames(name), S, nf, rate, nsv, ntv)
+        ref = gold[name]["views"]
+        assert len(views) == ref.shape[0] == nsv * ntv
+        for v, r in zip(views, ref):
+            assert v.shape == r.shape and torch.equal(v, r), name
+
+
+def test_input_stage_geometry_matches_oracle():
+    """EvalInputStage's integer geometry (resize target, crop offsets, temporal starts) reproduces the oracle's crops."""
+    import torch
+    from gava_clip_b200.input_stage import EvalInputStage, aggregate_views
+    from oracle import input_oracle as io
+    for name, (T0, H0, W0, S, nf, rate, nsv, ntv) in io.INPUT_CASES.items():
+        st = EvalInputStage(S, nf, rate, nsv, ntv, io.MEAN, io.STD)
+        nh, nw = st.resized_hw(H0, W0)
+        idx = torch.arange(T0 * nh * nw, dtype=torch.float32).view(1, T0, nh, nw)        # position-coded tensor
+        want = sum([io.temporal_crops(v, nf, rate, ntv) for v in io.spatial_crops(idx, S, nsv)], [])
+        got = []
+        for (h0, w0) in st.spatial_offsets(nh, nw):
+            for t0 in st.temporal_starts(T0):
+                ts = [min(t0 + i * rate, T0 - 1) for i in range(nf)]
+                got.append(idx[:, ts, h0:h0 + S, w0:w0 + S])
+        assert len(got) == len(want) and all(torch.equal(a, b) for a, b in zip(got, want)), name
+    lg = torch.randn(6, 3)
+    assert torch.allclose(aggregate_views(lg), lg.softmax(-1).mean(0))
+    assert torch.allclose(aggregate_views(lg, n_views=3), lg.softmax(-1).view(2, 3, 3).mean(1))
