@@ -65,6 +65,7 @@ SIGNATURES = {
     "gava_layernorm_bwd": [_p, _i64, _i32, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _f32, _p],
     "gava_attention_bwd": [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p],
     "gava_temporal_attention_bwd": [_p, _p, _p, _i32, _i32, _i32, _p],
+    "gava_causal_attention_bwd": [_p, _p, _p, _i32, _i32, _i32, _p],
     "gava_prompt_rows_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p],
     "gava_group_sum": [_p, _i64, _i32, _p, _i32, _i32, _i32, _i32, _p],
     "gava_transpose_bf16": [_p, _i64, _i32, _p, _i32, _i32, _i32, _p],

@@ -143,6 +143,11 @@ int gava_temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, i
   return temporal_attention_bwd(qkv, dout, dqkv, B, T, H, (cudaStream_t)stream);
 }
 
+int gava_causal_attention_bwd(const float* qkv, const void* dout, void* dqkv, int32_t n_seq, int32_t L, int32_t H,
+                              void* stream) {
+  return causal_attention_bwd(qkv, dout, dqkv, n_seq, L, H, (cudaStream_t)stream);
+}
+
 int gava_prompt_rows_bwd(const void* d_rows_n, const float* global_prompts, const float* local_prompts,
                          const float* cls_proj_out, const float* summary, const float* ln_weight, float* d_global,
                          float* d_local_cp, float* d_summary, const float* d_summary_ext, int32_t G, int32_t B, int32_t T,

@@ -369,11 +369,15 @@ int adamw_step(float* p, const float* g, float* m, float* v, long long n, float 
 }
 
 // ================================================================================================
-// Temporal (summary-token) attention backward: one block per (video, head), everything in shared memory in f32.
-//   P = softmax(q k^T / 8); o = P v.   dV = P^T dO; dP = dO V^T; dS = P (dP - rowsum(P dP)); dQ = dS K / 8; dK = dS^T Q / 8
-__global__ void __launch_bounds__(128) temporal_attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                                     const __nv_bfloat16* __restrict__ dout,
-                                                                     __nv_bfloat16* __restrict__ dqkv, int T, int H) {
+// Small-sequence attention backward: one block per (sequence, head), everything in shared memory in f32.
+//   P = softmax(q k^T / 8 [+ causal mask]); o = P v.
+//   dV = P^T dO; dP = dO V^T; dS = P (dP - rowsum(P dP)); dQ = dS K / 8; dK = dS^T Q / 8
+// Used for the T x T summary-token attention of the video tower (bf16 qkv, no mask) and for the 77 x 77 causal attention
+// of the CLIP text transformer (f32 qkv, VitaCLIP_text_encoder.py:83-88,146-152).
+template <bool IN_F32, bool CAUSAL>
+__global__ void __launch_bounds__(128) seq_attention_bwd_kernel(const void* __restrict__ qkv_,
+                                                                const __nv_bfloat16* __restrict__ dout,
+                                                                __nv_bfloat16* __restrict__ dqkv, int T, int H) {
   extern __shared__ float tsm[];
   const int PITCH = 65, PP = T + 1;
   float* sq = tsm;
@@ -385,50 +389,62 @@ __global__ void __launch_bounds__(128) temporal_attention_bwd_kernel(const __nv_
   const int D = H * 64;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long ld = 3LL * D;
-  const __nv_bfloat16* base = qkv + (long long)b * T * ld + h * 64;
+  const long long base = (long long)b * T * ld + h * 64;
   const __nv_bfloat16* dbase = dout + (long long)b * T * D + h * 64;
   for (int i = tid; i < T * 64; i += 128) {
     const int t = i >> 6, d = i & 63;
-    sq[t * PITCH + d] = __bfloat162float(base[t * ld + d]);
-    sk[t * PITCH + d] = __bfloat162float(base[t * ld + D + d]);
-    sv[t * PITCH + d] = __bfloat162float(base[t * ld + 2 * D + d]);
+    if constexpr (IN_F32) {
+      const float* src = reinterpret_cast<const float*>(qkv_) + base;
+      sq[t * PITCH + d] = src[t * ld + d];
+      sk[t * PITCH + d] = src[t * ld + D + d];
+      sv[t * PITCH + d] = src[t * ld + 2 * D + d];
+    } else {
+      const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(qkv_) + base;
+      sq[t * PITCH + d] = __bfloat162float(src[t * ld + d]);
+      sk[t * PITCH + d] = __bfloat162float(src[t * ld + D + d]);
+      sv[t * PITCH + d] = __bfloat162float(src[t * ld + 2 * D + d]);
+    }
     sdo[t * PITCH + d] = __bfloat162float(dbase[(long long)t * D + d]);
   }
   __syncthreads();
   for (int idx = tid; idx < T * T; idx += 128) {
     const int i = idx / T, j = idx - i * T;
     float acc = 0.f;
+    if (!CAUSAL || j <= i) {
 #pragma unroll 16
-    for (int d = 0; d < 64; ++d) acc += sq[i * PITCH + d] * sk[j * PITCH + d];
+      for (int d = 0; d < 64; ++d) acc += sq[i * PITCH + d] * sk[j * PITCH + d];
+    }
     sp[i * PP + j] = acc * 0.125f;
   }
   __syncthreads();
-  for (int i = warp; i < T; i += 4) {   // row softmax
+  for (int i = warp; i < T; i += 4) {   // row softmax over the visible keys
+    const int n = CAUSAL ? i + 1 : T;
     float m = -INFINITY;
-    for (int j = lane; j < T; j += 32) m = fmaxf(m, sp[i * PP + j]);
+    for (int j = lane; j < n; j += 32) m = fmaxf(m, sp[i * PP + j]);
     m = warp_max(m);
     float s = 0.f;
-    for (int j = lane; j < T; j += 32) { const float e = __expf(sp[i * PP + j] - m); sp[i * PP + j] = e; s += e; }
+    for (int j = lane; j < n; j += 32) { const float e = __expf(sp[i * PP + j] - m); sp[i * PP + j] = e; s += e; }
     s = 1.0f / warp_sum(s);
-    for (int j = lane; j < T; j += 32) sp[i * PP + j] *= s;
+    for (int j = lane; j < T; j += 32) sp[i * PP + j] = (j < n) ? sp[i * PP + j] * s : 0.f;
   }
   __syncthreads();
   __nv_bfloat16* obase = dqkv + (long long)b * T * ld + h * 64;
   for (int idx = tid; idx < T * 64; idx += 128) {   // dV[j][d] = sum_i P[i][j] dO[i][d]
     const int j = idx >> 6, d = idx & 63;
     float acc = 0.f;
-    for (int i = 0; i < T; ++i) acc += sp[i * PP + j] * sdo[i * PITCH + d];
+    for (int i = CAUSAL ? j : 0; i < T; ++i) acc += sp[i * PP + j] * sdo[i * PITCH + d];
     obase[j * ld + 2 * D + d] = __float2bfloat16(acc);
   }
   __syncthreads();
   for (int i = warp; i < T; i += 4) {   // dS row i (overwrites P row i)
+    const int n = CAUSAL ? i + 1 : T;
     float delta = 0.f;
     float dp_loc[4];   // T <= 128
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
       const int j = lane + 32 * jj;
       float acc = 0.f;
-      if (j < T) {
+      if (j < n) {
 #pragma unroll 16
         for (int d = 0; d < 64; ++d) acc += sdo[i * PITCH + d] * sv[j * PITCH + d];
         delta += sp[i * PP + j] * acc;
@@ -439,14 +455,14 @@ __global__ void __launch_bounds__(128) temporal_attention_bwd_kernel(const __nv_
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
       const int j = lane + 32 * jj;
-      if (j < T) sp[i * PP + j] = sp[i * PP + j] * (dp_loc[jj] - delta);
+      if (j < n) sp[i * PP + j] = sp[i * PP + j] * (dp_loc[jj] - delta);
     }
   }
   __syncthreads();
   for (int idx = tid; idx < T * 64; idx += 128) {
     const int t = idx >> 6, d = idx & 63;
     float aq = 0.f, ak = 0.f;
-    for (int j = 0; j < T; ++j) {
+    for (int j = 0; j < T; ++j) {      // masked entries of dS are exactly 0
       aq += sp[t * PP + j] * sk[j * PITCH + d];   // dQ[t] = sum_j dS[t][j] K[j]
       ak += sp[j * PP + t] * sq[j * PITCH + d];   // dK[t] = sum_i dS[i][t] Q[i]
     }
@@ -455,20 +471,30 @@ __global__ void __launch_bounds__(128) temporal_attention_bwd_kernel(const __nv_
   }
 }
 
-int temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int B, int T, int H, cudaStream_t stream) {
-  if (!qkv || !dout || !dqkv || B <= 0 || T <= 0 || H <= 0) { set_error("temporal_attention_bwd: bad arguments"); return GAVA_ERR_ARG; }
-  if (T > 128) { set_error("temporal_attention_bwd: T=%d > 128 unsupported", T); return GAVA_ERR_SHAPE; }
+template <bool IN_F32, bool CAUSAL>
+static int launch_seq_attention_bwd(const void* qkv, const void* dout, void* dqkv, int n_seq, int T, int H,
+                                    cudaStream_t stream, const char* what) {
+  if (!qkv || !dout || !dqkv || n_seq <= 0 || T <= 0 || H <= 0) { set_error("%s: bad arguments", what); return GAVA_ERR_ARG; }
+  if (T > 128) { set_error("%s: sequence length %d > 128 unsupported", what, T); return GAVA_ERR_SHAPE; }
   const size_t smem = sizeof(float) * ((size_t)4 * T * 65 + (size_t)T * (T + 1));
   static size_t attr_bytes = 48 * 1024;
+  auto kern = seq_attention_bwd_kernel<IN_F32, CAUSAL>;
   if (smem > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(temporal_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(temporal_attention_bwd): %s", cudaGetErrorString(e)); return (int)e; }
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(e)); return (int)e; }
     attr_bytes = smem;
   }
-  temporal_attention_bwd_kernel<<<dim3(H, B), 128, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
-                                                                   reinterpret_cast<const __nv_bfloat16*>(dout),
-                                                                   reinterpret_cast<__nv_bfloat16*>(dqkv), T, H);
-  return check_launch("temporal_attention_bwd");
+  kern<<<dim3(H, n_seq), 128, smem, stream>>>(qkv, reinterpret_cast<const __nv_bfloat16*>(dout),
+                                              reinterpret_cast<__nv_bfloat16*>(dqkv), T, H);
+  return check_launch(what);
+}
+
+int temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int B, int T, int H, cudaStream_t stream) {
+  return launch_seq_attention_bwd<false, false>(qkv, dout, dqkv, B, T, H, stream, "temporal_attention_bwd");
+}
+
+int causal_attention_bwd(const float* qkv, const void* dout, void* dqkv, int n_seq, int L, int H, cudaStream_t stream) {
+  return launch_seq_attention_bwd<true, true>(qkv, dout, dqkv, n_seq, L, H, stream, "causal_attention_bwd");
 }
 
 }  // namespace gava

@@ -76,6 +76,7 @@ int layernorm_bwd(const void* dy, long long dy_stride, int dy_bf16, const float*
 int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, void* dqkv, float* dkv_aux,
                   int B, int T, int N0, int G, int H, cudaStream_t stream);
 int temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int B, int T, int H, cudaStream_t stream);
+int causal_attention_bwd(const float* qkv, const void* dout, void* dqkv, int n_seq, int L, int H, cudaStream_t stream);
 int prompt_rows_bwd(const void* d_rows_n, const float* global_prompts, const float* local_prompts,
                     const float* cls_proj_out, const float* summary, const float* ln_w, float* d_global,
                     float* d_local_cp, float* d_summary, const float* d_summary_ext, int G, int B, int T, int D, float eps,

@@ -92,7 +92,7 @@ class FineTuner:
     def __init__(self, model, lr: float = 1e-4, weight_decay: float = 0.2, betas: Tuple[float, float] = (0.9, 0.999),
                  eps: float = 1e-8, focal_ordinal: bool = True, ordinal_beta: float = 0.2,
                  memory_loss_weight: float = 0.1, process_group=None,
-                 lr_schedule: Optional[Callable[[int], float]] = None):
+                 lr_schedule: Optional[Callable[[int], float]] = None, text_tf32: bool = False):
         self.model = model
         tower_ids = {id(p) for p in model.visual.parameters()}
         tower = [p for p in model.visual.parameters() if p.requires_grad]
@@ -110,6 +110,9 @@ class FineTuner:
         self.focal_ordinal, self.ordinal_beta, self.memory_loss_weight = focal_ordinal, ordinal_beta, memory_loss_weight
         self.group = process_group
         self.lr_schedule = lr_schedule
+        # Only the prompt assembly / KAPT projector / cosine head / memory heads are PyTorch matmuls in a step (the text
+        # transformer runs on text_train.TextTrainer); text_tf32=True lets those few use TF32 tensor-core products.
+        self.text_tf32 = text_tf32
         self.step_count = 0
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
 
@@ -134,6 +137,8 @@ class FineTuner:
         self.model.train()
         eng = self.model.visual.engine(video.device)
         eng.grad_ready_hook = self._tower_slice_ready if self.world > 1 else None
+        tf32_prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32_prev or self.text_tf32
         try:
             logits, logits_mt, logits_vm = self.model(video, memory=memory, video_nte=video_nte)
             loss = finetune_loss(logits, labels, logits_mt, memory_labels, focal_ordinal=self.focal_ordinal,
@@ -142,6 +147,7 @@ class FineTuner:
             (loss * loss_scale).backward()
         finally:
             eng.grad_ready_hook = None
+            torch.backends.cuda.matmul.allow_tf32 = tf32_prev
         self.last_logits = logits.detach()
         return loss.detach()
 

@@ -197,7 +197,21 @@ class VitaCLIP(nn.Module):
             return self.logit_scale.requires_grad
         return self.logit_scale.requires_grad or any(p.requires_grad for p in self.prompt_learner.parameters())
 
-    def _forward_finetune(self, ff: Tensor, st: Tensor, B: int, T: int, memory, video_nte):
+    def _text_features_on_side_stream(self, dev):
+        main = torch.cuda.current_stream(dev)
+        side = getattr(self, "_text_stream", None)
+        if side is None or side.device != dev:
+            side = self._text_stream = torch.cuda.Stream(dev)
+        side.wait_stream(main)                       # parameters updated by the optimizer on the main stream
+        with torch.cuda.stream(side):
+            out = self._text_tower.features(dev, need_grad=True)
+        done = torch.cuda.Event()
+        done.record(side)
+        for t in (out[0], out[2]):
+            t.record_stream(main)                    # consumed by the head on the main stream
+        return out, done
+
+    def _forward_finetune(self, ff: Tensor, st: Tensor, B: int, T: int, memory, video_nte, text_ahead=None):
         """Training-mode forward (train.py:441-443).  The video tower ran on the sm_100a kernels; when any of its trainable
         parameters requires grad, `ff`/`st` come from train_engine.TowerFunction and loss.backward() drives the backward
         kernels.  The head -- temporal mean, cosine logits (VitaCLIP_model.py:248-293) -- and the text side (prompt learner
@@ -210,7 +224,11 @@ class VitaCLIP(nn.Module):
         v_hat = vf / vf.norm(dim=-1, keepdim=True)
         scale = self.logit_scale.exp()
         if self.use_text_prompt_learning:
-            t_hat, offs, text_features, counts = self._text_tower.features(dev, need_grad=self._text_side_needs_grad())
+            if text_ahead is not None:
+                (t_hat, offs, text_features, counts), done = text_ahead
+                torch.cuda.current_stream(dev).wait_event(done)
+            else:
+                t_hat, offs, text_features, counts = self._text_tower.features(dev, need_grad=self._text_side_needs_grad())
             logits = torch.cat([(scale * v_hat @ t.t()).mean(-1, keepdim=True) for t in t_hat.split(counts, dim=0)], dim=-1)
             self.text_features = text_features
         else:
@@ -225,11 +243,17 @@ class VitaCLIP(nn.Module):
     def forward(self, x: Tensor, memory=None, video_nte=None, desc_wise=False):
         """x: fp32 clip (B,3,T,H,W) as in the reference, or -- after self.visual.set_input_norm(mean, std) -- the
         decoder's uint8 frames (B,T,H,W,3), normalised on the fly inside the patch gather."""
+        text_ahead = None
+        if self.use_text_prompt_learning and x.is_cuda and self._text_side_needs_grad():
+            # fine-tune step: the text side (a few hundred small library kernels, launch-bound) is issued FIRST on a side
+            # stream so that it runs underneath the video tower instead of in front of it; autograd replays its backward
+            # on the same side stream, i.e. underneath the tower's backward
+            text_ahead = self._text_features_on_side_stream(x.device)
         ff, st, B, T = self.visual.frames_forward(x)
         dev = ff.device
         if self.training and torch.is_grad_enabled() and (ff.requires_grad or self._text_side_needs_grad()):
             assert not desc_wise
-            return self._forward_finetune(ff, st, B, T, memory, video_nte)
+            return self._forward_finetune(ff, st, B, T, memory, video_nte, text_ahead)
         if self.use_text_prompt_learning:
             t_hat, offs, text_features, counts = self._text_tower.features(dev)
             if desc_wise:

@@ -351,6 +351,18 @@ def temporal_attention_bwd(qkv: Tensor, dout: Tensor, dqkv: Tensor, B: int, T: i
     return dqkv
 
 
+def causal_attention_bwd(qkv: Tensor, dout: Tensor, dqkv: Tensor, *, n_seq: int, L: int, H: int) -> Tensor:
+    """backward of causal_attention_f32: qkv f32 [n_seq*L, 3D], dout bf16 [n_seq*L, D] -> dqkv bf16 [n_seq*L, 3D]."""
+    _req(qkv, torch.float32, "causal_attention_bwd qkv"); _req(dout, torch.bfloat16, "causal_attention_bwd dout")
+    _req(dqkv, torch.bfloat16, "causal_attention_bwd dqkv")
+    D = H * 64
+    assert qkv.is_contiguous() and dout.is_contiguous() and dqkv.is_contiguous()
+    assert qkv.shape == (n_seq * L, 3 * D) and dqkv.shape == qkv.shape and dout.shape == (n_seq * L, D)
+    rc = _lib.load().gava_causal_attention_bwd(qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), n_seq, L, H, _stream())
+    _lib.check(rc, "gava_causal_attention_bwd")
+    return dqkv
+
+
 def prompt_rows_bwd(d_rows_n: Tensor, global_prompts: Tensor, local_prompts: Tensor, cls_proj_out: Tensor, summary: Tensor,
                     ln_w: Tensor, d_global: Tensor, d_local_cp: Tensor, d_summary: Tensor, d_summary_ext: Optional[Tensor],
                     B: int, T: int, eps: float = 1e-5) -> None:

@@ -11,6 +11,8 @@ of SURVEY.md section 8); only prompt assembly (concatenation, the tiny KAPT proj
 """
 from __future__ import annotations
 
+import os
+
 from collections import OrderedDict
 from typing import List, Optional, Sequence, Tuple
 
@@ -170,6 +172,7 @@ class TextTower:
         self.textual, self.prompt_learner = textual, prompt_learner
         self._sig = None
         self._cache: Optional[Tuple[Tensor, Tensor, Tensor, List[int]]] = None
+        self.native_train = os.environ.get("GAVA_TEXT_NATIVE_TRAIN", "1") != "0"   # text_train.TextTrainer in training
 
     def _signature(self, device):
         ps = list(self.textual.parameters()) + list(self.prompt_learner.parameters())
@@ -257,7 +260,13 @@ class TextTower:
             tok = torch.cat([t.to(device) for t in self.prompt_learner.tokenized_prompts], dim=0)
             if device.type == "cuda" and not need_grad:
                 raw = self._encode_sm100(torch.cat(prompts, dim=0).to(device).float(), tok)
-            else:       # host-side tests / autograd: the module's own PyTorch forward
+            elif device.type == "cuda" and self.native_train and not any(p.requires_grad for p in self.textual.parameters()):
+                # fine-tune step: frozen transformer forward + input-gradient backward on the sm_100a kernels
+                from .text_train import TextTrainer, TextTrainFunction
+                if getattr(self, "_trainer", None) is None or self._trainer.device != device:
+                    self._trainer = TextTrainer(self.textual, device)
+                raw = TextTrainFunction.apply(self._trainer, torch.cat(prompts, dim=0).to(device), tok)
+            else:       # host-side tests, or a trainable text transformer: the module's own PyTorch forward
                 raw = self.textual(torch.cat(prompts, dim=0).to(device), tok).float()
             t_hat = raw / raw.norm(dim=-1, keepdim=True)
             offs = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32, device=device)

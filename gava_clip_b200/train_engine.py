@@ -314,5 +314,7 @@ class TowerFunction(torch.autograd.Function):
         grads = tr.backward(ctx.B, ctx.T, d_ff, d_st)
         out = []
         for (name, p), need in zip(tr.trainable_named(), ctx.needs_input_grad[3:]):
-            out.append(grads[name].view_as(p) if need else None)
+            # clones: autograd may adopt the returned tensor as .grad; the flat buffer is rewritten by the next backward
+            # (gradient accumulation over micro-batches, train.py:426-485, must add, not alias)
+            out.append(grads[name].view_as(p).clone() if need else None)
         return (None, None, None, *out)

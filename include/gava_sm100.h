@@ -191,6 +191,11 @@ int gava_attention_bwd(const void* qkv, const void* kv_aux, const void* out, con
 int gava_temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int32_t B, int32_t T, int32_t H,
                                 void* stream);
 
+/* Backward of gava_causal_attention_f32_fwd (text transformer, fine-tune step): qkv f32 [n_seq*L, 3D] (the forward's
+ * input), dout bf16 [n_seq*L, D] -> dqkv bf16 [n_seq*L, 3D].  L <= 128, dh = 64. */
+int gava_causal_attention_bwd(const float* qkv, const void* dout, void* dqkv, int32_t n_seq, int32_t L, int32_t H,
+                              void* stream);
+
 /* Backward of gava_prompt_rows_fwd.  d_rows_n: bf16 [G + 2*B*T, D] gradient of the normalised rows.  Outputs (f32):
  * d_global [G, D]; d_local_cp [B*T, D] (gradient of local_prompts[t] + cls_proj_out[f], per frame);
  * d_summary [B*T, D] (+ d_summary_ext[f] if given: the gradient arriving at the encoder's summary output). */

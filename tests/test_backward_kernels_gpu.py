@@ -194,3 +194,24 @@ def test_adamw_matches_torch(cuda):
         opt.step()
         ops.adamw_step(p, gr, m, v, lr=1e-3, weight_decay=0.2, step=step, grad_scale=0.5)
     assert _rel(p, ref.detach()) < 1e-5
+
+
+@pytest.mark.parametrize("n_seq,L,H", [(15, 77, 8), (3, 20, 2)])
+def test_causal_attention_bwd(cuda, n_seq, L, H):
+    from gava_clip_b200 import ops
+    g = _gen(n_seq + L + H)
+    D = H * 64
+    qkv = torch.randn(n_seq * L, 3 * D, device=cuda, generator=g)
+    dout = torch.randn(n_seq * L, D, device=cuda, generator=g).bfloat16()
+    qr = qkv.clone().requires_grad_()
+    q, k, v = qr.view(n_seq, L, 3, H, 64).unbind(2)
+    mask = torch.full((L, L), float("-inf"), device=cuda).triu(1)
+    s = (torch.einsum("bqhc,bkhc->bhqk", q / 8.0, k) + mask).softmax(-1)
+    ref_out = torch.einsum("bhqk,bkhc->bqhc", s, v).reshape(n_seq * L, D)
+    ref_out.backward(dout.float())
+    out = torch.empty(n_seq * L, D, device=cuda)
+    ops.causal_attention_f32(qkv, out, n_seq=n_seq, L=L, H=H)
+    assert _rel(out, ref_out.detach()) < 1e-4
+    dqkv = torch.empty(n_seq * L, 3 * D, device=cuda, dtype=torch.bfloat16)
+    ops.causal_attention_bwd(qkv, dout, dqkv, n_seq=n_seq, L=L, H=H)
+    assert _rel(dqkv.float(), qr.grad) < 1e-2
