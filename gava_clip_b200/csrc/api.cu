@@ -82,7 +82,12 @@ int gava_prompt_rows_fwd(const float* global_prompts, const float* local_prompts
 
 int gava_attention_fwd(const void* qkv, const void* kv_aux, void* out, int32_t B, int32_t T, int32_t N0, int32_t G,
                        int32_t H, int32_t n_q, void* stream) {
-  return attention(qkv, kv_aux, out, B, T, N0, G, H, n_q, (cudaStream_t)stream);
+  return attention(qkv, kv_aux, out, nullptr, B, T, N0, G, H, n_q, (cudaStream_t)stream);
+}
+
+int gava_attention_train_fwd(const void* qkv, const void* kv_aux, void* out, float* lse, int32_t B, int32_t T, int32_t N0,
+                             int32_t G, int32_t H, void* stream) {
+  return attention(qkv, kv_aux, out, lse, B, T, N0, G, H, N0, (cudaStream_t)stream);
 }
 
 int gava_head_fwd(const float* frame_feat, const float* summary_tok, const float* text_hat,
@@ -133,9 +138,9 @@ int gava_layernorm_bwd(const void* dy, int64_t dy_stride, int32_t dy_bf16, const
                        dx_stride, dx_bf16, dxb_stride, dw, db, rows, D, eps, (cudaStream_t)stream);
 }
 
-int gava_attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, void* dqkv,
-                       float* dkv_aux, int32_t B, int32_t T, int32_t N0, int32_t G, int32_t H, void* stream) {
-  return attention_bwd(qkv, kv_aux, out, dout, dqkv, dkv_aux, B, T, N0, G, H, (cudaStream_t)stream);
+int gava_attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, const float* lse,
+                       void* dqkv, float* dkv_aux, int32_t B, int32_t T, int32_t N0, int32_t G, int32_t H, void* stream) {
+  return attention_bwd(qkv, kv_aux, out, dout, lse, dqkv, dkv_aux, B, T, N0, G, H, (cudaStream_t)stream);
 }
 
 int gava_temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int32_t B, int32_t T, int32_t H,

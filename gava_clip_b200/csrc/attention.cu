@@ -21,6 +21,7 @@ struct AttnArgs {
   const __nv_bfloat16* qkv;
   const __nv_bfloat16* kv_aux;
   __nv_bfloat16* out;
+  float* lse;   // optional [BT, H, N0] log2-domain log-sum-exp rows
   int T, N0, G, H, n_q, S, n_chunks, BT;
 };
 
@@ -161,6 +162,11 @@ __global__ void __launch_bounds__(128, 3) attention_kernel(const AttnArgs p) {
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    if (p.lse != nullptr && tg == 0) {
+      float* ls = p.lse + ((long long)f * p.H + h) * p.N0;
+      if (r0 < p.n_q) ls[r0] = m0 + log2f(l0);
+      if (r1 < p.n_q) ls[r1] = m1 + log2f(l1);
+    }
     __nv_bfloat16* o0 = p.out + ((long long)f * p.N0 + r0) * D + h * 64 + 2 * tg;
     __nv_bfloat16* o1 = o0 + 8LL * D;
 #pragma unroll
@@ -184,7 +190,7 @@ static int launch_attention(const AttnArgs& a, int frames, size_t smem_bytes, cu
   return check_launch("attention");
 }
 
-int attention(const void* qkv, const void* kv_aux, void* out, int B, int T, int N0, int G, int H, int n_q,
+int attention(const void* qkv, const void* kv_aux, void* out, float* lse, int B, int T, int N0, int G, int H, int n_q,
               cudaStream_t stream) {
   if (!qkv || !kv_aux || !out || B <= 0 || T <= 0 || N0 <= 0 || G < 0 || H <= 0 || n_q <= 0 || n_q > N0) {
     set_error("attention: bad arguments");
@@ -193,11 +199,12 @@ int attention(const void* qkv, const void* kv_aux, void* out, int B, int T, int 
   // tcgen05 path for every shape inside its specialisation (G = 8, T % 8 == 0, <= 256 keys); the mma.sync kernel
   // below covers the remaining shapes (ViT-L/14: 282 keys, long clips).  GAVA_ATTN_TC=0 forces the latter (A/B tests).
   static const bool use_tc = [] { const char* e = getenv("GAVA_ATTN_TC"); return !(e && e[0] == '0'); }();
-  if (use_tc && G == 8 && (T % 8) == 0 && ((N0 + 7) / 8 * 8 + 16 + T) <= 256) return attention_tc(qkv, kv_aux, out, B, T, N0, G, H, n_q, stream);
+  if (use_tc && G == 8 && (T % 8) == 0 && ((N0 + 7) / 8 * 8 + 16 + T) <= 256) return attention_tc(qkv, kv_aux, out, lse, B, T, N0, G, H, n_q, stream);
   AttnArgs a;
   a.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
   a.kv_aux = reinterpret_cast<const __nv_bfloat16*>(kv_aux);
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.lse = lse;
   a.T = T; a.N0 = N0; a.G = G; a.H = H; a.n_q = n_q; a.BT = B * T;
   a.S = N0 + G + T + 1;
   const int tiles16 = (a.S + 15) / 16;

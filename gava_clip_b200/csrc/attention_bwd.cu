@@ -28,11 +28,13 @@ struct AttnBwdArgs {
   const __nv_bfloat16* dout;    // [BT*N0, D]
   __nv_bfloat16* dqkv;          // [BT*N0, 3D]
   float* dkv_aux;               // [G+2BT, 2D]  atomically accumulated (zeroed by the launcher)
+  const float* lse;             // [BT, H, N0] log2-domain log-sum-exp rows saved by the forward, or null (recomputed)
   int T, N0, G, H, S, BT, q_pad, s_pad;
 };
 
 constexpr int AB_WARPS = 4;
 
+template <bool HAVE_LSE>
 __global__ void __launch_bounds__(32 * AB_WARPS, 2) attention_bwd_kernel(const AttnBwdArgs p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int h = blockIdx.x, f = blockIdx.y;
@@ -106,6 +108,10 @@ __global__ void __launch_bounds__(32 * AB_WARPS, 2) attention_bwd_kernel(const A
     acc += __shfl_xor_sync(0xffffffffu, acc, 4);
     if (ch == 0) s_delta[row] = acc;
   }
+  if constexpr (HAVE_LSE) {
+    const float* src = p.lse + ((long long)f * p.H + h) * p.N0;
+    for (int i = tid; i < p.q_pad; i += NT) s_lse[i] = (i < p.N0) ? src[i] : 0.f;   // padded rows: dO = 0 kills them
+  }
   cp_async_wait_all();
   __syncthreads();
 
@@ -114,16 +120,15 @@ __global__ void __launch_bounds__(32 * AB_WARPS, 2) attention_bwd_kernel(const A
   const int n_qt = p.q_pad >> 4, n_kt = p.s_pad >> 4;
   const int mi = lane >> 3;
 
-  // =========================================================== phase 1: lse, dQ
+  // =========================================================== lse pass (only when the forward did not save it)
+  if constexpr (!HAVE_LSE) {
   for (int mt = warp; mt < n_qt; mt += AB_WARPS) {
-    uint32_t qf[4][4], dof[4][4];
+    uint32_t qf[4][4];
     {
       const int row = mt * 16 + (lane & 15);
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
+      for (int ks = 0; ks < 4; ++ks)
         ldmatrix_x4(sQ + kv_off(row, 2 * ks + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
-        ldmatrix_x4(sdO + kv_off(row, 2 * ks + (lane >> 4)), dof[ks][0], dof[ks][1], dof[ks][2], dof[ks][3]);
-      }
     }
     // ---- lse (log2 domain) of rows g and g+8
     float m0 = -1e30f, m1 = -1e30f, l0 = 0.f, l1 = 0.f;
@@ -163,7 +168,27 @@ __global__ void __launch_bounds__(32 * AB_WARPS, 2) attention_bwd_kernel(const A
     }
     const float lse0 = m0 + log2f(l0), lse1 = m1 + log2f(l1);
     const int r0 = mt * 16 + g, r1 = r0 + 8;
-    if (tg == 0) { s_lse[r0] = lse0; s_lse[r1] = lse1; }
+    if (tg == 0) { s_lse[r0] = m0 + log2f(l0); s_lse[r1] = m1 + log2f(l1); }
+  }
+  __syncthreads();   // s_lse of every query tile is complete
+  }
+
+  // =========================================================== work units: 16-query tiles (dQ) and 16-key tiles (dK, dV),
+  // independent of each other once lse / delta are in shared memory: dealt round-robin to the warps
+  for (int u = warp; u < n_qt + n_kt; u += AB_WARPS) {
+  if (u < n_qt) {
+    const int mt = u;
+    uint32_t qf[4][4], dof[4][4];
+    {
+      const int row = mt * 16 + (lane & 15);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        ldmatrix_x4(sQ + kv_off(row, 2 * ks + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+        ldmatrix_x4(sdO + kv_off(row, 2 * ks + (lane >> 4)), dof[ks][0], dof[ks][1], dof[ks][2], dof[ks][3]);
+      }
+    }
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    const float lse0 = s_lse[r0], lse1 = s_lse[r1];
     const float dl0 = s_delta[r0], dl1 = s_delta[r1];
 
     float dq[8][4];
@@ -214,11 +239,8 @@ __global__ void __launch_bounds__(32 * AB_WARPS, 2) attention_bwd_kernel(const A
       if (r0 < p.N0) *reinterpret_cast<uint32_t*>(o0 + 8 * n) = pack_bf16x2(dq[n][0] * scale, dq[n][1] * scale);
       if (r1 < p.N0) *reinterpret_cast<uint32_t*>(o1 + 8 * n) = pack_bf16x2(dq[n][2] * scale, dq[n][3] * scale);
     }
-  }
-  __syncthreads();   // s_lse of every query tile is complete
-
-  // =========================================================== phase 2: dK, dV
-  for (int kt = warp; kt < n_kt; kt += AB_WARPS) {
+  } else {
+    const int kt = u - n_qt;
     uint32_t kf[4][4], vf[4][4];
     {
       const int row = kt * 16 + (lane & 15);
@@ -304,11 +326,12 @@ __global__ void __launch_bounds__(32 * AB_WARPS, 2) attention_bwd_kernel(const A
         }
       }
     }
-  }
+  }   // key-tile unit
+  }   // unit loop
 }
 
-int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, void* dqkv, float* dkv_aux,
-                  int B, int T, int N0, int G, int H, cudaStream_t stream) {
+int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, const float* lse, void* dqkv,
+                  float* dkv_aux, int B, int T, int N0, int G, int H, cudaStream_t stream) {
   if (!qkv || !kv_aux || !out || !dout || !dqkv || !dkv_aux || B <= 0 || T <= 0 || N0 <= 0 || G < 0 || H <= 0) {
     set_error("attention_bwd: bad arguments");
     return GAVA_ERR_ARG;
@@ -320,6 +343,7 @@ int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const vo
   a.dout = reinterpret_cast<const __nv_bfloat16*>(dout);
   a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   a.dkv_aux = dkv_aux;
+  a.lse = lse;
   a.T = T; a.N0 = N0; a.G = G; a.H = H; a.BT = B * T;
   a.S = N0 + G + T + 1;
   a.q_pad = (N0 + 15) / 16 * 16;
@@ -328,14 +352,16 @@ int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const vo
   if (smem_bytes > 226 * 1024) { set_error("attention_bwd: %d keys x %d queries exceed the shared-memory budget", a.S, N0); return GAVA_ERR_SHAPE; }
   static size_t attr_bytes = 0;
   if (smem_bytes > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(attention_bwd): %s", cudaGetErrorString(e)); return (int)e; }
     attr_bytes = smem_bytes;
   }
   const long long D = 64LL * H;
   cudaError_t e = cudaMemsetAsync(dkv_aux, 0, sizeof(float) * (size_t)(G + 2 * B * T) * 2 * D, stream);
   if (e != cudaSuccess) { set_error("attention_bwd memset: %s", cudaGetErrorString(e)); return (int)e; }
-  attention_bwd_kernel<<<dim3(H, B * T), 32 * AB_WARPS, smem_bytes, stream>>>(a);
+  if (lse) attention_bwd_kernel<true><<<dim3(H, B * T), 32 * AB_WARPS, smem_bytes, stream>>>(a);
+  else attention_bwd_kernel<false><<<dim3(H, B * T), 32 * AB_WARPS, smem_bytes, stream>>>(a);
   return check_launch("attention_bwd");
 }
 

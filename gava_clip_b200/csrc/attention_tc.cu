@@ -35,6 +35,7 @@ constexpr int ATC_QTILE_BYTES = 128 * 128;  // 128 rows x 64 bf16
 
 struct AttnTcArgs {
   __nv_bfloat16* out;
+  float* lse;      // optional [BT, H, N0]: log2-domain log-sum-exp of every query row (saved for the backward)
   int T, N0, G, H, n_q, BT, D;
   int kb_live;     // N0 rounded up to 8: smem row where the prompt rows start
   int num_items;   // BT * H
@@ -331,8 +332,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         // ---- O = P V done: normalise, cast, store this thread's 32 of the row's 64 output values
         { ATC_T0(); mbar_wait(&o_full[w], it_ph); ATC_ACC(d_ofull); }
         tc_fence_after();
-        const float inv = 1.0f / (sum + *ot_sum);   // partner's sum was written before its p_ready arrive
+        const float tot = sum + *ot_sum;            // partner's sum was written before its p_ready arrive
+        const float inv = 1.0f / tot;
         const int qrow = w * 128 + row_in_tile;
+        if (p.lse != nullptr && hh == 0 && qrow < p.n_q) p.lse[((long long)f * p.H + h) * p.N0 + qrow] = mc + log2f(tot);
         __nv_bfloat16* orow = p.out + ((long long)f * p.N0 + qrow) * p.D + h * 64 + hh * 32;
 #pragma unroll
         for (int d0 = 0; d0 < 32; d0 += 16) {
@@ -388,7 +391,7 @@ static int launch_attention_tc(const CUtensorMap& tq, const CUtensorMap& tkv, co
   return check_launch("attention_tc");
 }
 
-int attention_tc(const void* qkv, const void* kv_aux, void* out, int B, int T, int N0, int G, int H, int n_q,
+int attention_tc(const void* qkv, const void* kv_aux, void* out, float* lse, int B, int T, int N0, int G, int H, int n_q,
                  cudaStream_t stream) {
   const int kb_live = (N0 + 7) / 8 * 8;
   const int keys = kb_live + 8 + T + 8;          // live | global | local | summary box
@@ -407,6 +410,7 @@ int attention_tc(const void* qkv, const void* kv_aux, void* out, int B, int T, i
   if (rc) return rc;
   AttnTcArgs a;
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
+  a.lse = lse;
   a.T = T; a.N0 = N0; a.G = G; a.H = H; a.n_q = n_q; a.BT = BT; a.D = D;
   a.kb_live = kb_live;
   a.num_items = BT * H;

@@ -43,10 +43,10 @@ int prompt_rows(const float* global_prompts, const float* local_prompts, const f
                 float eps, cudaStream_t stream);
 
 // tcgen05/TMEM/TMA attention (attention_tc.cu); returns GAVA_ERR_SHAPE when the shape is outside its specialisation
-int attention_tc(const void* qkv, const void* kv_aux, void* out, int B, int T, int N0, int G, int H, int n_q,
+int attention_tc(const void* qkv, const void* kv_aux, void* out, float* lse, int B, int T, int N0, int G, int H, int n_q,
                  cudaStream_t stream);
 
-int attention(const void* qkv, const void* kv_aux, void* out, int B, int T, int N0, int G, int H, int n_q,
+int attention(const void* qkv, const void* kv_aux, void* out, float* lse, int B, int T, int N0, int G, int H, int n_q,
               cudaStream_t stream);
 
 int head(const float* frame_feat, const float* summary_tok, const float* text_hat, const int* class_offsets,
@@ -73,8 +73,8 @@ int layernorm_bwd(const void* dy, long long dy_stride, int dy_bf16, const float*
                   const float* add1, long long add1_stride, const float* add2, long long add2_stride, float* dx_out,
                   long long dx_stride, void* dx_bf16, long long dxb_stride, float* dw, float* db, long long rows, int D,
                   float eps, cudaStream_t stream);
-int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, void* dqkv, float* dkv_aux,
-                  int B, int T, int N0, int G, int H, cudaStream_t stream);
+int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, const float* lse, void* dqkv,
+                  float* dkv_aux, int B, int T, int N0, int G, int H, cudaStream_t stream);
 int temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int B, int T, int H, cudaStream_t stream);
 int causal_attention_bwd(const float* qkv, const void* dout, void* dqkv, int n_seq, int L, int H, cudaStream_t stream);
 int prompt_rows_bwd(const void* d_rows_n, const float* global_prompts, const float* local_prompts,

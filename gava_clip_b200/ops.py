@@ -327,8 +327,23 @@ def layernorm_bwd(dy: Tensor, x: Tensor, weight: Tensor, dx_out: Tensor, *, rows
     return dx_out
 
 
+def attention_train(qkv: Tensor, kv_aux: Tensor, out: Tensor, lse: Tensor, *, B: int, T: int, N0: int, G: int,
+                    H: int) -> Tensor:
+    """attention() over all query rows that also saves the per-row log-sum-exp (f32 [B*T, H, N0]) for attention_bwd."""
+    _req(qkv, torch.bfloat16, "attention qkv"); _req(kv_aux, torch.bfloat16, "attention kv_aux")
+    _req(out, torch.bfloat16, "attention out"); _req(lse, torch.float32, "attention lse")
+    D = H * 64
+    assert qkv.is_contiguous() and kv_aux.is_contiguous() and out.is_contiguous() and lse.is_contiguous()
+    assert qkv.shape == (B * T * N0, 3 * D) and kv_aux.shape == (G + 2 * B * T, 2 * D) and out.shape == (B * T * N0, D)
+    assert lse.numel() == B * T * H * N0
+    rc = _lib.load().gava_attention_train_fwd(qkv.data_ptr(), kv_aux.data_ptr(), out.data_ptr(), lse.data_ptr(), B, T, N0, G,
+                                              H, _stream())
+    _lib.check(rc, "gava_attention_train_fwd")
+    return out
+
+
 def attention_bwd(qkv: Tensor, kv_aux: Tensor, out: Tensor, dout: Tensor, dqkv: Tensor, dkv_aux: Tensor, *, B: int,
-                  T: int, N0: int, G: int, H: int) -> None:
+                  T: int, N0: int, G: int, H: int, lse: Optional[Tensor] = None) -> None:
     for t in (qkv, kv_aux, out, dout, dqkv):
         _req(t, torch.bfloat16, "attention_bwd"); assert t.is_contiguous()
     _req(dkv_aux, torch.float32, "attention_bwd dkv_aux")
@@ -336,8 +351,10 @@ def attention_bwd(qkv: Tensor, kv_aux: Tensor, out: Tensor, dout: Tensor, dqkv: 
     assert qkv.shape == (B * T * N0, 3 * D) and dqkv.shape == qkv.shape and out.shape == (B * T * N0, D)
     assert dout.shape == out.shape and kv_aux.shape == (G + 2 * B * T, 2 * D) and dkv_aux.shape == kv_aux.shape
     assert dkv_aux.is_contiguous()
-    rc = _lib.load().gava_attention_bwd(qkv.data_ptr(), kv_aux.data_ptr(), out.data_ptr(), dout.data_ptr(), dqkv.data_ptr(),
-                                        dkv_aux.data_ptr(), B, T, N0, G, H, _stream())
+    if lse is not None:
+        _req(lse, torch.float32, "attention_bwd lse"); assert lse.is_contiguous() and lse.numel() == B * T * H * N0
+    rc = _lib.load().gava_attention_bwd(qkv.data_ptr(), kv_aux.data_ptr(), out.data_ptr(), dout.data_ptr(), _ptr(lse),
+                                        dqkv.data_ptr(), dkv_aux.data_ptr(), B, T, N0, G, H, _stream())
     _lib.check(rc, "gava_attention_bwd")
 
 

@@ -94,11 +94,10 @@ class TowerTrainer(TowerEngine):
             key = (src.data_ptr(), src._version)
             if name in P and vers.get(name) == key:
                 return
-            val = src.detach().t().to(self.device, torch.bfloat16).contiguous()
-            if name in P and P[name].shape == val.shape:
-                P[name].copy_(val)
+            if name in P and P[name].shape == (src.shape[1], src.shape[0]):
+                P[name].copy_(src.detach().t())             # one strided-read kernel
             else:
-                P[name] = val
+                P[name] = src.detach().t().to(self.device, torch.bfloat16).contiguous()
             vers[name] = key
 
         D = e.feature_dim
@@ -131,6 +130,7 @@ class TowerTrainer(TowerEngine):
             # ---- tape
             "x0_pre": z(M, D, dt=f32), "x_in": [z(M, D, dt=f32) for _ in range(L + 1)], "x_mid": per_layer(M, D, dt=f32),
             "qkv": per_layer(M, 3 * D, dt=bf), "kvaux": per_layer(R, 2 * D, dt=bf), "o": per_layer(M, D, dt=bf),
+            "lse": per_layer(BT * e.num_heads * N0, dt=f32),
             "a1": per_layer(M, Dm, dt=bf), "cls_proj": per_layer(BT, D, dt=f32), "summary": per_layer(BT, D, dt=f32),
             "sum_n": per_layer(BT, D, dt=bf), "sqkv": per_layer(BT, 3 * D, dt=bf), "smix": per_layer(BT, D, dt=bf),
             # ---- forward scratch
@@ -188,7 +188,7 @@ class TowerTrainer(TowerEngine):
             # x = x + attn(norm1(x))   (utils.py:190-191)
             ops.layernorm(xin, P[k + "norm1.w"], P[k + "norm1.b"], xn, rows=M, in_row_stride=D)
             ops.gemm(xn, P[k + "qkv.w"], W["qkv"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"])
-            ops.attention(W["qkv"][i], W["kvaux"][i], W["o"][i], B=B, T=T, N0=N0, G=G, H=H)
+            ops.attention_train(W["qkv"][i], W["kvaux"][i], W["o"][i], W["lse"][i], B=B, T=T, N0=N0, G=G, H=H)
             ops.gemm(W["o"][i], P[k + "out.w"], xmid, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "out.b"], resid=xin)
             # x = x + fc2(QuickGELU(fc1(norm2(x))))   (utils.py:199); the pre-activations stay for the DGELU epilogue
             ops.layernorm(xmid, P[k + "norm2.w"], P[k + "norm2.b"], xn, rows=M, in_row_stride=D)
@@ -248,7 +248,8 @@ class TowerTrainer(TowerEngine):
             ops.layernorm_bwd(gD, W["x_mid"][i], P[k + "norm2.w"], dx, rows=M, D=D, add1=dx, dx_bf16=dxb)
             # ---- attention: dO = dx Wo; (dq, dk, dv, d kv_aux); dx += dLN1(dqkv Wqkv)
             ops.gemm(dxb, P[k + "out.wT"], gD, mode=ops.EPI_BIAS_BF16)
-            ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G, H=H)
+            ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G, H=H,
+                              lse=W["lse"][i])
             ops.gemm(W["dqkv"], P[k + "qkv.wT"], gD, mode=ops.EPI_BIAS_BF16)
             ops.layernorm_bwd(gD, W["x_in"][i], P[k + "norm1.w"], dx, rows=M, D=D, add1=dx)
             # ---- K/V-only prompt rows: d kv_aux -> normalised rows -> global / local / summary / cls_proj gradients

@@ -170,12 +170,17 @@ class TowerEngine:
             key = tuple((t.data_ptr(), t._version) for t in srcs)
             if name in P and vers.get(name) == key:
                 return
-            val = make()
             old = P.get(name)
-            if old is not None and old.shape == val.shape and old.dtype == val.dtype:
-                old.copy_(val)
+            if old is not None and len(srcs) == 1 and old.shape == srcs[0].shape and old.device == srcs[0].device:
+                if old.data_ptr() != srcs[0].data_ptr():      # an fp32 "copy" may simply alias the parameter
+                    old.copy_(srcs[0].detach())               # one kernel: dtype conversion inside the copy
+            elif old is not None and len(srcs) > 1 and old.shape[0] == sum(t.shape[0] for t in srcs):
+                r = 0
+                for t in srcs:                                # concatenated q|k|v blocks: slice-wise converting copies
+                    old[r: r + t.shape[0]].copy_(t.detach())
+                    r += t.shape[0]
             else:
-                P[name] = val
+                P[name] = make()
                 moved = True
             vers[name] = key
 

@@ -87,10 +87,26 @@ def test_attention_bwd(cuda, B, T, N0, G, H):
     dkv_aux = torch.empty(G + 2 * BT, 2 * D, device=cuda)
     ops.attention_bwd(qkv, kv_aux, out, dout, dqkv, dkv_aux, B=B, T=T, N0=N0, G=G, H=H)
     # bf16 P / dS operands and bf16 outputs: ~2^-8 relative per element, averaged down by the reductions
-    for name, got, ref in (("dq", dqkv[:, :D], qr.grad[:, :D]), ("dk", dqkv[:, D:2 * D], qr.grad[:, D:2 * D]),
-                           ("dv", dqkv[:, 2 * D:], qr.grad[:, 2 * D:]), ("dk_aux", dkv_aux[:, :D], ar.grad[:, :D]),
-                           ("dv_aux", dkv_aux[:, D:], ar.grad[:, D:])):
-        assert _rel(got.float(), ref) < 2e-2, name
+    def check(dqkv, dkv_aux):
+        for name, got, ref in (("dq", dqkv[:, :D], qr.grad[:, :D]), ("dk", dqkv[:, D:2 * D], qr.grad[:, D:2 * D]),
+                               ("dv", dqkv[:, 2 * D:], qr.grad[:, 2 * D:]), ("dk_aux", dkv_aux[:, :D], ar.grad[:, :D]),
+                               ("dv_aux", dkv_aux[:, D:], ar.grad[:, D:])):
+            assert _rel(got.float(), ref) < 2e-2, name
+    check(dqkv, dkv_aux)
+    # training forward: same output plus the saved log-sum-exp rows, which the backward then reuses
+    out2 = torch.empty_like(out)
+    lse = torch.empty(BT, H, N0, device=cuda)
+    ops.attention_train(qkv, kv_aux, out2, lse, B=B, T=T, N0=N0, G=G, H=H)
+    assert _rel(out2.float(), o_ref.detach()) < 1e-2
+    q, k, v = qkv.float().view(BT, N0, 3, H, 64).unbind(2)
+    ka = kv_aux.float().view(-1, 2, H, 64)[:, 0]
+    for f in (0, BT - 1):
+        rows = list(range(G)) + [G + (f // T) * T + t for t in range(T)] + [G + BT + f]
+        sc = torch.einsum("qhc,khc->hqk", q[f] / 8.0, torch.cat([k[f], ka[rows]], 0))
+        assert float((lse[f] - torch.logsumexp(sc, -1) * 1.4426950408889634).abs().max()) < 2e-3
+    dqkv2 = torch.zeros_like(qkv); dkv_aux2 = torch.empty_like(dkv_aux)
+    ops.attention_bwd(qkv, kv_aux, out2, dout, dqkv2, dkv_aux2, B=B, T=T, N0=N0, G=G, H=H, lse=lse)
+    check(dqkv2, dkv_aux2)
 
 
 @pytest.mark.parametrize("B,T,H", [(3, 8, 12), (2, 70, 2), (1, 3, 2)])

@@ -354,10 +354,11 @@ def test_unsupported_trainable_parameter_is_refused(cuda):
 
 
 def test_finetuner_step_matches_torch_adamw(cuda):
-    """FineTuner (flat parameters + fused AdamW kernel) against torch.optim.AdamW on a twin model fed the same gradients;
-    the second step must see the updated weights (packed bf16 copies / cached text features are refreshed)."""
-    import torch.nn.functional as Fn
-    from gava_clip_b200.finetune import FineTuner, finetune_loss
+    """FineTuner (flat parameters + fused AdamW kernel) against torch.optim.AdamW on a twin model fed the SAME gradients
+    (the backward itself is only reproducible to bf16 rounding, see test_finetune_gradients_match_oracle, and Adam turns
+    a sign flip of a near-zero gradient into a full +-lr step); the following forward must see the updated weights
+    (packed bf16 copies / text features are refreshed) and the loss must go down on the repeated batch."""
+    from gava_clip_b200.finetune import FineTuner
     video = fx.make_inputs("tiny")["video"].to(cuda)
     labels = torch.tensor([2, 0], device=cuda)
     a, _, _ = build_model("tiny", device=cuda)
@@ -365,26 +366,26 @@ def test_finetuner_step_matches_torch_adamw(cuda):
     a.train(); b.train()
     keys_before = list(a.state_dict().keys())
     tuner = FineTuner(a, lr=1e-3, weight_decay=0.2)
+    pb = dict(b.named_parameters())
     opt = torch.optim.AdamW([p for p in b.parameters() if p.requires_grad], lr=1e-3, weight_decay=0.2)
     losses = []
-    for _ in range(3):
-        la = tuner.step(video, labels)
-        opt.zero_grad(set_to_none=True)
-        lb = finetune_loss(b(video)[0], labels)
-        lb.backward()
+    for _ in range(4):
+        tuner.zero_grad()
+        losses.append(float(tuner.forward_backward(video, labels)))
+        tuner.reduce_gradients()
+        for n, p in a.named_parameters():
+            if p.requires_grad:
+                pb[n].grad = p.grad.detach().clone()
+        tuner.optimizer_step()
         opt.step()
-        losses.append((float(la), float(lb.detach())))
     assert list(a.state_dict().keys()) == keys_before
-    assert abs(losses[0][0] - losses[0][1]) < 1e-5 * max(1.0, abs(losses[0][1]))
-    assert losses[2][0] != losses[0][0]                      # the weights moved and the forward saw it
-    for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
-        if pa.requires_grad:
-            # Adam normalises the update to ~lr per element, so atomics-order noise in tiny gradients can flip a few
-            # elements by a fraction of lr; compare against the step size
-            assert float((pa - pb).abs().max()) < 3 * 1e-3 * 0.35, n
-            assert rel_l2(pa, pb) < 2e-3, n
-    for la, lb in losses:
-        assert abs(la - lb) < 2e-2 * max(1e-3, abs(lb))
+    for n, p in a.named_parameters():
+        if p.requires_grad:
+            assert float((p - pb[n]).abs().max()) < 2e-6, n
+    assert losses[3] < losses[0]                      # the weights moved and the forward saw it
+    # state_dict still holds plain tensors of the right shapes (checkpoint contract) and they carry the updates
+    sd = a.state_dict()
+    assert all(sd[n].shape == pb[n].shape for n in pb)
 
 
 @pytest.mark.parametrize("name", ["tiny", "b16_t8"])
