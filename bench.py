@@ -448,7 +448,7 @@ def run_finetune(args):
     per = {}
     if rank == 0:
         names = ["gemm", "layernorm", "patch_gather", "cls_rows", "temporal_attention", "prompt_rows", "attention",
-                 "quickgelu_bf16", "layernorm_bwd", "attention_bwd", "temporal_attention_bwd", "prompt_rows_bwd", "group_sum",
+                 "attention_train", "quickgelu_bf16", "causal_attention_f32", "causal_attention_bwd", "split_bf16", "quickgelu_f32", "layernorm_bwd", "attention_bwd", "temporal_attention_bwd", "prompt_rows_bwd", "group_sum",
                  "transpose_bf16", "adamw_step"]
         orig = {n: getattr(ops, n) for n in names}
         records = []

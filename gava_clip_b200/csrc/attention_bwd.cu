@@ -33,6 +33,10 @@ struct AttnBwdArgs {
 };
 
 constexpr int AB_WARPS = 4;
+#ifndef GAVA_AB_UNROLL
+#define GAVA_AB_UNROLL 2
+#endif
+constexpr int AB_UNROLL = GAVA_AB_UNROLL;   // key / query tiles per loop trip: independent MMA chains to overlap
 
 template <bool HAVE_LSE>
 __global__ void __launch_bounds__(32 * AB_WARPS, 2) attention_bwd_kernel(const AttnBwdArgs p) {
@@ -194,6 +198,7 @@ __global__ void __launch_bounds__(32 * AB_WARPS, 2) attention_bwd_kernel(const A
     float dq[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) { dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f; }
+#pragma unroll AB_UNROLL
     for (int kt = 0; kt < n_kt; ++kt) {
       float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       float dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -253,6 +258,7 @@ __global__ void __launch_bounds__(32 * AB_WARPS, 2) attention_bwd_kernel(const A
     float dk[8][4], dv[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) { dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f; dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f; }
+#pragma unroll AB_UNROLL
     for (int qt = 0; qt < n_qt; ++qt) {
       float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       float dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
