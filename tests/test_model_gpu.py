@@ -406,3 +406,39 @@ def test_text_trainer_matches_torch_autograd(cuda, name):
     (out * w).sum().backward()
     assert rel_err(out.detach(), ref.detach()) < 1.5e-2
     assert rel_l2(pb.grad, pa.grad) < 4e-2 and _cos(pb.grad, pa.grad) > 0.999
+
+
+def test_finetune_recipe_shape_t70(cuda):
+    """The shipped fine-tune recipe runs 70-frame clips (train_scripts/updrs_3cls_train_tulip.sh: --num_frames 70,
+    --batch_size 4): 276 keys per frame (mma.sync attention forward, 288-key backward tiles), BT not a multiple of 64
+    (zero-padded wgrad operands).  One clip, forward + backward, visual-prompt gradients against fp32 oracle autograd."""
+    import torch.nn.functional as Fn
+    from gava_clip_b200 import VitaCLIP, tokenizer
+    from oracle import vita_oracle as vo
+    tokenizer.register_tokens(fx.load_tokens())
+    kw, _ = fx.case_kwargs("b16_t8")
+    kw = dict(kw, num_frames=70, num_layers=3)               # 3 layers keep the CPU oracle's autograd to a few seconds
+    model = VitaCLIP(**kw)
+    fx.fill_params_(model.state_dict().items(), seed=1)
+    model.prompt_learner.refresh_token_embeddings(model.textual)
+    cpu_sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    tok = [t.clone() for t in model.tokenized_prompts]
+    model = model.to(cuda).train()
+    g = torch.Generator().manual_seed(5)
+    video = torch.randn(1, 3, 70, 224, 224, generator=g)
+    labels = torch.tensor([1])
+    logits = model(video.to(cuda))[0]
+    Fn.cross_entropy(logits, labels.to(cuda)).backward()
+    names = ["visual.time_embed", "visual.global_prompts", "visual.blocks.0.local_prompts",
+             "visual.blocks.1.summary_attn_layer.out_proj.weight", "visual.blocks.2.summary_ln.weight"]
+    for n in names:
+        cpu_sd[n].requires_grad_(True)
+    v, _ = vo.vision_encoder(cpu_sd, video, num_frames=70, num_heads=12, num_layers=3)
+    prompts = vo.assemble_prompts(cpu_sd, tok, 8, kapt=False)
+    tfs = [vo.text_encoder(cpu_sd, p, t, heads=8, layers=12) for p, t in zip(prompts, tok)]
+    ref_logits, _ = vo.logit_head(v, tfs, cpu_sd["logit_scale"])
+    Fn.cross_entropy(ref_logits, labels).backward()
+    assert rel_err(logits.detach(), ref_logits.detach()) < TOL
+    params = dict(model.named_parameters())
+    for n in names:
+        assert _cos(params[n].grad, cpu_sd[n].grad) > 0.995 and rel_l2(params[n].grad, cpu_sd[n].grad) < 8e-2, n
