@@ -36,6 +36,7 @@ class GemmEpilogue(C.Structure):
         ("time_embed", C.c_void_p),
         ("aux", C.c_void_p),
         ("ld_aux", C.c_int64),
+        ("aux_out", C.c_void_p),
     ]
 
 

@@ -32,14 +32,18 @@ struct AttnBwdArgs {
   int T, N0, G, H, S, BT, q_pad, s_pad;
 };
 
-constexpr int AB_WARPS = 4;
+#ifndef GAVA_AB_WARPS
+#define GAVA_AB_WARPS 4
+#endif
+constexpr int AB_WARPS = GAVA_AB_WARPS;     // 4: 255 registers/thread, K/V A-fragments live in registers; 8: <= 128 registers
+constexpr bool AB_RELOAD_KV = AB_WARPS > 4; //    (2 CTAs x 8 warps per SM), key-tile units re-read their K/V fragments per trip
 #ifndef GAVA_AB_UNROLL
-#define GAVA_AB_UNROLL 2
+#define GAVA_AB_UNROLL (GAVA_AB_WARPS > 4 ? 1 : 2)
 #endif
 constexpr int AB_UNROLL = GAVA_AB_UNROLL;   // key / query tiles per loop trip: independent MMA chains to overlap
 
 template <bool HAVE_LSE>
-__global__ void __launch_bounds__(32 * AB_WARPS, 2) attention_bwd_kernel(const AttnBwdArgs p) {
+__global__ void __launch_bounds__(32 * AB_WARPS, AB_WARPS > 4 ? 2 : 2) attention_bwd_kernel(const AttnBwdArgs p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int h = blockIdx.x, f = blockIdx.y;
   const int D = p.H * 64;
@@ -246,13 +250,13 @@ __global__ void __launch_bounds__(32 * AB_WARPS, 2) attention_bwd_kernel(const A
     }
   } else {
     const int kt = u - n_qt;
-    uint32_t kf[4][4], vf[4][4];
-    {
-      const int row = kt * 16 + (lane & 15);
+    uint32_t kf[AB_RELOAD_KV ? 1 : 4][4], vf[AB_RELOAD_KV ? 1 : 4][4];
+    const int krow_a = kt * 16 + (lane & 15);
+    if constexpr (!AB_RELOAD_KV) {
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        ldmatrix_x4(sK + kv_off(row, 2 * ks + (lane >> 4)), kf[ks][0], kf[ks][1], kf[ks][2], kf[ks][3]);
-        ldmatrix_x4(sV + kv_off(row, 2 * ks + (lane >> 4)), vf[ks][0], vf[ks][1], vf[ks][2], vf[ks][3]);
+        ldmatrix_x4(sK + kv_off(krow_a, 2 * ks + (lane >> 4)), kf[ks][0], kf[ks][1], kf[ks][2], kf[ks][3]);
+        ldmatrix_x4(sV + kv_off(krow_a, 2 * ks + (lane >> 4)), vf[ks][0], vf[ks][1], vf[ks][2], vf[ks][3]);
       }
     }
     float dk[8][4], dv[8][4];
@@ -266,12 +270,17 @@ __global__ void __launch_bounds__(32 * AB_WARPS, 2) attention_bwd_kernel(const A
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         uint32_t b0, b1, b2, b3;
+        constexpr int fi = AB_RELOAD_KV ? 0 : 1;
+        if constexpr (AB_RELOAD_KV) {
+          ldmatrix_x4(sK + kv_off(krow_a, 2 * ks + (lane >> 4)), kf[0][0], kf[0][1], kf[0][2], kf[0][3]);
+          ldmatrix_x4(sV + kv_off(krow_a, 2 * ks + (lane >> 4)), vf[0][0], vf[0][1], vf[0][2], vf[0][3]);
+        }
         ldmatrix_x4(sQ + kv_off(qrow, 2 * ks + (mi & 1)), b0, b1, b2, b3);
-        mma_bf16_16816(s[0], kf[ks], b0, b1);
-        mma_bf16_16816(s[1], kf[ks], b2, b3);
+        mma_bf16_16816(s[0], kf[fi * ks], b0, b1);
+        mma_bf16_16816(s[1], kf[fi * ks], b2, b3);
         ldmatrix_x4(sdO + kv_off(qrow, 2 * ks + (mi & 1)), b0, b1, b2, b3);
-        mma_bf16_16816(dp[0], vf[ks], b0, b1);
-        mma_bf16_16816(dp[1], vf[ks], b2, b3);
+        mma_bf16_16816(dp[0], vf[fi * ks], b0, b1);
+        mma_bf16_16816(dp[1], vf[fi * ks], b2, b3);
       }
       uint32_t pa[4], da[4];
       {

@@ -52,6 +52,7 @@ struct GemmArgs {
   const float* time_embed;  // [T, N]
   int T;
   const __nv_bfloat16* aux;  // EPI_DGELU_BF16: fc1 pre-activations bf16 [M, ld_aux]
+  __nv_bfloat16* aux_out;    // EPI_BIAS_GELU_BF16 (optional): also store the pre-activations acc + bias here, pitch ld_aux
   long long ld_aux;
 };
 
@@ -83,36 +84,40 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
         acc[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z; acc[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
       }
     }
+    // stage as bf16 (row pitch 64 B = 4 chunks of 16 B, chunk' = chunk ^ ((row >> 1) & 3)), then store transposed
+    auto stage_store = [&](const float (&a)[32], __nv_bfloat16* base, long long ld, bool dgelu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 w;
+        w.x = pack_bf16x2(a[8 * j + 0], a[8 * j + 1]);
+        w.y = pack_bf16x2(a[8 * j + 2], a[8 * j + 3]);
+        w.z = pack_bf16x2(a[8 * j + 4], a[8 * j + 5]);
+        w.w = pack_bf16x2(a[8 * j + 6], a[8 * j + 7]);
+        *reinterpret_cast<uint4*>(stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = w;
+      }
+      __syncwarp();
+      const int c = lane & 3;
+      __nv_bfloat16* obase = base + col0 + 8 * c;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = 8 * i + (lane >> 2);
+        uint4 w = *reinterpret_cast<const uint4*>(stage + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+        if (dgelu) {   // dgrad through QuickGELU: multiply by g'(a1), a1 read coalesced (row segments)
+          if (row0 + r < p.M) {
+            const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(p.aux + (long long)(row0 + r) * p.ld_aux + col0 + 8 * c));
+            w.x = dgelu_mul2(w.x, a1.x); w.y = dgelu_mul2(w.y, a1.y); w.z = dgelu_mul2(w.z, a1.z); w.w = dgelu_mul2(w.w, a1.w);
+          }
+        }
+        if (row0 + r < p.M) *reinterpret_cast<uint4*>(obase + (long long)(row0 + r) * ld) = w;
+      }
+      __syncwarp();
+    };
     if constexpr (MODE == EPI_BIAS_GELU_BF16) {
+      if (p.aux_out != nullptr) stage_store(acc, p.aux_out, p.ld_aux, false);   // training forward keeps the pre-activations
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = quick_gelu(acc[j]);
     }
-    // stage as bf16: row pitch 64 B (4 chunks of 16 B), chunk' = chunk ^ ((row >> 1) & 3)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 w;
-      w.x = pack_bf16x2(acc[8 * j + 0], acc[8 * j + 1]);
-      w.y = pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]);
-      w.z = pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]);
-      w.w = pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]);
-      *reinterpret_cast<uint4*>(stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = w;
-    }
-    __syncwarp();
-    const int c = lane & 3;
-    __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + col0 + 8 * c;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = 8 * i + (lane >> 2);
-      uint4 w = *reinterpret_cast<const uint4*>(stage + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
-      if constexpr (MODE == EPI_DGELU_BF16) {   // dgrad through QuickGELU: multiply by g'(a1), a1 read coalesced (row segments)
-        if (row0 + r < p.M) {
-          const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.aux + (long long)(row0 + r) * p.ld_aux + col0 + 8 * c));
-          w.x = dgelu_mul2(w.x, a.x); w.y = dgelu_mul2(w.y, a.y); w.z = dgelu_mul2(w.z, a.z); w.w = dgelu_mul2(w.w, a.w);
-        }
-      }
-      if (row0 + r < p.M) *reinterpret_cast<uint4*>(obase + (long long)(row0 + r) * p.ldo) = w;
-    }
-    __syncwarp();
+    stage_store(acc, reinterpret_cast<__nv_bfloat16*>(p.out), p.ldo, MODE == EPI_DGELU_BF16);
   } else {
     // stage raw fp32 accumulators: row pitch 128 B (8 chunks of 16 B), chunk' = chunk ^ (row & 7)
 #pragma unroll
@@ -667,6 +672,7 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
   a.group = epi->group; a.group_stride = epi->group_stride; a.row_offset = epi->row_offset;
   a.pos = epi->pos; a.time_embed = epi->time_embed; a.T = epi->T;
   a.aux = reinterpret_cast<const __nv_bfloat16*>(epi->aux); a.ld_aux = epi->ld_aux;
+  a.aux_out = epi->mode == EPI_BIAS_GELU_BF16 ? reinterpret_cast<__nv_bfloat16*>(epi->aux_out) : nullptr;
   if (pair) return dispatch_mode2(epi->mode, ta, tb, a, stream);
   return bn_eff == 256 ? dispatch_mode<256>(epi->mode, ta, tb, a, stream) : dispatch_mode<128>(epi->mode, ta, tb, a, stream);
 }

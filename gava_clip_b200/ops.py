@@ -45,7 +45,8 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
 
 def gemm(a: Tensor, w: Tensor, out: Tensor, *, mode: int, bias: Optional[Tensor] = None,
          resid: Optional[Tensor] = None, pos: Optional[Tensor] = None, time_embed: Optional[Tensor] = None,
-         group: int = 0, group_stride: int = 0, row_offset: int = 0, T: int = 0, aux: Optional[Tensor] = None) -> Tensor:
+         group: int = 0, group_stride: int = 0, row_offset: int = 0, T: int = 0, aux: Optional[Tensor] = None,
+         aux_out: Optional[Tensor] = None) -> Tensor:
     """out = epilogue(a @ w.T).  a: bf16 [M,K] (row stride free), w: bf16 [N,K], fp32 bias [N]."""
     _req(a, torch.bfloat16, "gemm a"); _req(w, torch.bfloat16, "gemm w")
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
@@ -80,6 +81,11 @@ def gemm(a: Tensor, w: Tensor, out: Tensor, *, mode: int, bias: Optional[Tensor]
         epi.aux = aux.data_ptr(); epi.ld_aux = aux.stride(0)
     else:
         assert out.shape[0] >= M
+    if aux_out is not None:      # GELU epilogue of the training forward: keep the pre-activations too
+        assert mode == EPI_BIAS_GELU_BF16
+        _req(aux_out, torch.bfloat16, "gemm aux_out")
+        assert aux_out.dim() == 2 and aux_out.stride(1) == 1 and aux_out.shape[0] >= M and aux_out.shape[1] >= N
+        epi.aux_out = aux_out.data_ptr(); epi.ld_aux = aux_out.stride(0)
     rc = _lib.load().gava_gemm_bf16_fwd(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), M, N, K,
                                         C.byref(epi), _stream())
     _lib.check(rc, "gava_gemm_bf16_fwd")

@@ -192,8 +192,7 @@ class TowerTrainer(TowerEngine):
             ops.gemm(W["o"][i], P[k + "out.w"], xmid, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "out.b"], resid=xin)
             # x = x + fc2(QuickGELU(fc1(norm2(x))))   (utils.py:199); the pre-activations stay for the DGELU epilogue
             ops.layernorm(xmid, P[k + "norm2.w"], P[k + "norm2.b"], xn, rows=M, in_row_stride=D)
-            ops.gemm(xn, P[k + "fc1.w"], W["a1"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "fc1.b"])
-            ops.quickgelu_bf16(W["a1"][i], h)
+            ops.gemm(xn, P[k + "fc1.w"], h, mode=ops.EPI_BIAS_GELU_BF16, bias=P[k + "fc1.b"], aux_out=W["a1"][i])
             ops.gemm(h, P[k + "fc2.w"], xnext, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"], resid=xmid)
 
         ops.layernorm(W["x_in"][L], P["ln_post.w"], P["ln_post.b"], W["cls_bf"], rows=BT, in_row_stride=N0 * D)
@@ -220,6 +219,10 @@ class TowerTrainer(TowerEngine):
         pending: List = []
         n0 = ops.launch_count()
 
+        # bf16 copy of dx for the dgrad GEMMs: written by the LayerNorm-backward kernels as a by-product; only the BT cls
+        # rows change outside those kernels (ln_post / cls_proj contributions) and are re-cast by a BT-row launch
+        cast_cls = lambda: ops.layernorm(dx, None, None, dxb, rows=BT, in_row_stride=N0 * D, out_row_stride=N0 * D)
+        dxb.zero_()
         # ---- frame_feat = ln_post(x_cls) @ proj   (vision_encoder.py:126-127)
         dx.zero_()
         if d_frame_feat is not None:
@@ -234,6 +237,7 @@ class TowerTrainer(TowerEngine):
             ops.gemm(W["dff_bf"], P["proj.w"], W["dcls_n"], mode=ops.EPI_BIAS_BF16)
             ops.layernorm_bwd(W["dcls_n"], W["x_in"][L], P["ln_post.w"], dx, rows=BT, D=D, x_stride=N0 * D,
                               dx_stride=N0 * D)
+            cast_cls()
         ext = None
         if d_summary is not None:
             ext = d_summary.contiguous().float()
@@ -242,7 +246,6 @@ class TowerTrainer(TowerEngine):
             k, kb = f"b{i}.", f"blocks.{i}."
             cp, sm = W["cls_proj"][i], W["summary"][i]
             # ---- MLP: dx += dLN2( (dx W2 * g'(a1)) W1 )
-            ops.layernorm(dx, None, None, dxb, rows=M, in_row_stride=D)                        # cast
             ops.gemm(dxb, P[k + "fc2.wT"], W["g4"], mode=ops.EPI_DGELU_BF16, aux=W["a1"][i])
             ops.gemm(W["g4"], P[k + "fc1.wT"], gD, mode=ops.EPI_BIAS_BF16)
             ops.layernorm_bwd(gD, W["x_mid"][i], P[k + "norm2.w"], dx, rows=M, D=D, add1=dx, dx_bf16=dxb)
@@ -251,7 +254,7 @@ class TowerTrainer(TowerEngine):
             ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G, H=H,
                               lse=W["lse"][i])
             ops.gemm(W["dqkv"], P[k + "qkv.wT"], gD, mode=ops.EPI_BIAS_BF16)
-            ops.layernorm_bwd(gD, W["x_in"][i], P[k + "norm1.w"], dx, rows=M, D=D, add1=dx)
+            ops.layernorm_bwd(gD, W["x_in"][i], P[k + "norm1.w"], dx, rows=M, D=D, add1=dx, dx_bf16=dxb)
             # ---- K/V-only prompt rows: d kv_aux -> normalised rows -> global / local / summary / cls_proj gradients
             ops.layernorm(W["dkvaux"].view(2 * R, D), None, None, W["dkvaux_bf"].view(2 * R, D), rows=2 * R, in_row_stride=D)
             ops.gemm(W["dkvaux_bf"], P[k + "qkv.wT"][:, D:], W["daux_n"], mode=ops.EPI_BIAS_BF16)
@@ -273,6 +276,7 @@ class TowerTrainer(TowerEngine):
                               db=g[kb + "summary_ln.bias"])
             # ---- cls_proj (frozen): dx[cls rows] += d_cp Wc
             ops.gemm(W["d_cp_bf"], P[k + "cls.wT"], dx_cls, mode=ops.EPI_BIAS_RESID_F32, resid=dx_cls)
+            cast_cls()
             if hook is not None:
                 pending.append(hook(self.layer_slices[i]))   # this layer's gradients are final: start their all-reduce now
 

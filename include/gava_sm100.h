@@ -50,6 +50,7 @@ typedef struct gava_gemm_epilogue {
   const float* time_embed; /* PATCH: f32 [T, N]        (visual.time_embed, already resized to T) */
   const void* aux;         /* DGELU: bf16 [M, ld_aux] */
   int64_t ld_aux;
+  void* aux_out;           /* GELU (optional): also store the pre-activations acc + bias as bf16 [M, ld_aux] */
 } gava_gemm_epilogue;
 
 int gava_version(void);
