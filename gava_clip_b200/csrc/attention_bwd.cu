@@ -30,6 +30,7 @@ struct AttnBwdArgs {
   float* dkv_aux;               // [G+2BT, 2D]  atomically accumulated (zeroed by the launcher)
   const float* lse;             // [BT, H, N0] log2-domain log-sum-exp rows saved by the forward, or null (recomputed)
   int T, N0, G, H, S, BT, q_pad, s_pad;
+  int n_q;   // query rows per frame that carry a gradient (N0, or 1 in the last layer: only the cls row reaches the output)
 };
 
 #ifndef GAVA_AB_WARPS
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(32 * AB_WARPS, AB_WARPS > 4 ? 2 : 2) attention
   for (int i = tid; i < p.q_pad * 8; i += NT) {
     const int row = i >> 3, ch = i & 7;
     const uint32_t off = kv_off(row, ch);
-    if (row < p.N0) {
+    if (row < p.n_q) {
       cp_async16(sQ + off, p.qkv + ((long long)f * p.N0 + row) * ldq + h * 64 + ch * 8);
       cp_async16(sdO + off, p.dout + ((long long)f * p.N0 + row) * D + h * 64 + ch * 8);
     } else {
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(32 * AB_WARPS, AB_WARPS > 4 ? 2 : 2) attention
   for (int i = tid; i < p.q_pad * 8; i += NT) {
     const int row = i >> 3, ch = i & 7;
     float acc = 0.f;
-    if (row < p.N0) {
+    if (row < p.n_q) {
       const long long off = ((long long)f * p.N0 + row) * D + h * 64 + ch * 8;
       const uint4 o = *reinterpret_cast<const uint4*>(p.out + off);
       const uint4 d = *reinterpret_cast<const uint4*>(p.dout + off);
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(32 * AB_WARPS, AB_WARPS > 4 ? 2 : 2) attention
   }
   if constexpr (HAVE_LSE) {
     const float* src = p.lse + ((long long)f * p.H + h) * p.N0;
-    for (int i = tid; i < p.q_pad; i += NT) s_lse[i] = (i < p.N0) ? src[i] : 0.f;   // padded rows: dO = 0 kills them
+    for (int i = tid; i < p.q_pad; i += NT) s_lse[i] = (i < p.n_q) ? src[i] : 0.f;   // padded rows: dO = 0 kills them
   }
   cp_async_wait_all();
   __syncthreads();
@@ -245,8 +246,8 @@ __global__ void __launch_bounds__(32 * AB_WARPS, AB_WARPS > 4 ? 2 : 2) attention
     __nv_bfloat16* o1 = o0 + 8 * ldq;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      if (r0 < p.N0) *reinterpret_cast<uint32_t*>(o0 + 8 * n) = pack_bf16x2(dq[n][0] * scale, dq[n][1] * scale);
-      if (r1 < p.N0) *reinterpret_cast<uint32_t*>(o1 + 8 * n) = pack_bf16x2(dq[n][2] * scale, dq[n][3] * scale);
+      if (r0 < p.n_q) *reinterpret_cast<uint32_t*>(o0 + 8 * n) = pack_bf16x2(dq[n][0] * scale, dq[n][1] * scale);
+      if (r1 < p.n_q) *reinterpret_cast<uint32_t*>(o1 + 8 * n) = pack_bf16x2(dq[n][2] * scale, dq[n][3] * scale);
     }
   } else {
     const int kt = u - n_qt;
@@ -346,8 +347,9 @@ __global__ void __launch_bounds__(32 * AB_WARPS, AB_WARPS > 4 ? 2 : 2) attention
 }
 
 int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, const float* lse, void* dqkv,
-                  float* dkv_aux, int B, int T, int N0, int G, int H, cudaStream_t stream) {
-  if (!qkv || !kv_aux || !out || !dout || !dqkv || !dkv_aux || B <= 0 || T <= 0 || N0 <= 0 || G < 0 || H <= 0) {
+                  float* dkv_aux, int B, int T, int N0, int G, int H, int n_q, cudaStream_t stream) {
+  if (!qkv || !kv_aux || !out || !dout || !dqkv || !dkv_aux || B <= 0 || T <= 0 || N0 <= 0 || G < 0 || H <= 0 || n_q <= 0 ||
+      n_q > N0) {
     set_error("attention_bwd: bad arguments");
     return GAVA_ERR_ARG;
   }
@@ -361,7 +363,8 @@ int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const vo
   a.lse = lse;
   a.T = T; a.N0 = N0; a.G = G; a.H = H; a.BT = B * T;
   a.S = N0 + G + T + 1;
-  a.q_pad = (N0 + 15) / 16 * 16;
+  a.n_q = n_q;
+  a.q_pad = (n_q + 15) / 16 * 16;
   a.s_pad = (a.S + 15) / 16 * 16;
   const size_t smem_bytes = (size_t)(2 * a.q_pad + 2 * a.s_pad) * 128 + (size_t)a.q_pad * 8;
   if (smem_bytes > 226 * 1024) { set_error("attention_bwd: %d keys x %d queries exceed the shared-memory budget", a.S, N0); return GAVA_ERR_SHAPE; }

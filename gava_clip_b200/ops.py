@@ -334,7 +334,7 @@ def layernorm_bwd(dy: Tensor, x: Tensor, weight: Tensor, dx_out: Tensor, *, rows
 
 
 def attention_train(qkv: Tensor, kv_aux: Tensor, out: Tensor, lse: Tensor, *, B: int, T: int, N0: int, G: int,
-                    H: int) -> Tensor:
+                    H: int, n_q: Optional[int] = None) -> Tensor:
     """attention() over all query rows that also saves the per-row log-sum-exp (f32 [B*T, H, N0]) for attention_bwd."""
     _req(qkv, torch.bfloat16, "attention qkv"); _req(kv_aux, torch.bfloat16, "attention kv_aux")
     _req(out, torch.bfloat16, "attention out"); _req(lse, torch.float32, "attention lse")
@@ -343,13 +343,13 @@ def attention_train(qkv: Tensor, kv_aux: Tensor, out: Tensor, lse: Tensor, *, B:
     assert qkv.shape == (B * T * N0, 3 * D) and kv_aux.shape == (G + 2 * B * T, 2 * D) and out.shape == (B * T * N0, D)
     assert lse.numel() == B * T * H * N0
     rc = _lib.load().gava_attention_train_fwd(qkv.data_ptr(), kv_aux.data_ptr(), out.data_ptr(), lse.data_ptr(), B, T, N0, G,
-                                              H, _stream())
+                                              H, N0 if n_q is None else n_q, _stream())
     _lib.check(rc, "gava_attention_train_fwd")
     return out
 
 
 def attention_bwd(qkv: Tensor, kv_aux: Tensor, out: Tensor, dout: Tensor, dqkv: Tensor, dkv_aux: Tensor, *, B: int,
-                  T: int, N0: int, G: int, H: int, lse: Optional[Tensor] = None) -> None:
+                  T: int, N0: int, G: int, H: int, lse: Optional[Tensor] = None, n_q: Optional[int] = None) -> None:
     for t in (qkv, kv_aux, out, dout, dqkv):
         _req(t, torch.bfloat16, "attention_bwd"); assert t.is_contiguous()
     _req(dkv_aux, torch.float32, "attention_bwd dkv_aux")
@@ -360,7 +360,8 @@ def attention_bwd(qkv: Tensor, kv_aux: Tensor, out: Tensor, dout: Tensor, dqkv: 
     if lse is not None:
         _req(lse, torch.float32, "attention_bwd lse"); assert lse.is_contiguous() and lse.numel() == B * T * H * N0
     rc = _lib.load().gava_attention_bwd(qkv.data_ptr(), kv_aux.data_ptr(), out.data_ptr(), dout.data_ptr(), _ptr(lse),
-                                        dqkv.data_ptr(), dkv_aux.data_ptr(), B, T, N0, G, H, _stream())
+                                        dqkv.data_ptr(), dkv_aux.data_ptr(), B, T, N0, G, H, N0 if n_q is None else n_q,
+                                        _stream())
     _lib.check(rc, "gava_attention_bwd")
 
 

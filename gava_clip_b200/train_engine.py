@@ -128,10 +128,10 @@ class TowerTrainer(TowerEngine):
         per_layer = lambda *s, dt: [z(*s, dt=dt) for _ in range(L)]
         W: Dict[str, object] = {
             # ---- tape
-            "x0_pre": z(M, D, dt=f32), "x_in": [z(M, D, dt=f32) for _ in range(L + 1)], "x_mid": per_layer(M, D, dt=f32),
+            "x0_pre": z(M, D, dt=f32), "x_in": per_layer(M, D, dt=f32), "x_mid": [z(M, D, dt=f32) for _ in range(L - 1)],
             "qkv": per_layer(M, 3 * D, dt=bf), "kvaux": per_layer(R, 2 * D, dt=bf), "o": per_layer(M, D, dt=bf),
             "lse": per_layer(BT * e.num_heads * N0, dt=f32),
-            "a1": per_layer(M, Dm, dt=bf), "cls_proj": per_layer(BT, D, dt=f32), "summary": per_layer(BT, D, dt=f32),
+            "a1": [z(M, Dm, dt=bf) for _ in range(L - 1)], "cls_proj": per_layer(BT, D, dt=f32), "summary": per_layer(BT, D, dt=f32),
             "sum_n": per_layer(BT, D, dt=bf), "sqkv": per_layer(BT, 3 * D, dt=bf), "smix": per_layer(BT, D, dt=bf),
             # ---- forward scratch
             "patches": z(BT * (N0 - 1), self.packed["patch.w"].shape[1], dt=bf), "xn": z(M, D, dt=bf), "h": z(M, Dm, dt=bf),
@@ -143,13 +143,16 @@ class TowerTrainer(TowerEngine):
             "dsmix": z(BT, D, dt=bf), "dsqkv": z(BT, 3 * D, dt=bf), "dsn": z(BT, D, dt=bf), "d_cp": z(BT, D, dt=f32),
             "d_cp_bf": z(BT, D, dt=bf), "tA": z(3 * D, BTp, dt=bf), "tB": z(D, BTp, dt=bf),
             "dff_bf": z(BT, Ep, dt=bf), "dcls_n": z(BT, D, dt=bf), "dff": z(BT, Ep, dt=f32),
+            # ---- last layer, cls rows only (vision_encoder.py:126: nothing else reaches the output)
+            "xc_mid": z(BT, D, dt=f32), "xc_out": z(BT, D, dt=f32), "a1c": z(BT, Dm, dt=bf), "hc": z(BT, Dm, dt=bf),
+            "dxc": z(BT, D, dt=f32), "dxc_bf": z(BT, D, dt=bf), "g4c": z(BT, Dm, dt=bf), "gDc": z(BT, D, dt=bf),
         }
         self.ws[key] = W
         return W
 
     # ------------------------------------------------------------------ forward with tape
     def forward_train(self, video: Tensor) -> Tuple[Tensor, Tensor]:
-        """Same schedule as TowerEngine.encode_frames (all layers in full), activations kept for backward()."""
+        """Same schedule as TowerEngine.encode_frames (incl. the cls-rows-only last layer), activations kept for backward()."""
         self.pack_train()
         e, P = self.enc, self.packed
         B, T, _, _ = _clip_dims(video)
@@ -173,7 +176,8 @@ class TowerTrainer(TowerEngine):
         L = len(e.blocks)
         for i in range(L):
             k = f"b{i}."
-            xin, xmid, xnext = W["x_in"][i], W["x_mid"][i], W["x_in"][i + 1]
+            xin = W["x_in"][i]
+            xmid, xnext = (W["x_mid"][i], W["x_in"][i + 1]) if i < L - 1 else (None, None)
             cp, sm = W["cls_proj"][i], W["summary"][i]
             # temporal message (utils.py:160-188)
             ops.layernorm(xin, None, None, W["cls_bf"], rows=BT, in_row_stride=N0 * D)
@@ -187,6 +191,23 @@ class TowerTrainer(TowerEngine):
             ops.gemm(W["aux_n"], P[k + "qkv.w"][D:], W["kvaux"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:])
             # x = x + attn(norm1(x))   (utils.py:190-191)
             ops.layernorm(xin, P[k + "norm1.w"], P[k + "norm1.b"], xn, rows=M, in_row_stride=D)
+            if i == L - 1:
+                # Last layer: only the cls row of each frame reaches the output, so -- exactly as in the inference
+                # schedule -- K/V are projected for all rows, Q / attention query / out-proj / MLP for the cls rows alone.
+                qkv = W["qkv"][i]
+                xn_cls = xn.view(BT, N0 * D)[:, :D]
+                ops.gemm(xn, P[k + "qkv.w"][D:], qkv[:, D:], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:])
+                ops.gemm(xn_cls, P[k + "qkv.w"][:D], qkv.view(BT, N0 * 3 * D)[:, :D], mode=ops.EPI_BIAS_BF16,
+                         bias=P[k + "qkv.b"][:D])
+                ops.attention_train(qkv, W["kvaux"][i], W["o"][i], W["lse"][i], B=B, T=T, N0=N0, G=G, H=H, n_q=1)
+                ops.gemm(W["o"][i].view(BT, N0 * D)[:, :D], P[k + "out.w"], W["xc_mid"], mode=ops.EPI_BIAS_RESID_F32,
+                         bias=P[k + "out.b"], resid=xin.view(BT, N0 * D)[:, :D])
+                ops.layernorm(W["xc_mid"], P[k + "norm2.w"], P[k + "norm2.b"], W["cls_bf"], rows=BT, in_row_stride=D)
+                ops.gemm(W["cls_bf"], P[k + "fc1.w"], W["hc"], mode=ops.EPI_BIAS_GELU_BF16, bias=P[k + "fc1.b"],
+                         aux_out=W["a1c"])
+                ops.gemm(W["hc"], P[k + "fc2.w"], W["xc_out"], mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"],
+                         resid=W["xc_mid"])
+                break
             ops.gemm(xn, P[k + "qkv.w"], W["qkv"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"])
             ops.attention_train(W["qkv"][i], W["kvaux"][i], W["o"][i], W["lse"][i], B=B, T=T, N0=N0, G=G, H=H)
             ops.gemm(W["o"][i], P[k + "out.w"], xmid, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "out.b"], resid=xin)
@@ -195,7 +216,7 @@ class TowerTrainer(TowerEngine):
             ops.gemm(xn, P[k + "fc1.w"], h, mode=ops.EPI_BIAS_GELU_BF16, bias=P[k + "fc1.b"], aux_out=W["a1"][i])
             ops.gemm(h, P[k + "fc2.w"], xnext, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"], resid=xmid)
 
-        ops.layernorm(W["x_in"][L], P["ln_post.w"], P["ln_post.b"], W["cls_bf"], rows=BT, in_row_stride=N0 * D)
+        ops.layernorm(W["xc_out"], P["ln_post.w"], P["ln_post.b"], W["cls_bf"], rows=BT, in_row_stride=D)
         ops.gemm(W["cls_bf"], P["proj.wT"], W["frame_feat"], mode=ops.EPI_BIAS_F32)
         self.launches_last_call = ops.launch_count() - n0
         return W["frame_feat"], W["summary"][L - 1]
@@ -222,7 +243,6 @@ class TowerTrainer(TowerEngine):
         # bf16 copy of dx for the dgrad GEMMs: written by the LayerNorm-backward kernels as a by-product; only the BT cls
         # rows change outside those kernels (ln_post / cls_proj contributions) and are re-cast by a BT-row launch
         cast_cls = lambda: ops.layernorm(dx, None, None, dxb, rows=BT, in_row_stride=N0 * D, out_row_stride=N0 * D)
-        dxb.zero_()
         # ---- frame_feat = ln_post(x_cls) @ proj   (vision_encoder.py:126-127)
         dx.zero_()
         if d_frame_feat is not None:
@@ -235,9 +255,9 @@ class TowerTrainer(TowerEngine):
                 dff.copy_(d_frame_feat)
             ops.layernorm(dff, None, None, W["dff_bf"], rows=BT, in_row_stride=Ep)            # f32 -> bf16 cast
             ops.gemm(W["dff_bf"], P["proj.w"], W["dcls_n"], mode=ops.EPI_BIAS_BF16)
-            ops.layernorm_bwd(W["dcls_n"], W["x_in"][L], P["ln_post.w"], dx, rows=BT, D=D, x_stride=N0 * D,
-                              dx_stride=N0 * D)
-            cast_cls()
+            ops.layernorm_bwd(W["dcls_n"], W["xc_out"], P["ln_post.w"], W["dxc"], rows=BT, D=D, dx_bf16=W["dxc_bf"])
+        else:
+            W["dxc"].zero_(); W["dxc_bf"].zero_()
         ext = None
         if d_summary is not None:
             ext = d_summary.contiguous().float()
@@ -245,14 +265,26 @@ class TowerTrainer(TowerEngine):
         for i in reversed(range(L)):
             k, kb = f"b{i}.", f"blocks.{i}."
             cp, sm = W["cls_proj"][i], W["summary"][i]
-            # ---- MLP: dx += dLN2( (dx W2 * g'(a1)) W1 )
-            ops.gemm(dxb, P[k + "fc2.wT"], W["g4"], mode=ops.EPI_DGELU_BF16, aux=W["a1"][i])
-            ops.gemm(W["g4"], P[k + "fc1.wT"], gD, mode=ops.EPI_BIAS_BF16)
-            ops.layernorm_bwd(gD, W["x_mid"][i], P[k + "norm2.w"], dx, rows=M, D=D, add1=dx, dx_bf16=dxb)
-            # ---- attention: dO = dx Wo; (dq, dk, dv, d kv_aux); dx += dLN1(dqkv Wqkv)
-            ops.gemm(dxb, P[k + "out.wT"], gD, mode=ops.EPI_BIAS_BF16)
-            ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G, H=H,
-                              lse=W["lse"][i])
+            if i == L - 1:
+                # ---- last layer: MLP / out-proj / attention-query gradients exist for the BT cls rows only
+                ops.gemm(W["dxc_bf"], P[k + "fc2.wT"], W["g4c"], mode=ops.EPI_DGELU_BF16, aux=W["a1c"])
+                ops.gemm(W["g4c"], P[k + "fc1.wT"], W["gDc"], mode=ops.EPI_BIAS_BF16)
+                ops.layernorm_bwd(W["gDc"], W["xc_mid"], P[k + "norm2.w"], W["dxc"], rows=BT, D=D, add1=W["dxc"],
+                                  dx_bf16=W["dxc_bf"])
+                dx_cls.copy_(W["dxc"])                                               # residual path into the stream's cls rows
+                ops.gemm(W["dxc_bf"], P[k + "out.wT"], gD.view(BT, N0 * D)[:, :D], mode=ops.EPI_BIAS_BF16)   # dO, cls rows of gD
+                W["dqkv"].view(BT * N0, 3, D)[:, 0].zero_()                          # dq of the rows without a query
+                ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G,
+                                  H=H, lse=W["lse"][i], n_q=1)
+            else:
+                # ---- MLP: dx += dLN2( (dx W2 * g'(a1)) W1 )
+                ops.gemm(dxb, P[k + "fc2.wT"], W["g4"], mode=ops.EPI_DGELU_BF16, aux=W["a1"][i])
+                ops.gemm(W["g4"], P[k + "fc1.wT"], gD, mode=ops.EPI_BIAS_BF16)
+                ops.layernorm_bwd(gD, W["x_mid"][i], P[k + "norm2.w"], dx, rows=M, D=D, add1=dx, dx_bf16=dxb)
+                # ---- attention: dO = dx Wo; (dq, dk, dv, d kv_aux); dx += dLN1(dqkv Wqkv)
+                ops.gemm(dxb, P[k + "out.wT"], gD, mode=ops.EPI_BIAS_BF16)
+                ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G,
+                                  H=H, lse=W["lse"][i])
             ops.gemm(W["dqkv"], P[k + "qkv.wT"], gD, mode=ops.EPI_BIAS_BF16)
             ops.layernorm_bwd(gD, W["x_in"][i], P[k + "norm1.w"], dx, rows=M, D=D, add1=dx, dx_bf16=dxb)
             # ---- K/V-only prompt rows: d kv_aux -> normalised rows -> global / local / summary / cls_proj gradients

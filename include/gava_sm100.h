@@ -182,17 +182,20 @@ int gava_layernorm_bwd(const void* dy, int64_t dy_stride, int32_t dy_bf16, const
                        int64_t add2_stride, float* dx_out, int64_t dx_stride, void* dx_bf16, int64_t dxb_stride,
                        float* dw, float* db, int64_t rows, int32_t D, float eps, void* stream);
 
-/* gava_attention_fwd for the training forward: all N0 query rows, and additionally lse f32 [B*T, H, N0] = the log2-domain
+/* gava_attention_fwd for the training forward: additionally writes lse f32 [B*T, H, N0] (rows < n_q) = the log2-domain
  * log-sum-exp of every query row's scaled scores (log2(sum_k 2^(s_k log2 e / 8))), saved for gava_attention_bwd. */
 int gava_attention_train_fwd(const void* qkv, const void* kv_aux, void* out, float* lse, int32_t B, int32_t T, int32_t N0,
-                             int32_t G, int32_t H, void* stream);
+                             int32_t G, int32_t H, int32_t n_q, void* stream);
 
-/* Backward of gava_attention_fwd (all N0 query rows).  out/dout: bf16 [B*T*N0, D] forward output and its gradient.
+/* Backward of gava_attention_fwd for the first n_q query rows of every frame (n_q = N0, or 1 in the last layer where only
+ * the cls row reaches the output: dq is then written for that row only, dk/dv still cover every key).
+ * out/dout: bf16 [B*T*N0, D] forward output and its gradient (rows >= n_q of a frame are not read).
  * lse: the rows saved by gava_attention_train_fwd, or NULL (recomputed inside, one more pass over the keys).
  * dqkv: bf16 [B*T*N0, 3D] = [dq | dk | dv] of the live rows; dkv_aux: f32 [G + 2*B*T, 2D] = [dk | dv] of the K/V-only rows
  * (zeroed and atomically accumulated inside: global rows collect all frames, local rows the T frames of a video). */
 int gava_attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, const float* lse,
-                       void* dqkv, float* dkv_aux, int32_t B, int32_t T, int32_t N0, int32_t G, int32_t H, void* stream);
+                       void* dqkv, float* dkv_aux, int32_t B, int32_t T, int32_t N0, int32_t G, int32_t H, int32_t n_q,
+                       void* stream);
 
 /* Backward of gava_temporal_attention_fwd: qkv bf16 [B*T, 3D], dout bf16 [B*T, D] -> dqkv bf16 [B*T, 3D].  T <= 128. */
 int gava_temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int32_t B, int32_t T, int32_t H,
