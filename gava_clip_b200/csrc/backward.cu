@@ -374,8 +374,9 @@ int adamw_step(float* p, const float* g, float* m, float* v, long long n, float 
 //   dV = P^T dO; dP = dO V^T; dS = P (dP - rowsum(P dP)); dQ = dS K / 8; dK = dS^T Q / 8
 // Used for the T x T summary-token attention of the video tower (bf16 qkv, no mask) and for the 77 x 77 causal attention
 // of the CLIP text transformer (f32 qkv, VitaCLIP_text_encoder.py:83-88,146-152).
+constexpr int SAB_THREADS = 256;
 template <bool IN_F32, bool CAUSAL>
-__global__ void __launch_bounds__(128) seq_attention_bwd_kernel(const void* __restrict__ qkv_,
+__global__ void __launch_bounds__(SAB_THREADS) seq_attention_bwd_kernel(const void* __restrict__ qkv_,
                                                                 const __nv_bfloat16* __restrict__ dout,
                                                                 __nv_bfloat16* __restrict__ dqkv, int T, int H) {
   extern __shared__ float tsm[];
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(128) seq_attention_bwd_kernel(const void* __re
   const long long ld = 3LL * D;
   const long long base = (long long)b * T * ld + h * 64;
   const __nv_bfloat16* dbase = dout + (long long)b * T * D + h * 64;
-  for (int i = tid; i < T * 64; i += 128) {
+  for (int i = tid; i < T * 64; i += SAB_THREADS) {
     const int t = i >> 6, d = i & 63;
     if constexpr (IN_F32) {
       const float* src = reinterpret_cast<const float*>(qkv_) + base;
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(128) seq_attention_bwd_kernel(const void* __re
     sdo[t * PITCH + d] = __bfloat162float(dbase[(long long)t * D + d]);
   }
   __syncthreads();
-  for (int idx = tid; idx < T * T; idx += 128) {
+  for (int idx = tid; idx < T * T; idx += SAB_THREADS) {
     const int i = idx / T, j = idx - i * T;
     float acc = 0.f;
     if (!CAUSAL || j <= i) {
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(128) seq_attention_bwd_kernel(const void* __re
     sp[i * PP + j] = acc * 0.125f;
   }
   __syncthreads();
-  for (int i = warp; i < T; i += 4) {   // row softmax over the visible keys
+  for (int i = warp; i < T; i += SAB_THREADS / 32) {   // row softmax over the visible keys
     const int n = CAUSAL ? i + 1 : T;
     float m = -INFINITY;
     for (int j = lane; j < n; j += 32) m = fmaxf(m, sp[i * PP + j]);
@@ -429,14 +430,14 @@ __global__ void __launch_bounds__(128) seq_attention_bwd_kernel(const void* __re
   }
   __syncthreads();
   __nv_bfloat16* obase = dqkv + (long long)b * T * ld + h * 64;
-  for (int idx = tid; idx < T * 64; idx += 128) {   // dV[j][d] = sum_i P[i][j] dO[i][d]
+  for (int idx = tid; idx < T * 64; idx += SAB_THREADS) {   // dV[j][d] = sum_i P[i][j] dO[i][d]
     const int j = idx >> 6, d = idx & 63;
     float acc = 0.f;
     for (int i = CAUSAL ? j : 0; i < T; ++i) acc += sp[i * PP + j] * sdo[i * PITCH + d];
     obase[j * ld + 2 * D + d] = __float2bfloat16(acc);
   }
   __syncthreads();
-  for (int i = warp; i < T; i += 4) {   // dS row i (overwrites P row i)
+  for (int i = warp; i < T; i += SAB_THREADS / 32) {   // dS row i (overwrites P row i)
     const int n = CAUSAL ? i + 1 : T;
     float delta = 0.f;
     float dp_loc[4];   // T <= 128
@@ -459,7 +460,7 @@ __global__ void __launch_bounds__(128) seq_attention_bwd_kernel(const void* __re
     }
   }
   __syncthreads();
-  for (int idx = tid; idx < T * 64; idx += 128) {
+  for (int idx = tid; idx < T * 64; idx += SAB_THREADS) {
     const int t = idx >> 6, d = idx & 63;
     float aq = 0.f, ak = 0.f;
     for (int j = 0; j < T; ++j) {      // masked entries of dS are exactly 0
@@ -484,7 +485,7 @@ static int launch_seq_attention_bwd(const void* qkv, const void* dout, void* dqk
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(e)); return (int)e; }
     attr_bytes = smem;
   }
-  kern<<<dim3(H, n_seq), 128, smem, stream>>>(qkv, reinterpret_cast<const __nv_bfloat16*>(dout),
+  kern<<<dim3(H, n_seq), SAB_THREADS, smem, stream>>>(qkv, reinterpret_cast<const __nv_bfloat16*>(dout),
                                               reinterpret_cast<__nv_bfloat16*>(dqkv), T, H);
   return check_launch(what);
 }

@@ -141,6 +141,7 @@ class VitaCLIP(nn.Module):
             self._freeze_textual()
         self._scale_cache = (None, 0.0)
         self._zs_cache = None
+        self.text_side_stream = os.environ.get("GAVA_TEXT_SIDE_STREAM", "0") == "1"   # fine-tune step: text side on a side stream (measured neutral)
 
     # ------------------------------------------------------------------ freezing (reference :230-239)
     def _freeze_visual_except_prompts_time_embed(self):
@@ -244,7 +245,7 @@ class VitaCLIP(nn.Module):
         """x: fp32 clip (B,3,T,H,W) as in the reference, or -- after self.visual.set_input_norm(mean, std) -- the
         decoder's uint8 frames (B,T,H,W,3), normalised on the fly inside the patch gather."""
         text_ahead = None
-        if self.use_text_prompt_learning and x.is_cuda and self._text_side_needs_grad():
+        if self.use_text_prompt_learning and x.is_cuda and self._text_side_needs_grad() and self.text_side_stream:
             # fine-tune step: the text side (a few hundred small library kernels, launch-bound) is issued FIRST on a side
             # stream so that it runs underneath the video tower instead of in front of it; autograd replays its backward
             # on the same side stream, i.e. underneath the tower's backward
