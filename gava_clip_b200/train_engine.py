@@ -95,7 +95,7 @@ class TowerTrainer(TowerEngine):
             if name in P and vers.get(name) == key:
                 return
             if name in P and P[name].shape == (src.shape[1], src.shape[0]):
-                P[name].copy_(src.detach().t())             # one strided-read kernel
+                ops.transpose_bf16(src.detach(), P[name])   # bf16 [N,K] -> [K,N]
             else:
                 P[name] = src.detach().t().to(self.device, torch.bfloat16).contiguous()
             vers[name] = key

@@ -163,6 +163,7 @@ class TowerEngine:
         P = self.packed
         vers = getattr(self, "_src_versions", {})
         moved = False
+        copies = []          # (dst, src) refreshes of existing packed tensors, issued as ONE multi-tensor copy
 
         def put(name: str, srcs, make) -> None:
             """packed[name] = make() unless none of the source parameters changed since the last pack."""
@@ -173,11 +174,11 @@ class TowerEngine:
             old = P.get(name)
             if old is not None and len(srcs) == 1 and old.shape == srcs[0].shape and old.device == srcs[0].device:
                 if old.data_ptr() != srcs[0].data_ptr():      # an fp32 "copy" may simply alias the parameter
-                    old.copy_(srcs[0].detach())               # one kernel: dtype conversion inside the copy
+                    copies.append((old, srcs[0].detach()))
             elif old is not None and len(srcs) > 1 and old.shape[0] == sum(t.shape[0] for t in srcs):
                 r = 0
                 for t in srcs:                                # concatenated q|k|v blocks: slice-wise converting copies
-                    old[r: r + t.shape[0]].copy_(t.detach())
+                    copies.append((old[r: r + t.shape[0]], t.detach()))
                     r += t.shape[0]
             else:
                 P[name] = make()
@@ -229,6 +230,8 @@ class TowerEngine:
             put(k + "local", [blk.local_prompts], lambda blk=blk: f32(blk.local_prompts))
         for key in [key for key in P if key.startswith("time_embed@")]:
             del P[key]                                  # resized copies are rebuilt on demand
+        if copies:           # fine-tuning refreshes ~100 small tensors per step: a handful of launches instead of one each
+            torch._foreach_copy_([d for d, _ in copies], [s_ for _, s_ in copies])
         self._src_versions = vers
         self.signature = sig
         if moved:

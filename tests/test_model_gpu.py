@@ -442,3 +442,35 @@ def test_finetune_recipe_shape_t70(cuda):
     params = dict(model.named_parameters())
     for n in names:
         assert _cos(params[n].grad, cpu_sd[n].grad) > 0.995 and rel_l2(params[n].grad, cpu_sd[n].grad) < 8e-2, n
+
+
+def test_eval_after_training_steps_sees_updated_weights(cuda):
+    """train -> eval round trip: the inference schedule replays CUDA graphs captured BEFORE the optimizer steps; the
+    in-place refresh of the packed weights must make those graphs (and the cached text features) see the new parameters.
+    Checked against a fresh model that loads the fine-tuned state_dict (which also exercises the checkpoint contract after
+    FineTuner re-pointed the parameters into its flat buffer)."""
+    from gava_clip_b200.finetune import FineTuner
+    video = fx.make_inputs("tiny")["video"].to(cuda)
+    labels = torch.tensor([2, 0], device=cuda)
+    model, _, _ = build_model("tiny", device=cuda)
+    model.eval()
+    with torch.no_grad():
+        before = model(video)[0].clone()              # captures the inference graph for this shape
+    tuner = FineTuner(model, lr=5e-3, weight_decay=0.0)
+    for _ in range(3):
+        tuner.step(video, labels)
+    model.eval()
+    with torch.no_grad():
+        after = model(video)[0].clone()
+    assert float((after - before).abs().max()) > 1e-3          # the update is visible through the replayed graph
+    fresh, _, _ = build_model("tiny", device=cuda)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    fresh.load_state_dict(sd, strict=True)
+    fresh.prompt_learner.refresh_token_embeddings(fresh.textual)
+    fresh.eval()
+    with torch.no_grad():
+        ref = fresh(video)[0]
+    assert torch.equal(after, ref)
+    # a different batch size in training (ragged last batch) allocates its own tape and still works
+    loss = tuner.step(video[:1], labels[:1])
+    assert torch.isfinite(loss)
