@@ -29,6 +29,7 @@ struct AttnBwdArgs {
   __nv_bfloat16* dqkv;          // [BT*N0, 3D]
   float* dkv_aux;               // [G+2BT, 2D]  atomically accumulated (zeroed by the launcher)
   const float* lse;             // [BT, H, N0] log2-domain log-sum-exp rows saved by the forward, or null (recomputed)
+  float* scratch;               // optional [BT, H, G+T+1, 128]: per-(frame, head) prompt-row gradients, reduced by a 2nd kernel
   int T, N0, G, H, S, BT, q_pad, s_pad;
   int n_q;   // query rows per frame that carry a gradient (N0, or 1 in the last layer: only the cls row reaches the output)
 };
@@ -325,6 +326,14 @@ __global__ void __launch_bounds__(32 * AB_WARPS, AB_WARPS > 4 ? 2 : 2) attention
           *reinterpret_cast<uint32_t*>(ok + 8 * n) = pack_bf16x2(dk[n][2 * half] * scale, dk[n][2 * half + 1] * scale);
           *reinterpret_cast<uint32_t*>(ov + 8 * n) = pack_bf16x2(dv[n][2 * half], dv[n][2 * half + 1]);
         }
+      } else if (kr < p.S && p.scratch != nullptr) {
+        // deterministic path: this CTA's contribution goes to its own slot, attention_bwd_reduce_kernel sums the slots
+        float* ok = p.scratch + (((long long)f * p.H + h) * (p.S - p.N0) + (kr - p.N0)) * 128 + 2 * tg;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          *reinterpret_cast<float2*>(ok + 8 * n) = make_float2(dk[n][2 * half] * scale, dk[n][2 * half + 1] * scale);
+          *reinterpret_cast<float2*>(ok + 64 + 8 * n) = make_float2(dv[n][2 * half], dv[n][2 * half + 1]);
+        }
       } else if (kr < p.S) {
         const int a = kr - p.N0;
         int arow;
@@ -346,8 +355,40 @@ __global__ void __launch_bounds__(32 * AB_WARPS, AB_WARPS > 4 ? 2 : 2) attention
   }   // unit loop
 }
 
+// dkv_aux[arow, :] = sum of the per-(frame, head) slots that reference prompt row `arow`, in a fixed order:
+//   global row g: all BT frames; local row (b, t'): the T frames of video b; summary row f: frame f alone.
+// 128 threads along x = 64 dk + 64 dv values of one head.  Global rows: grid (G, H), 8 thread groups along y take every
+// 8th frame and are combined through shared memory in index order; local / summary rows: grid (2 BT, H), blockDim.y = 1.
+__global__ void __launch_bounds__(1024) attention_bwd_reduce_kernel(const float* __restrict__ scratch, float* __restrict__ dkv_aux,
+                                                                    int row0, int G, int T, int BT, int H) {
+  __shared__ float part[8][128];
+  const int arow = row0 + blockIdx.x, h = blockIdx.y, c = threadIdx.x, y = threadIdx.y, ny = blockDim.y;
+  const int n_aux = G + T + 1, D = H * 64;
+  float acc0 = 0.f, acc1 = 0.f;
+  auto slot = [&](int f, int a) { return scratch + (((long long)f * H + h) * n_aux + a) * 128 + c; };
+  if (arow < G) {
+    int f = y;
+    for (; f + ny < BT; f += 2 * ny) { acc0 += *slot(f, arow); acc1 += *slot(f + ny, arow); }
+    if (f < BT) acc0 += *slot(f, arow);
+  } else if (arow < G + BT) {
+    const int b = (arow - G) / T, tp = (arow - G) - b * T;
+    for (int t = y; t < T; t += ny) acc0 += *slot(b * T + t, G + tp);
+  } else if (y == 0) {
+    acc0 = *slot(arow - G - BT, G + T);
+  }
+  float v = acc0 + acc1;
+  if (ny > 1) {
+    part[y][c] = v;
+    __syncthreads();
+    if (y != 0) return;
+    v = 0.f;
+    for (int i = 0; i < ny; ++i) v += part[i][c];
+  }
+  dkv_aux[(long long)arow * 2 * D + (c < 64 ? h * 64 + c : D + h * 64 + (c - 64))] = v;
+}
+
 int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, const float* lse, void* dqkv,
-                  float* dkv_aux, int B, int T, int N0, int G, int H, int n_q, cudaStream_t stream) {
+                  float* dkv_aux, float* scratch, int B, int T, int N0, int G, int H, int n_q, cudaStream_t stream) {
   if (!qkv || !kv_aux || !out || !dout || !dqkv || !dkv_aux || B <= 0 || T <= 0 || N0 <= 0 || G < 0 || H <= 0 || n_q <= 0 ||
       n_q > N0) {
     set_error("attention_bwd: bad arguments");
@@ -361,6 +402,7 @@ int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const vo
   a.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
   a.dkv_aux = dkv_aux;
   a.lse = lse;
+  a.scratch = scratch;
   a.T = T; a.N0 = N0; a.G = G; a.H = H; a.BT = B * T;
   a.S = N0 + G + T + 1;
   a.n_q = n_q;
@@ -376,11 +418,17 @@ int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const vo
     attr_bytes = smem_bytes;
   }
   const long long D = 64LL * H;
-  cudaError_t e = cudaMemsetAsync(dkv_aux, 0, sizeof(float) * (size_t)(G + 2 * B * T) * 2 * D, stream);
-  if (e != cudaSuccess) { set_error("attention_bwd memset: %s", cudaGetErrorString(e)); return (int)e; }
+  if (scratch == nullptr) {   // atomics path: accumulate straight into dkv_aux
+    cudaError_t e = cudaMemsetAsync(dkv_aux, 0, sizeof(float) * (size_t)(G + 2 * B * T) * 2 * D, stream);
+    if (e != cudaSuccess) { set_error("attention_bwd memset: %s", cudaGetErrorString(e)); return (int)e; }
+  }
   if (lse) attention_bwd_kernel<true><<<dim3(H, B * T), 32 * AB_WARPS, smem_bytes, stream>>>(a);
   else attention_bwd_kernel<false><<<dim3(H, B * T), 32 * AB_WARPS, smem_bytes, stream>>>(a);
-  return check_launch("attention_bwd");
+  int rc = check_launch("attention_bwd");
+  if (rc || scratch == nullptr) return rc;
+  if (G > 0) attention_bwd_reduce_kernel<<<dim3(G, H), dim3(128, 8), 0, stream>>>(scratch, dkv_aux, 0, G, T, B * T, H);
+  attention_bwd_reduce_kernel<<<dim3(2 * B * T, H), dim3(128, 1), 0, stream>>>(scratch, dkv_aux, G, G, T, B * T, H);
+  return check_launch("attention_bwd_reduce");
 }
 
 }  // namespace gava

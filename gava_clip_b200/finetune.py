@@ -169,6 +169,59 @@ class FineTuner:
         # cached text features are refreshed on the next forward
         torch.autograd.graph.increment_version(self.params)
 
+    def run(self, host_batches, memory: Optional[Tensor] = None, memory_labels: Optional[Tensor] = None):
+        """Training loop over (clip, labels) batches that live in (pinned) HOST memory -- what the reference's DataLoader
+        yields (train.py:395-421): the H2D copy of batch i+1 runs on a copy stream underneath step i (two device staging
+        buffers), and every step's loss is returned in pinned host memory.  Yields one loss (0-d pinned tensor) per batch."""
+        dev = self.params[0].device
+        copy_stream = torch.cuda.Stream(dev)
+        stage = [None, None]
+        staged = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        losses = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def upload(k, batch):
+            clip, labels = batch
+            if stage[k] is None or stage[k][0].shape != clip.shape or stage[k][0].dtype != clip.dtype:
+                stage[k] = (torch.empty(clip.shape, device=dev, dtype=clip.dtype), torch.empty(labels.shape, device=dev, dtype=labels.dtype))
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[k])
+                stage[k][0].copy_(clip, non_blocking=True)
+                stage[k][1].copy_(labels, non_blocking=True)
+                staged[k].record(copy_stream)
+
+        it = iter(host_batches)
+        try:
+            nxt = next(it)
+        except StopIteration:
+            return
+        upload(0, nxt)
+        i, pending = 0, None
+        while True:
+            k = i & 1
+            try:
+                nxt = next(it)
+                upload(k ^ 1, nxt)
+                more = True
+            except StopIteration:
+                more = False
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(staged[k])
+            loss = self.step(stage[k][0], stage[k][1], memory, memory_labels)
+            consumed[k].record(cur)
+            losses[k].copy_(loss, non_blocking=True)
+            done[k].record(cur)
+            if pending is not None:
+                done[pending].synchronize()
+                yield losses[pending]
+            pending = k
+            if not more:
+                break
+            i += 1
+        done[pending].synchronize()
+        yield losses[pending]
+
     def step(self, video: Tensor, labels: Tensor, memory: Optional[Tensor] = None, memory_labels: Optional[Tensor] = None,
              video_nte: Optional[Tensor] = None, vnte_loss_weight: float = 0.0) -> Tensor:
         self.zero_grad()

@@ -349,7 +349,8 @@ def attention_train(qkv: Tensor, kv_aux: Tensor, out: Tensor, lse: Tensor, *, B:
 
 
 def attention_bwd(qkv: Tensor, kv_aux: Tensor, out: Tensor, dout: Tensor, dqkv: Tensor, dkv_aux: Tensor, *, B: int,
-                  T: int, N0: int, G: int, H: int, lse: Optional[Tensor] = None, n_q: Optional[int] = None) -> None:
+                  T: int, N0: int, G: int, H: int, lse: Optional[Tensor] = None, n_q: Optional[int] = None,
+                  scratch: Optional[Tensor] = None) -> None:
     for t in (qkv, kv_aux, out, dout, dqkv):
         _req(t, torch.bfloat16, "attention_bwd"); assert t.is_contiguous()
     _req(dkv_aux, torch.float32, "attention_bwd dkv_aux")
@@ -359,9 +360,12 @@ def attention_bwd(qkv: Tensor, kv_aux: Tensor, out: Tensor, dout: Tensor, dqkv: 
     assert dkv_aux.is_contiguous()
     if lse is not None:
         _req(lse, torch.float32, "attention_bwd lse"); assert lse.is_contiguous() and lse.numel() == B * T * H * N0
+    if scratch is not None:
+        _req(scratch, torch.float32, "attention_bwd scratch")
+        assert scratch.is_contiguous() and scratch.numel() >= B * T * H * (G + T + 1) * 128
     rc = _lib.load().gava_attention_bwd(qkv.data_ptr(), kv_aux.data_ptr(), out.data_ptr(), dout.data_ptr(), _ptr(lse),
-                                        dqkv.data_ptr(), dkv_aux.data_ptr(), B, T, N0, G, H, N0 if n_q is None else n_q,
-                                        _stream())
+                                        dqkv.data_ptr(), dkv_aux.data_ptr(), _ptr(scratch), B, T, N0, G, H,
+                                        N0 if n_q is None else n_q, _stream())
     _lib.check(rc, "gava_attention_bwd")
 
 

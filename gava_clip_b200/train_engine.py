@@ -138,7 +138,8 @@ class TowerTrainer(TowerEngine):
             "cls_bf": z(BT, D, dt=bf), "aux_n": z(R, D, dt=bf), "frame_feat": z(BT, Ep, dt=f32),
             # ---- backward scratch
             "dx": z(M, D, dt=f32), "dxb": z(M, D, dt=bf), "g4": z(M, Dm, dt=bf), "gD": z(M, D, dt=bf),
-            "dqkv": z(M, 3 * D, dt=bf), "dkvaux": z(R, 2 * D, dt=f32), "dkvaux_bf": z(R, 2 * D, dt=bf),
+            "dqkv": z(M, 3 * D, dt=bf), "dkvaux": z(R, 2 * D, dt=f32),
+            "dkv_slots": z(BT * e.num_heads * (G + T + 1) * 128, dt=f32), "dkvaux_bf": z(R, 2 * D, dt=bf),
             "daux_n": z(R, D, dt=bf), "d_lcp": z(BT, D, dt=f32), "d_sum": z(BT, D, dt=f32), "d_sum_bf": z(BT, D, dt=bf),
             "dsmix": z(BT, D, dt=bf), "dsqkv": z(BT, 3 * D, dt=bf), "dsn": z(BT, D, dt=bf), "d_cp": z(BT, D, dt=f32),
             "d_cp_bf": z(BT, D, dt=bf), "tA": z(3 * D, BTp, dt=bf), "tB": z(D, BTp, dt=bf),
@@ -275,7 +276,7 @@ class TowerTrainer(TowerEngine):
                 ops.gemm(W["dxc_bf"], P[k + "out.wT"], gD.view(BT, N0 * D)[:, :D], mode=ops.EPI_BIAS_BF16)   # dO, cls rows of gD
                 W["dqkv"].view(BT * N0, 3, D)[:, 0].zero_()                          # dq of the rows without a query
                 ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G,
-                                  H=H, lse=W["lse"][i], n_q=1)
+                                  H=H, lse=W["lse"][i], n_q=1, scratch=W["dkv_slots"])
             else:
                 # ---- MLP: dx += dLN2( (dx W2 * g'(a1)) W1 )
                 ops.gemm(dxb, P[k + "fc2.wT"], W["g4"], mode=ops.EPI_DGELU_BF16, aux=W["a1"][i])
@@ -284,7 +285,7 @@ class TowerTrainer(TowerEngine):
                 # ---- attention: dO = dx Wo; (dq, dk, dv, d kv_aux); dx += dLN1(dqkv Wqkv)
                 ops.gemm(dxb, P[k + "out.wT"], gD, mode=ops.EPI_BIAS_BF16)
                 ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G,
-                                  H=H, lse=W["lse"][i])
+                                  H=H, lse=W["lse"][i], scratch=W["dkv_slots"])
             ops.gemm(W["dqkv"], P[k + "qkv.wT"], gD, mode=ops.EPI_BIAS_BF16)
             ops.layernorm_bwd(gD, W["x_in"][i], P[k + "norm1.w"], dx, rows=M, D=D, add1=dx, dx_bf16=dxb)
             # ---- K/V-only prompt rows: d kv_aux -> normalised rows -> global / local / summary / cls_proj gradients

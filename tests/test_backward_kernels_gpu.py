@@ -107,6 +107,23 @@ def test_attention_bwd(cuda, B, T, N0, G, H):
     dqkv2 = torch.zeros_like(qkv); dkv_aux2 = torch.empty_like(dkv_aux)
     ops.attention_bwd(qkv, kv_aux, out2, dout, dqkv2, dkv_aux2, B=B, T=T, N0=N0, G=G, H=H, lse=lse)
     check(dqkv2, dkv_aux2)
+    # two-stage (slot + fixed-order sum) accumulation of the prompt-row gradients: same values, bit-reproducible
+    slots = torch.empty(BT * H * (G + T + 1) * 128, device=cuda)
+    runs = []
+    for _ in range(2):
+        dq3 = torch.zeros_like(qkv); da3 = torch.full_like(dkv_aux, float("nan"))
+        ops.attention_bwd(qkv, kv_aux, out2, dout, dq3, da3, B=B, T=T, N0=N0, G=G, H=H, lse=lse, scratch=slots)
+        check(dq3, da3)
+        runs.append((dq3, da3))
+    assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+    # last-layer form: gradients arrive at the cls query row only
+    dout1 = torch.zeros_like(dout)
+    dout1.view(BT, N0, D)[:, 0] = dout.view(BT, N0, D)[:, 0]
+    qr.grad = None; ar.grad = None
+    _attn_ref(qr, ar, B, T, N0, G, H).backward(dout1.float())
+    dq4 = torch.zeros_like(qkv); da4 = torch.empty_like(dkv_aux)
+    ops.attention_bwd(qkv, kv_aux, out2, dout1, dq4, da4, B=B, T=T, N0=N0, G=G, H=H, lse=lse, scratch=slots, n_q=1)
+    check(dq4, da4)
 
 
 @pytest.mark.parametrize("B,T,H", [(3, 8, 12), (2, 70, 2), (1, 3, 2)])

@@ -316,15 +316,15 @@ def test_finetune_gradients_match_oracle(cuda, name):
     bad = {n: v for n, v in worst.items() if v[0] > 6e-2 or v[1] < 0.998}
     assert not bad, f"gradient mismatch (rel-L2, cosine): {bad}"
     # A second pass WITHOUT zeroing reuses tape / scratch and must accumulate (micro-batch loop of train.py:426-485):
-    # grad == 2 x the first pass.  Not bit-exact: the K/V-only prompt rows collect their gradients with f32 atomics, whose
-    # order varies from run to run, and each bf16 cast of the gradient stream re-rounds that noise, so two runs agree to
-    # bf16 rounding (~2^-8), not to fp32.  k_proj.* of the summary attention are cancellation-dominated and skipped.
+    # grad == 2 x the first pass.  The gradient stream is reproducible (the prompt rows' K/V gradients are summed in a
+    # fixed order, attention_bwd's slot path); only leaf reductions that use f32 atomics (bias / LayerNorm-weight /
+    # time_embed / local_prompts sums) vary in the last bits.  k_proj.* of the summary attention are cancellation-dominated.
     g1 = {n: params[n].grad.clone() for n in vis}
     Fn.cross_entropy(model(video.to(cuda))[0], labels.to(cuda)).backward()
     for n in vis:
         if "k_proj" in n:
             continue
-        assert rel_l2(params[n].grad, 2 * g1[n]) < 1e-2, n
+        assert rel_l2(params[n].grad, 2 * g1[n]) < 1e-4, n
 
 
 def test_text_side_finetune_with_frozen_tower(cuda):

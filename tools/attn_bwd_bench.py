@@ -13,12 +13,14 @@ lse = torch.empty(BT, H, N0, device=dev)
 ops.attention_train(qkv, kv_aux, out, lse, B=B, T=T, N0=N0, G=G, H=H)
 dout = torch.randn(BT * N0, D, device=dev, generator=g).bfloat16()
 dqkv = torch.empty_like(qkv); dkv = torch.empty(G + 2 * BT, 2 * D, device=dev)
-for use_lse in (True, False):
+slots = torch.empty(BT * H * (G + T + 1) * 128, device=dev)
+for use_lse, use_slots in ((True, True), (True, False), (False, False)):
+    kw = dict(B=B, T=T, N0=N0, G=G, H=H, lse=lse if use_lse else None, scratch=slots if use_slots else None)
     for _ in range(3):
-        ops.attention_bwd(qkv, kv_aux, out, dout, dqkv, dkv, B=B, T=T, N0=N0, G=G, H=H, lse=lse if use_lse else None)
+        ops.attention_bwd(qkv, kv_aux, out, dout, dqkv, dkv, **kw)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(10):
-        ops.attention_bwd(qkv, kv_aux, out, dout, dqkv, dkv, B=B, T=T, N0=N0, G=G, H=H, lse=lse if use_lse else None)
+        ops.attention_bwd(qkv, kv_aux, out, dout, dqkv, dkv, **kw)
     e1.record(); torch.cuda.synchronize()
-    print(f"{os.environ.get('GAVA_LIB_PATH', 'default')} lse={use_lse}: {e0.elapsed_time(e1) / 10 * 1e3:.1f} us per launch")
+    print(f"{os.environ.get('GAVA_LIB_PATH', 'default')} T={T} lse={use_lse} slots={use_slots}: {e0.elapsed_time(e1) / 10 * 1e3:.1f} us")
