@@ -303,6 +303,22 @@ def memory_head(sd: SD, text_features: Tensor, memory: Tensor, n_cls: int) -> Te
     return F.log_softmax(torch.cat(cols, dim=1), dim=-1)
 
 
+def nte_head(sd: SD, summary: Tensor, video_nte: Tensor) -> Tensor:
+    """Video <-> numeric-text-embedding branch -- VitaCLIP_model.py:311-343.
+
+    summary: (B, D) temporal mean of the summary tokens; video_nte: (B, NUM_COMB, E).
+    """
+    sp = F.linear(summary, sd["sum_proj.weight"], sd["sum_proj.bias"])
+    sp = sp / sp.norm(dim=-1, keepdim=True)
+    with torch.no_grad():
+        valid = (video_nte.sum(dim=-1).sum(dim=-1) != 0).float()
+        valid_mat = valid.unsqueeze(1) * valid.unsqueeze(0)
+    nte = video_nte / video_nte.norm(dim=-1, keepdim=True)
+    sim = torch.bmm(sp.unsqueeze(0).expand(nte.shape[1], -1, -1), nte.permute(1, 2, 0)).mean(0)
+    mat = sd["logit_scale_vm"] * (sim * valid_mat)
+    return F.log_softmax(mat, dim=-1) + F.log_softmax(mat, dim=-2)
+
+
 # --------------------------------------------------------------------------- #
 # whole path
 # --------------------------------------------------------------------------- #

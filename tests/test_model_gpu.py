@@ -474,3 +474,50 @@ def test_eval_after_training_steps_sees_updated_weights(cuda):
     # a different batch size in training (ragged last batch) allocates its own tape and still works
     loss = tuner.step(video[:1], labels[:1])
     assert torch.isfinite(loss)
+
+
+def test_finetune_config5_model_gradients(cuda):
+    """BASELINE configs[4] model: KAPT prompt learner (knowledge-aware context through the per-class projector MLPs) +
+    support-memory head + NTE head, one fine-tune forward/backward with the reference's loss (focal-ordinal CE + memory CE
+    + NTE diagonal term).  Gradients of every trainable family against fp32 CPU autograd through the oracle -- this is
+    the path where the gradient of the encoder's `summary` output (NTE head) enters the tower's backward."""
+    from gava_clip_b200.finetune import finetune_loss
+    from oracle import vita_oracle as vo
+    name = "kapt_b16_t8"
+    model, kw, B = build_model(name, device=cuda)
+    inp = fx.make_inputs(name)
+    labels = torch.tensor([2, 0])
+    mt_labels = torch.tensor([1, 2])
+    model.train()
+    out = model(inp["video"].to(cuda), memory=inp["memory"].to(cuda), video_nte=inp["video_nte"].to(cuda))
+    assert out[1] is not None and out[2] is not None
+    loss = finetune_loss(out[0], labels.to(cuda), out[1], mt_labels.to(cuda), logits_vm=out[2], vnte_loss_weight=0.1)
+    loss.backward()
+    # ---- oracle
+    cpu, _, _ = build_model(name)
+    names = [n for n, p in cpu.named_parameters() if p.requires_grad]
+    sd = {k: v.detach().clone() for k, v in cpu.state_dict().items()}
+    for n in names:
+        sd[n].requires_grad_(True)
+    v, summary = vo.vision_encoder(sd, inp["video"], num_frames=8, num_heads=12, num_layers=12)
+    cntn = cpu.prompt_learner.context_prompt_learner.cntn_embeds
+    prompts = vo.assemble_prompts(sd, cpu.tokenized_prompts, 8, kapt=True, cntn_embeds=cntn)
+    tfs = [vo.text_encoder(sd, p, t, heads=8, layers=12) for p, t in zip(prompts, cpu.tokenized_prompts)]
+    ref_logits, text_features = vo.logit_head(v, tfs, sd["logit_scale"])
+    ref_mt = vo.memory_head(sd, text_features, inp["memory"], 3)
+    ref_vm = vo.nte_head(sd, summary, inp["video_nte"])
+    ref_loss = finetune_loss(ref_logits, labels, ref_mt, mt_labels, logits_vm=ref_vm, vnte_loss_weight=0.1)
+    ref_loss.backward()
+    assert rel_err(out[0].detach(), ref_logits.detach()) < TOL
+    assert abs(float(loss.detach()) - float(ref_loss.detach())) < 2e-2 * max(1.0, abs(float(ref_loss.detach())))
+    params = dict(model.named_parameters())
+    bad = {}
+    for n in names:
+        g, r = params[n].grad, sd[n].grad
+        assert g is not None and torch.isfinite(g).all(), n
+        if r is None or float(r.abs().max()) == 0.0 or "k_proj" in n:
+            continue
+        c, e = _cos(g, r), rel_l2(g, r)
+        if c < 0.995 or e > 1e-1:
+            bad[n] = (round(e, 4), round(c, 5))
+    assert not bad, f"gradient mismatch (rel-L2, cosine): {bad}"

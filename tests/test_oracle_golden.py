@@ -95,3 +95,18 @@ def test_input_stage_geometry_matches_oracle():
     lg = torch.randn(6, 3)
     assert torch.allclose(aggregate_views(lg), lg.softmax(-1).mean(0))
     assert torch.allclose(aggregate_views(lg, n_views=3), lg.softmax(-1).view(2, 3, 3).mean(1))
+
+
+def test_oracle_memory_and_nte_heads_match_reference():
+    """memory_head / nte_head (VitaCLIP_model.py:311-343, 347-391) against the reference's logits_mt / logits_vm goldens."""
+    import torch
+    from oracle import vita_oracle as vo
+    from tests.util import build_model, load_golden
+    g = load_golden("kapt_b16_t8")
+    model, kw, _ = build_model("kapt_b16_t8")
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    inp = fx.make_inputs("kapt_b16_t8")
+    with torch.no_grad():
+        v, summary = vo.vision_encoder(sd, inp["video"], num_frames=8, num_heads=12, num_layers=12)
+        assert float((vo.nte_head(sd, summary, inp["video_nte"]) - g["logits_vm"]).abs().max()) < 1e-4
+        assert float((vo.memory_head(sd, g["text_features"], inp["memory"], 3) - g["logits_mt"]).abs().max()) < 1e-3
