@@ -249,6 +249,15 @@ class TextTower:
         mm(rn, R, Wd, (w_hi, w_lo), out)
         return out[:, :E].contiguous()
 
+    def _tokens_on(self, device) -> Tensor:
+        """concatenated token ids on `device`, cached: the SAME tensor every step, so consumers can key per-tokenisation
+        state (EOT row indices, which need a host sync to compute) on it"""
+        toks = self.prompt_learner.tokenized_prompts
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in toks)
+        if getattr(self, "_tok_cache", (None, None))[0] != key:
+            self._tok_cache = (key, torch.cat([t.to(device) for t in toks], dim=0))
+        return self._tok_cache[1]
+
     def features(self, device: torch.device, need_grad: bool = False):
         """-> (t_hat (R,E) L2-normalised rows, class_offsets int32 (n_cls+1), text_features (n_cls,E), counts)."""
         sig = self._signature(device)
@@ -257,7 +266,7 @@ class TextTower:
         with torch.set_grad_enabled(need_grad):
             prompts = self.prompt_learner()
             counts = [p.shape[0] for p in prompts]
-            tok = torch.cat([t.to(device) for t in self.prompt_learner.tokenized_prompts], dim=0)
+            tok = self._tokens_on(device)
             if device.type == "cuda" and not need_grad:
                 raw = self._encode_sm100(torch.cat(prompts, dim=0).to(device).float(), tok)
             elif device.type == "cuda" and self.native_train and not any(p.requires_grad for p in self.textual.parameters()):

@@ -18,6 +18,7 @@ front of it, the cosine head behind it.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -33,6 +34,8 @@ class TextTrainer:
         self._pack_key = None
         self.P: Dict[str, object] = {}
         self.ws: Dict[tuple, Dict[str, object]] = {}
+        self.graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
+        self.use_graph = os.environ.get("GAVA_CUDA_GRAPH", "1") != "0"
 
     # ------------------------------------------------------------------ frozen weights: bf16 [N,K] and transposed copies
     def pack(self) -> None:
@@ -66,6 +69,8 @@ class TextTrainer:
                 "fc.w": pair(blk.mlp.c_fc.weight), "fc.wT": bft(blk.mlp.c_fc.weight), "fc.b": f32(blk.mlp.c_fc.bias),
                 "pj.w": pair(blk.mlp.c_proj.weight), "pj.wT": bft(blk.mlp.c_proj.weight), "pj.b": f32(blk.mlp.c_proj.bias)})
         self.P, self._pack_key = P, key
+        self.graphs.clear()      # captured graphs hold pointers into the old packed tensors
+        self.ws.clear()
 
     def workspace(self, R: int, L: int) -> Dict[str, object]:
         key = (R, L)
@@ -85,23 +90,22 @@ class TextTrainer:
              "rows": z(R, Wd, dt=f32), "rn": z(R, Wd, dt=f32), "feat": z(R, Ep, dt=f32),
              "dx": z(M, Wd, dt=f32), "dxb": z(M, Wd, dt=bf), "g4": z(M, 4 * Wd, dt=bf), "gD": z(M, Wd, dt=bf),
              "dqkv": z(M, 3 * Wd, dt=bf), "dfeat": z(R, Ep, dt=f32), "dfeat_bf": z(R, Ep, dt=bf), "drn": z(R, Wd, dt=bf),
-             "drows": z(R, Wd, dt=f32)}
+             "drows": z(R, Wd, dt=f32),
+             "prompts_in": z(M, Wd, dt=f32), "pos_rep": self.P["pos"][:L].repeat(R, 1).contiguous(),
+             "row_idx": torch.zeros(R, device=dev, dtype=torch.long)}
+        W["dfeat"].zero_()
         self.ws[key] = W
         return W
 
     # ------------------------------------------------------------------ forward with tape
-    def forward_train(self, prompts: Tensor, tokenized: Tensor) -> Tensor:
-        """prompts f32 [R, L, W] (assembled token embeddings), tokenized int [R, L] -> raw text features f32 [R, E]."""
+    def _forward_body(self, R: int, L: int) -> None:
+        """W["prompts_in"] (f32 [R*L, W]) -> W["feat"]; every buffer is static, so the launch sequence can be replayed."""
         t = self.textual
-        R, L, Wd = prompts.shape
-        H = t.transformer.resblocks[0].n_head
-        if Wd // H != 64 or Wd % 128 != 0 or L > 128:
-            raise NotImplementedError("text tower kernels are specialised for head_dim 64, width % 128 == 0, <= 128 tokens")
-        self.pack()
         P, W = self.P, self.workspace(R, L)
+        Wd = t.text_projection.shape[0]
+        H = t.transformer.resblocks[0].n_head
         M = R * L
-        E = t.text_projection.shape[1]
-        torch.add(prompts.reshape(M, Wd), P["pos"].repeat(R, 1), out=W["x_in"][0])          # :157 (memory plumbing)
+        torch.add(W["prompts_in"], W["pos_rep"], out=W["x_in"][0])                          # :157 (memory plumbing)
 
         def mm(a32: Tensor, rows: int, K: int, w, out: Tensor, bias=None, resid=None) -> None:
             """out(f32) = [resid +] a32 @ (w_hi + w_lo)^T + bias as a 3-term split-bf16 product."""
@@ -120,42 +124,77 @@ class TextTrainer:
             ops.layernorm(W["h"].view(4 * M, Wd), None, None, W["a1"][i].view(4 * M, Wd), rows=4 * M, in_row_stride=Wd)  # keep bf16 pre-activations
             ops.quickgelu_f32(W["h"])
             mm(W["h"], M, 4 * Wd, b["pj.w"], xnext, bias=b["pj.b"], resid=xmid)
-        self.eot = torch.where(tokenized == t.vocab_size - 1)[-1]                 # :169 (un-shifted ids: KAPT quirk kept)
-        self.row_idx = torch.arange(R, device=prompts.device) * L + self.eot
-        torch.index_select(W["x_in"][len(P["blocks"])], 0, self.row_idx, out=W["rows"])   # EOT gather: memory plumbing
+        torch.index_select(W["x_in"][len(P["blocks"])], 0, W["row_idx"], out=W["rows"])     # EOT gather: memory plumbing
         ops.layernorm(W["rows"], P["lnf"][0], P["lnf"][1], W["rn"], rows=R, in_row_stride=Wd)
         mm(W["rn"], R, Wd, P["proj.wT"], W["feat"])
-        return W["feat"][:, :E]
+
+    def _replay(self, kind: str, R: int, L: int, body) -> None:
+        """Run `body` eagerly the first time for a shape (kernel attributes, allocator), then from a captured CUDA graph:
+        the text side is ~480 latency-bound launches per step, replayed back-to-back instead of issued one by one."""
+        if not self.use_graph or torch.cuda.is_current_stream_capturing():
+            body(R, L)
+            return
+        key = (kind, R, L)
+        g = self.graphs.get(key)
+        if g is None:
+            body(R, L)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):   # a DataLoader thread may be busy with CUDA calls
+                body(R, L)
+            self.graphs[key] = g
+        g.replay()
+
+    def forward_train(self, prompts: Tensor, tokenized: Tensor) -> Tensor:
+        """prompts f32 [R, L, W] (assembled token embeddings), tokenized int [R, L] -> raw text features f32 [R, E]."""
+        t = self.textual
+        R, L, Wd = prompts.shape
+        H = t.transformer.resblocks[0].n_head
+        if Wd // H != 64 or Wd % 128 != 0 or L > 128:
+            raise NotImplementedError("text tower kernels are specialised for head_dim 64, width % 128 == 0, <= 128 tokens")
+        self.pack()
+        W = self.workspace(R, L)
+        tok_key = (tokenized.data_ptr(), tokenized._version, R, L)
+        if W.get("tok_key") != tok_key:
+            eot = torch.where(tokenized == t.vocab_size - 1)[-1]                  # :169 (un-shifted ids: KAPT quirk kept)
+            W["row_idx"].copy_(torch.arange(R, device=prompts.device) * L + eot)
+            W["tok_key"] = tok_key
+        W["prompts_in"].copy_(prompts.reshape(R * L, Wd))
+        self._replay("fwd", R, L, self._forward_body)
+        return W["feat"][:, : t.text_projection.shape[1]]
 
     # ------------------------------------------------------------------ backward
-    def backward(self, R: int, L: int, d_feat: Tensor) -> Tensor:
-        """d(raw features) [R, E] -> d(prompts) f32 [R, L, W] (a workspace view; valid until the next backward)."""
+    def _backward_body(self, R: int, L: int) -> None:
+        """W["dfeat"] (f32 [R, Ep], zero-padded) -> W["dx"] = d(prompts)."""
         t = self.textual
         P, W = self.P, self.workspace(R, L)
         Wd = t.text_projection.shape[0]
         H = t.transformer.resblocks[0].n_head
         M = R * L
-        E = d_feat.shape[1]
         dx, dxb, gD = W["dx"], W["dxb"], W["gD"]
-        W["dfeat"].zero_()
-        W["dfeat"][:, :E].copy_(d_feat)
         Ep = W["dfeat"].shape[1]
         ops.layernorm(W["dfeat"], None, None, W["dfeat_bf"], rows=R, in_row_stride=Ep)
         ops.gemm(W["dfeat_bf"], P["proj.w"], W["drn"], mode=ops.EPI_BIAS_BF16)
         ops.layernorm_bwd(W["drn"], W["rows"], P["lnf"][0], W["drows"], rows=R, D=Wd)
         dx.zero_()
-        dx.index_copy_(0, self.row_idx, W["drows"])                               # scatter to the EOT rows
+        dx.index_copy_(0, W["row_idx"], W["drows"])                               # scatter to the EOT rows
+        ops.layernorm(dx, None, None, dxb, rows=M, in_row_stride=Wd)              # bf16 copy; kept current by the LN backward
         for i in reversed(range(len(P["blocks"]))):
             b = P["blocks"][i]
-            ops.layernorm(dx, None, None, dxb, rows=M, in_row_stride=Wd)
             ops.gemm(dxb, b["pj.wT"], W["g4"], mode=ops.EPI_DGELU_BF16, aux=W["a1"][i])
             ops.gemm(W["g4"], b["fc.wT"], gD, mode=ops.EPI_BIAS_BF16)
             ops.layernorm_bwd(gD, W["x_mid"][i], b["ln2"][0], dx, rows=M, D=Wd, add1=dx, dx_bf16=dxb)
             ops.gemm(dxb, b["out.wT"], gD, mode=ops.EPI_BIAS_BF16)
             ops.causal_attention_bwd(W["qkv"][i], gD, W["dqkv"], n_seq=R, L=L, H=H)
             ops.gemm(W["dqkv"], b["in.wT"], gD, mode=ops.EPI_BIAS_BF16)
-            ops.layernorm_bwd(gD, W["x_in"][i], b["ln1"][0], dx, rows=M, D=Wd, add1=dx)
-        return dx.view(R, L, Wd)
+            ops.layernorm_bwd(gD, W["x_in"][i], b["ln1"][0], dx, rows=M, D=Wd, add1=dx, dx_bf16=dxb)
+
+    def backward(self, R: int, L: int, d_feat: Tensor) -> Tensor:
+        """d(raw features) [R, E] -> d(prompts) f32 [R, L, W] (a workspace view; valid until the next backward)."""
+        W = self.workspace(R, L)
+        W["dfeat"][:, : d_feat.shape[1]].copy_(d_feat)                            # padding columns stay zero
+        self._replay("bwd", R, L, self._backward_body)
+        return W["dx"].view(R, L, -1)
 
 
 class TextTrainFunction(torch.autograd.Function):
