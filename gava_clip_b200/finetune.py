@@ -92,7 +92,8 @@ class FineTuner:
     def __init__(self, model, lr: float = 1e-4, weight_decay: float = 0.2, betas: Tuple[float, float] = (0.9, 0.999),
                  eps: float = 1e-8, focal_ordinal: bool = True, ordinal_beta: float = 0.2,
                  memory_loss_weight: float = 0.1, process_group=None,
-                 lr_schedule: Optional[Callable[[int], float]] = None, text_tf32: bool = False):
+                 lr_schedule: Optional[Callable[[int], float]] = None, text_tf32: bool = False,
+                 loss_fn: Optional[Callable[..., Tensor]] = None):
         self.model = model
         tower_ids = {id(p) for p in model.visual.parameters()}
         tower = [p for p in model.visual.parameters() if p.requires_grad]
@@ -113,6 +114,9 @@ class FineTuner:
         # Only the prompt assembly / KAPT projector / cosine head / memory heads are PyTorch matmuls in a step (the text
         # transformer runs on text_train.TextTrainer); text_tf32=True lets those few use TF32 tensor-core products.
         self.text_tf32 = text_tf32
+        # loss_fn(logits, logits_mt, logits_vm, labels, memory_labels) -> scalar: plug in the reference's other criteria
+        # (training/loss_utils.py: sigmoid_focal_loss, InfoNCE_loss, ...); default = finetune_loss, the shipped recipe
+        self.loss_fn = loss_fn
         self.step_count = 0
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
 
@@ -141,9 +145,12 @@ class FineTuner:
         torch.backends.cuda.matmul.allow_tf32 = tf32_prev or self.text_tf32
         try:
             logits, logits_mt, logits_vm = self.model(video, memory=memory, video_nte=video_nte)
-            loss = finetune_loss(logits, labels, logits_mt, memory_labels, focal_ordinal=self.focal_ordinal,
-                                 beta=self.ordinal_beta, memory_loss_weight=self.memory_loss_weight, logits_vm=logits_vm,
-                                 vnte_loss_weight=vnte_loss_weight)
+            if self.loss_fn is not None:
+                loss = self.loss_fn(logits, logits_mt, logits_vm, labels, memory_labels)
+            else:
+                loss = finetune_loss(logits, labels, logits_mt, memory_labels, focal_ordinal=self.focal_ordinal,
+                                     beta=self.ordinal_beta, memory_loss_weight=self.memory_loss_weight,
+                                     logits_vm=logits_vm, vnte_loss_weight=vnte_loss_weight)
             (loss * loss_scale).backward()
         finally:
             eng.grad_ready_hook = None

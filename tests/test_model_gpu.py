@@ -521,3 +521,38 @@ def test_finetune_config5_model_gradients(cuda):
         if c < 0.995 or e > 1e-1:
             bad[n] = (round(e, 4), round(c, 5))
     assert not bad, f"gradient mismatch (rel-L2, cosine): {bad}"
+
+
+def test_finetune_vit_l14_dims(cuda):
+    """ViT-L/14 dimensions (BASELINE configs[3]: D=1024, 16 heads, 14-pixel patches -> 257 tokens, K=588 patch rows, 16
+    frames -> 282 keys) through the fine-tune forward/backward, 2 layers to keep the CPU oracle's autograd short."""
+    import torch.nn.functional as Fn
+    from gava_clip_b200 import VitaCLIP, tokenizer
+    from oracle import vita_oracle as vo
+    tokenizer.register_tokens(fx.load_tokens())
+    kw, _ = fx.case_kwargs("l14_t16")
+    kw = dict(kw, num_layers=2, num_frames=16)
+    model = VitaCLIP(**kw)
+    fx.fill_params_(model.state_dict().items(), seed=2)
+    model.prompt_learner.refresh_token_embeddings(model.textual)
+    cpu_sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    tok = [t.clone() for t in model.tokenized_prompts]
+    model = model.to(cuda).train()
+    video = torch.randn(1, 3, 16, 224, 224, generator=torch.Generator().manual_seed(6))
+    labels = torch.tensor([0])
+    logits = model(video.to(cuda))[0]
+    Fn.cross_entropy(logits, labels.to(cuda)).backward()
+    names = ["visual.time_embed", "visual.global_prompts", "visual.blocks.0.local_prompts",
+             "visual.blocks.0.summary_attn_layer.q_proj.weight", "visual.blocks.1.summary_attn_layer.out_proj.bias",
+             "prompt_learner.ctx"]
+    for n in names:
+        cpu_sd[n].requires_grad_(True)
+    v, _ = vo.vision_encoder(cpu_sd, video, num_frames=16, num_heads=16, num_layers=2)
+    prompts = vo.assemble_prompts(cpu_sd, tok, 8, kapt=False)
+    tfs = [vo.text_encoder(cpu_sd, p, t, heads=12, layers=12) for p, t in zip(prompts, tok)]
+    ref_logits, _ = vo.logit_head(v, tfs, cpu_sd["logit_scale"])
+    Fn.cross_entropy(ref_logits, labels).backward()
+    assert rel_err(logits.detach(), ref_logits.detach()) < TOL
+    params = dict(model.named_parameters())
+    for n in names:
+        assert _cos(params[n].grad, cpu_sd[n].grad) > 0.995 and rel_l2(params[n].grad, cpu_sd[n].grad) < 8e-2, n
