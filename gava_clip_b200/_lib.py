@@ -37,6 +37,7 @@ class GemmEpilogue(C.Structure):
         ("aux", C.c_void_p),
         ("ld_aux", C.c_int64),
         ("aux_out", C.c_void_p),
+        ("max_ctas", C.c_int32),
     ]
 
 
@@ -49,6 +50,7 @@ SIGNATURES = {
     "gava_init": [],
     "gava_gemm_bf16_fwd": [_p, _i64, _p, _i64, _i64, _i64, _i64, C.POINTER(GemmEpilogue), _p],
     "gava_layernorm_fwd": [_p, _i64, _p, _p, _p, _i64, _i32, _i64, _i32, _f32, _p],
+    "gava_layernorm_resid_fwd": [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i32, _i64, _i32, _f32, _p],
     "gava_patch_gather_fwd": [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p],
     "gava_patch_gather_u8_fwd": [_p, _p, _p, C.POINTER(C.c_float), C.POINTER(C.c_float), _i32, _i32, _i32, _i32, _i32, _i32, _p],
     "gava_cls_rows_fwd": [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _p],

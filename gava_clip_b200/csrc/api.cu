@@ -54,6 +54,13 @@ int gava_layernorm_fwd(const float* x, int64_t in_row_stride, const float* weigh
   return layernorm(x, in_row_stride, weight, bias, out, out_row_stride, out_bf16, rows, D, eps, (cudaStream_t)stream);
 }
 
+int gava_layernorm_resid_fwd(const float* x, int64_t in_row_stride, const void* delta, int64_t delta_row_stride,
+                             const float* weight, const float* bias, void* out, int64_t out_row_stride, int32_t out_bf16,
+                             int64_t rows, int32_t D, float eps, void* stream) {
+  return layernorm_resid(x, in_row_stride, delta, delta_row_stride, weight, bias, out, out_row_stride, out_bf16, rows, D, eps,
+                         (cudaStream_t)stream);
+}
+
 int gava_patch_gather_fwd(const float* video, void* A, int32_t B, int32_t T, int32_t H, int32_t W, int32_t P,
                           int32_t Kpad, void* stream) {
   return patch_gather(video, A, B, T, H, W, P, Kpad, (cudaStream_t)stream);

@@ -212,6 +212,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage,
 #else
           resid[i] = (grow < p.M) ? *reinterpret_cast<const float4*>(p.resid + (long long)grow * p.ldr + col0 + 4 * (lane & 7))
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.aux != nullptr && grow < p.M) {   // second, bf16 addend (the attention branch kept as a bf16 delta)
+            const uint2 u = *reinterpret_cast<const uint2*>(p.aux + (long long)grow * p.ld_aux + col0 + 4 * (lane & 7));
+            const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+            resid[i].x += __bfloat162float(lo.x); resid[i].y += __bfloat162float(lo.y);
+            resid[i].z += __bfloat162float(hi.x); resid[i].w += __bfloat162float(hi.y);
+          }
 #endif
         }
       }
@@ -596,7 +602,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
 }
 
 template <int MODE>
-static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream, int max_ctas = 0) {
   using Cfg = Gemm2Cfg;
   static bool attr_set = false;
   auto kern = gemm2_tcgen05_kernel<MODE>;
@@ -606,15 +612,16 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
     attr_set = true;
   }
   const int tiles = ((args.M + 2 * BM - 1) / (2 * BM)) * (args.N / Cfg::BN);
-  const int max_clusters = num_sms() / 2;
+  int max_clusters = num_sms() / 2;
+  if (max_ctas > 1 && max_ctas / 2 < max_clusters) max_clusters = max_ctas / 2;   // leave SMs to a concurrent stream
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
   kern<<<2 * clusters, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, args);
   return check_launch("gemm2_tcgen05");
 }
 
-static int dispatch_mode2(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t s) {
+static int dispatch_mode2(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t s, int max_ctas) {
   switch (mode) {
-    case EPI_BIAS_BF16: return launch_gemm2<EPI_BIAS_BF16>(ta, tb, a, s);
+    case EPI_BIAS_BF16: return launch_gemm2<EPI_BIAS_BF16>(ta, tb, a, s, max_ctas);
     case EPI_BIAS_GELU_BF16: return launch_gemm2<EPI_BIAS_GELU_BF16>(ta, tb, a, s);
     case EPI_BIAS_RESID_F32: return launch_gemm2<EPI_BIAS_RESID_F32>(ta, tb, a, s);
     case EPI_BIAS_F32: return launch_gemm2<EPI_BIAS_F32>(ta, tb, a, s);
@@ -671,9 +678,10 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
   a.out = epi->out; a.ldo = epi->ldo;
   a.group = epi->group; a.group_stride = epi->group_stride; a.row_offset = epi->row_offset;
   a.pos = epi->pos; a.time_embed = epi->time_embed; a.T = epi->T;
-  a.aux = reinterpret_cast<const __nv_bfloat16*>(epi->aux); a.ld_aux = epi->ld_aux;
+  a.aux = (epi->mode == EPI_DGELU_BF16 || epi->mode == EPI_BIAS_RESID_F32) ? reinterpret_cast<const __nv_bfloat16*>(epi->aux) : nullptr;
+  a.ld_aux = epi->ld_aux;
   a.aux_out = epi->mode == EPI_BIAS_GELU_BF16 ? reinterpret_cast<__nv_bfloat16*>(epi->aux_out) : nullptr;
-  if (pair) return dispatch_mode2(epi->mode, ta, tb, a, stream);
+  if (pair) return dispatch_mode2(epi->mode, ta, tb, a, stream, epi->max_ctas);
   return bn_eff == 256 ? dispatch_mode<256>(epi->mode, ta, tb, a, stream) : dispatch_mode<128>(epi->mode, ta, tb, a, stream);
 }
 

@@ -27,6 +27,11 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
 int layernorm(const float* x, long long in_row_stride, const float* w, const float* b, void* out,
               long long out_row_stride, int out_bf16, long long rows, int D, float eps, cudaStream_t stream);
 
+// LayerNorm(x + delta), delta bf16 (may be null)
+int layernorm_resid(const float* x, long long in_row_stride, const void* delta, long long delta_row_stride, const float* w,
+                    const float* b, void* out, long long out_row_stride, int out_bf16, long long rows, int D, float eps,
+                    cudaStream_t stream);
+
 int patch_gather(const float* video, void* A, int B, int T, int H, int W, int P, int Kpad, cudaStream_t stream);
 
 // mean/std are HOST arrays of 3 floats (passed by value to the kernel); lo may be null

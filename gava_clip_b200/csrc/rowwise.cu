@@ -52,6 +52,7 @@ __device__ __forceinline__ void store_row(const float4 (&x)[V], void* out_row, i
 
 template <int V>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long in_stride,
+                                                        const __nv_bfloat16* __restrict__ delta, long long delta_stride,
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         void* out, long long out_stride, int out_bf16, long long rows,
                                                         float eps) {
@@ -62,25 +63,42 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   float4 v[V];
 #pragma unroll
   for (int j = 0; j < V; ++j) v[j] = src[lane + 32 * j];
+  if (delta != nullptr) {   // x + delta: a residual branch kept as a bf16 tensor (summed here instead of in a GEMM epilogue)
+    const uint2* d = reinterpret_cast<const uint2*>(delta + row * delta_stride);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const uint2 u = d[lane + 32 * j];
+      const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&u.x), hi = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+      v[j].x += __bfloat162float(lo.x); v[j].y += __bfloat162float(lo.y);
+      v[j].z += __bfloat162float(hi.x); v[j].w += __bfloat162float(hi.y);
+    }
+  }
   if (w != nullptr) ln_normalize<V>(v, w, b, eps);
   char* o = reinterpret_cast<char*>(out) + row * out_stride * (out_bf16 ? 2 : 4);
   store_row<V>(v, o, out_bf16);
 }
 
-int layernorm(const float* x, long long in_row_stride, const float* w, const float* b, void* out,
-              long long out_row_stride, int out_bf16, long long rows, int D, float eps, cudaStream_t stream) {
+int layernorm_resid(const float* x, long long in_row_stride, const void* delta, long long delta_row_stride, const float* w,
+                    const float* b, void* out, long long out_row_stride, int out_bf16, long long rows, int D, float eps,
+                    cudaStream_t stream) {
   if (!x || !out || rows < 0 || (w && !b)) { set_error("layernorm: bad arguments"); return GAVA_ERR_ARG; }
   if (rows == 0) return GAVA_OK;
-  if ((in_row_stride & 3) || (out_row_stride & 3)) { set_error("layernorm: row strides must be multiples of 4"); return GAVA_ERR_ARG; }
+  if ((in_row_stride & 3) || (out_row_stride & 3) || (delta_row_stride & 3)) { set_error("layernorm: row strides must be multiples of 4"); return GAVA_ERR_ARG; }
   const unsigned grid = (unsigned)((rows + 7) / 8);
+  const __nv_bfloat16* dl = reinterpret_cast<const __nv_bfloat16*>(delta);
 #define GAVA_LN_CASE(V) \
-  case 128 * V: layernorm_kernel<V><<<grid, 256, 0, stream>>>(x, in_row_stride, w, b, out, out_row_stride, out_bf16, rows, eps); break;
+  case 128 * V: layernorm_kernel<V><<<grid, 256, 0, stream>>>(x, in_row_stride, dl, delta_row_stride, w, b, out, out_row_stride, out_bf16, rows, eps); break;
   switch (D) {
     GAVA_LN_CASE(1) GAVA_LN_CASE(2) GAVA_LN_CASE(3) GAVA_LN_CASE(4) GAVA_LN_CASE(6) GAVA_LN_CASE(8)
     default: set_error("layernorm: unsupported width D=%d (128/256/384/512/768/1024)", D); return GAVA_ERR_SHAPE;
   }
 #undef GAVA_LN_CASE
   return check_launch("layernorm");
+}
+
+int layernorm(const float* x, long long in_row_stride, const float* w, const float* b, void* out,
+              long long out_row_stride, int out_bf16, long long rows, int D, float eps, cudaStream_t stream) {
+  return layernorm_resid(x, in_row_stride, nullptr, 0, w, b, out, out_row_stride, out_bf16, rows, D, eps, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

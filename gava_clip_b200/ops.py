@@ -46,7 +46,7 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
 def gemm(a: Tensor, w: Tensor, out: Tensor, *, mode: int, bias: Optional[Tensor] = None,
          resid: Optional[Tensor] = None, pos: Optional[Tensor] = None, time_embed: Optional[Tensor] = None,
          group: int = 0, group_stride: int = 0, row_offset: int = 0, T: int = 0, aux: Optional[Tensor] = None,
-         aux_out: Optional[Tensor] = None) -> Tensor:
+         aux_out: Optional[Tensor] = None, max_ctas: int = 0) -> Tensor:
     """out = epilogue(a @ w.T).  a: bf16 [M,K] (row stride free), w: bf16 [N,K], fp32 bias [N]."""
     _req(a, torch.bfloat16, "gemm a"); _req(w, torch.bfloat16, "gemm w")
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
@@ -63,11 +63,16 @@ def gemm(a: Tensor, w: Tensor, out: Tensor, *, mode: int, bias: Optional[Tensor]
     epi.bias = _ptr(bias)
     epi.out = out.data_ptr()
     epi.ldo = out.stride(0)
+    epi.max_ctas = max_ctas
     if mode == EPI_BIAS_RESID_F32:
         _req(resid, torch.float32, "gemm resid")
         assert resid.dim() == 2 and resid.stride(1) == 1 and resid.shape[0] >= M
         epi.resid = resid.data_ptr(); epi.ldr = resid.stride(0)
         assert out.shape[0] >= M
+        if aux is not None:      # second, bf16 addend: out = resid + aux + a @ w.T + bias
+            _req(aux, torch.bfloat16, "gemm aux")
+            assert aux.dim() == 2 and aux.stride(1) == 1 and aux.shape[0] >= M and aux.shape[1] >= N and aux.stride(0) % 4 == 0
+            epi.aux = aux.data_ptr(); epi.ld_aux = aux.stride(0)
     elif mode == EPI_PATCH_F32:
         _req(pos, torch.float32, "gemm pos"); _req(time_embed, torch.float32, "gemm time_embed")
         assert pos.is_contiguous() and time_embed.is_contiguous()
@@ -93,7 +98,8 @@ def gemm(a: Tensor, w: Tensor, out: Tensor, *, mode: int, bias: Optional[Tensor]
 
 
 def layernorm(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], out: Tensor, *, rows: int,
-              in_row_stride: int, out_row_stride: Optional[int] = None, eps: float = 1e-5) -> Tensor:
+              in_row_stride: int, out_row_stride: Optional[int] = None, eps: float = 1e-5,
+              delta: Optional[Tensor] = None) -> Tensor:
     """LayerNorm (or plain cast when weight is None) of `rows` rows of width D = weight/out last dim.
 
     Row r is read at x.data_ptr + r*in_row_stride floats: lets the caller gather e.g. the cls rows.
@@ -109,6 +115,13 @@ def layernorm(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], out: 
     if out_row_stride is None:
         out_row_stride = D
     assert x.numel() >= (rows - 1) * in_row_stride + D and out.numel() >= (rows - 1) * out_row_stride + D
+    if delta is not None:       # LayerNorm(x + delta), delta bf16 [rows, D] contiguous
+        _req(delta, torch.bfloat16, "layernorm delta")
+        assert delta.is_contiguous() and delta.shape[-1] == D and delta.numel() >= rows * D
+        rc = _lib.load().gava_layernorm_resid_fwd(x.data_ptr(), in_row_stride, delta.data_ptr(), D, _ptr(weight), _ptr(bias),
+                                                  out.data_ptr(), out_row_stride, out_bf16, rows, D, eps, _stream())
+        _lib.check(rc, "gava_layernorm_resid_fwd")
+        return out
     rc = _lib.load().gava_layernorm_fwd(x.data_ptr(), in_row_stride, _ptr(weight), _ptr(bias), out.data_ptr(),
                                         out_row_stride, out_bf16, rows, D, eps, _stream())
     _lib.check(rc, "gava_layernorm_fwd")

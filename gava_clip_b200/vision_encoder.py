@@ -142,6 +142,12 @@ class TowerEngine:
         # side-stream branch for the temporal-message chain: measured neutral on B200 (3061 vs 3056 clips/s; the pair
         # GEMM CTAs own a whole SM each, so the small kernels cannot co-run), hence off by default
         self.overlap_chain = os.environ.get("GAVA_OVERLAP_CHAIN", "0") == "1"
+        # with the chain on a side stream, the QKV GEMM's persistent grid is capped so that the chain's CTAs find free SMs
+        self.qkv_ctas = int(os.environ.get("GAVA_QKV_CTAS", "0"))
+        # Deferred attention residual: out_proj writes its result as a bf16 delta (no fp32 read-modify-write of the stream,
+        # which made that K=768 GEMM HBM-bound), norm2 normalises x + delta, and the fc2 epilogue -- hidden under a K=3072
+        # mainloop -- adds delta together with the MLP output.  Same bytes overall, but none of them on a critical path.
+        self.defer_resid = os.environ.get("GAVA_DEFER_RESID", "1") != "0"
         self.side_stream = torch.cuda.Stream(device) if device.type == "cuda" else None
         self.launches_last_call = 0      # sm_100a kernels launched (or replayed) by the last run()
 
@@ -308,6 +314,7 @@ class TowerEngine:
             "patches": z(BT * (N0 - 1), self.packed["patch.w"].shape[1], dt=bf),
             "x": z(M, D, dt=f32),
             "xn": z(M, D, dt=bf),
+            "delta": z(M, D, dt=bf),
             "qkv": z(M, 3 * D, dt=bf),
             "h": z(M, Dm, dt=bf),
             "cls_bf": z(BT, D, dt=bf),
@@ -423,22 +430,32 @@ class TowerEngine:
             # ---- x = x + attn(norm1(x)) on the live rows                                     utils.py:190-191
             ops.layernorm(x, P[k + "norm1.w"], P[k + "norm1.b"], xn, rows=M, in_row_stride=D)
             if i < L - 1:
-                ops.gemm(xn, P[k + "qkv.w"], qkv, mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"])
+                ops.gemm(xn, P[k + "qkv.w"], qkv, mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"],
+                         max_ctas=self.qkv_ctas if side is not None else 0)
                 if side is not None:
                     main.wait_event(ev_kv)
                 ops.attention(qkv, W["kvaux"], xn, B=B, T=T, N0=N0, G=G, H=H)
-                ops.gemm(xn, P[k + "out.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "out.b"], resid=x)
-                # ---- x = x + fc2(QuickGELU(fc1(norm2(x))))                                    utils.py:199
-                ops.layernorm(x, P[k + "norm2.w"], P[k + "norm2.b"], xn, rows=M, in_row_stride=D)
-                ops.gemm(xn, P[k + "fc1.w"], h, mode=ops.EPI_BIAS_GELU_BF16, bias=P[k + "fc1.b"])
-                ops.gemm(h, P[k + "fc2.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"], resid=x)
+                if self.defer_resid:
+                    dl = W["delta"]
+                    ops.gemm(xn, P[k + "out.w"], dl, mode=ops.EPI_BIAS_BF16, bias=P[k + "out.b"])
+                    # ---- x = (x + delta) + fc2(QuickGELU(fc1(norm2(x + delta))))              utils.py:191,199
+                    ops.layernorm(x, P[k + "norm2.w"], P[k + "norm2.b"], xn, rows=M, in_row_stride=D, delta=dl)
+                    ops.gemm(xn, P[k + "fc1.w"], h, mode=ops.EPI_BIAS_GELU_BF16, bias=P[k + "fc1.b"])
+                    ops.gemm(h, P[k + "fc2.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"], resid=x, aux=dl)
+                else:
+                    ops.gemm(xn, P[k + "out.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "out.b"], resid=x)
+                    # ---- x = x + fc2(QuickGELU(fc1(norm2(x))))                                    utils.py:199
+                    ops.layernorm(x, P[k + "norm2.w"], P[k + "norm2.b"], xn, rows=M, in_row_stride=D)
+                    ops.gemm(xn, P[k + "fc1.w"], h, mode=ops.EPI_BIAS_GELU_BF16, bias=P[k + "fc1.b"])
+                    ops.gemm(h, P[k + "fc2.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"], resid=x)
             else:
                 # Last layer: only the cls row of each frame reaches the output (vision_encoder.py:126), so every row-wise
                 # op after the key/value projection runs on the BT cls rows alone: K/V for all rows, Q / attention query /
                 # out-proj / MLP for one row per frame.  Row-independent ops => bit-for-meaning identical results.
                 xn_cls = xn.view(BT, N0 * D)[:, :D]                      # row f*N0 of a [M, D] buffer, pitch N0*D
                 x_cls_src = x.view(BT, N0 * D)[:, :D]
-                ops.gemm(xn, P[k + "qkv.w"][D:], qkv[:, D:], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:])
+                ops.gemm(xn, P[k + "qkv.w"][D:], qkv[:, D:], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:],
+                         max_ctas=self.qkv_ctas if side is not None else 0)
                 ops.gemm(xn_cls, P[k + "qkv.w"][:D], qkv.view(BT, N0 * 3 * D)[:, :D], mode=ops.EPI_BIAS_BF16,
                          bias=P[k + "qkv.b"][:D])
                 if side is not None:

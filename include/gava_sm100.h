@@ -48,9 +48,10 @@ typedef struct gava_gemm_epilogue {
   int32_t T;               /* PATCH: frames per clip */
   const float* pos;        /* PATCH: f32 [group+1, N]  (visual.pos_embed) */
   const float* time_embed; /* PATCH: f32 [T, N]        (visual.time_embed, already resized to T) */
-  const void* aux;         /* DGELU: bf16 [M, ld_aux] */
+  const void* aux;         /* DGELU: bf16 [M, ld_aux] pre-activations; RESID (optional): bf16 [M, ld_aux] second addend */
   int64_t ld_aux;
   void* aux_out;           /* GELU (optional): also store the pre-activations acc + bias as bf16 [M, ld_aux] */
+  int32_t max_ctas;        /* 0 = all SMs; otherwise cap the persistent grid (BIAS_BF16 mode) so a concurrent stream keeps SMs */
 } gava_gemm_epilogue;
 
 int gava_version(void);
@@ -72,6 +73,13 @@ int gava_gemm_bf16_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, i
  * D in {128,256,384,512,768,1024}.  Replaces LayerNorm.forward, VitaCLIP_vision_encoder_utils.py:22-28. */
 int gava_layernorm_fwd(const float* x, int64_t in_row_stride, const float* weight, const float* bias, void* out,
                        int64_t out_row_stride, int32_t out_bf16, int64_t rows, int32_t D, float eps, void* stream);
+
+/* gava_layernorm_fwd of (x + delta): delta is a bf16 [rows, D] tensor (row pitch delta_row_stride) holding a residual branch
+ * that was not yet added to the f32 stream -- `x + attn(...)` of VitaCLIP_vision_encoder_utils.py:191 with the out_proj result
+ * kept in bf16; the MLP's fc2 epilogue later adds the same delta (gava_gemm_bf16_fwd, RESID mode with `aux`). */
+int gava_layernorm_resid_fwd(const float* x, int64_t in_row_stride, const void* delta, int64_t delta_row_stride,
+                             const float* weight, const float* bias, void* out, int64_t out_row_stride, int32_t out_bf16,
+                             int64_t rows, int32_t D, float eps, void* stream);
 
 /* Patch gather (im2col) for Conv2d(3, D, k=s=P): video f32 [B,3,T,H,W] -> A bf16 [B*T*(H/P)*(W/P), Kpad] with
  * column index c*P*P + ph*P + pw (the flattened conv weight order); columns >= 3*P*P are zero.

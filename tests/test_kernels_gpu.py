@@ -340,3 +340,23 @@ def test_patch_gather_u8(cuda, P, H, Kpad):
     ops.patch_gather_u8(u8, hi2, lo, mean, std, P)                                                   # hi/lo (fp32 path)
     assert torch.equal(hi2[:, :3 * P * P], ref.bfloat16())
     assert _rel(hi2[:, :3 * P * P].float() + lo[:, :3 * P * P].float(), ref) < 2e-5
+
+
+def test_deferred_residual_pair(cuda):
+    """LayerNorm(x + delta) and the RESID GEMM epilogue with a second bf16 addend (the deferred attention residual)."""
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(21)
+    M, D, K = 1000, 768, 3072
+    x = torch.randn(M, D, device=cuda, generator=g)
+    delta = torch.randn(M, D, device=cuda, generator=g).bfloat16()
+    w = torch.randn(D, device=cuda, generator=g); b = torch.randn(D, device=cuda, generator=g)
+    out = torch.empty(M, D, device=cuda, dtype=torch.bfloat16)
+    ops.layernorm(x, w, b, out, rows=M, in_row_stride=D, delta=delta)
+    ref = F.layer_norm(x + delta.float(), (D,), w, b, 1e-5)
+    assert _rel(out.float(), ref) < 1e-2
+    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
+    wt = (torch.randn(D, K, device=cuda, generator=g) * K ** -0.5).bfloat16()
+    bias = torch.randn(D, device=cuda, generator=g)
+    want = x + delta.float() + a.float() @ wt.float().t() + bias
+    ops.gemm(a, wt, x, mode=ops.EPI_BIAS_RESID_F32, bias=bias, resid=x, aux=delta)
+    assert _rel(x, want) < 2e-5
