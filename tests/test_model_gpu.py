@@ -556,3 +556,23 @@ def test_finetune_vit_l14_dims(cuda):
     params = dict(model.named_parameters())
     for n in names:
         assert _cos(params[n].grad, cpu_sd[n].grad) > 0.995 and rel_l2(params[n].grad, cpu_sd[n].grad) < 8e-2, n
+
+
+def test_finetuner_run_streams_host_batches(cuda):
+    """FineTuner.run (H2D of batch i+1 under step i, losses returned in pinned host memory) == the same batches stepped one
+    by one from device memory on a twin model."""
+    from gava_clip_b200.finetune import FineTuner
+    g = torch.Generator().manual_seed(11)
+    batches = [(torch.randn(2, 3, 3, 64, 64, generator=g).pin_memory(), torch.randint(0, 3, (2,), generator=g).pin_memory())
+               for _ in range(4)]
+    a, _, _ = build_model("tiny", device=cuda)
+    b, _, _ = build_model("tiny", device=cuda)
+    ta, tb = FineTuner(a, lr=1e-3), FineTuner(b, lr=1e-3)
+    streamed = [float(l) for l in ta.run(batches)]
+    serial = [float(tb.step(v.to(cuda), y.to(cuda))) for v, y in batches]
+    assert len(streamed) == 4
+    for s, r in zip(streamed, serial):
+        assert abs(s - r) < 5e-3 * max(1.0, abs(r))
+    for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        if pa.requires_grad and "k_proj" not in n:
+            assert rel_l2(pa, pb) < 5e-3, n
