@@ -116,6 +116,9 @@ class TowerTrainer(TowerEngine):
         key = ("train", B, T)
         if key in self.ws:
             return self.ws[key]
+        # a tape is ~1.9 GB per layer at config 2: keep at most two clip shapes alive (the full batch and a ragged tail)
+        for old in [k for k in self.ws if isinstance(k, tuple) and k and k[0] == "train"][:-1]:
+            del self.ws[old]
         e, dev = self.enc, self.device
         D, N0, G, L = e.feature_dim, int(e.num_patches), e.num_global_prompts, len(e.blocks)
         BT, M = B * T, B * T * N0
