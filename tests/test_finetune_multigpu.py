@@ -70,3 +70,50 @@ def test_two_rank_step_equals_single_process_full_batch(cuda):
         if "k_proj" in n:
             continue      # cancellation-dominated (exact k bias gradient is 0: softmax shift invariance)
         assert rel_l2(ret[0][0][n], ref[n]) < 2e-2, n
+
+
+def _ddp_worker(rank, world, port, ret):
+    """the reference's own loop shape (train.py:347-351, 441-486): DistributedDataParallel + torch.optim.AdamW"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import torch.nn.functional as F
+        model, _, _ = build_model("tiny", device=dev)
+        model.train()
+        before = {n: p.detach().clone() for n, p in model.named_parameters() if p.requires_grad}
+        ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[rank], output_device=rank)
+        opt = torch.optim.AdamW(ddp.parameters(), lr=1e-3, weight_decay=0.2)
+        video, labels = _inputs(dev)
+        lo, hi = rank * 2, rank * 2 + 2
+        for _ in range(2):
+            logits, _, _ = ddp(video[lo:hi])
+            loss = F.cross_entropy(logits, labels[lo:hi])
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+        torch.cuda.synchronize()
+        after = {n: p.detach().cpu() for n, p in model.named_parameters() if p.requires_grad}
+        moved = all(float((after[n].to(dev) - before[n]).abs().max()) > 0 for n in after)
+        finite = all(bool(torch.isfinite(v).all()) for v in after.values())
+        ret[rank] = (after, moved and finite)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_reference_loop_with_ddp_and_torch_adamw(cuda):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = 35500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=600)
+        assert p.exitcode == 0
+    assert ret[0][1] and ret[1][1]
+    for n in ret[0][0]:
+        assert torch.equal(ret[0][0][n], ret[1][0][n]), f"DDP ranks diverged on {n}"
