@@ -576,3 +576,33 @@ def test_finetuner_run_streams_host_batches(cuda):
     for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
         if pa.requires_grad and "k_proj" not in n:
             assert rel_l2(pa, pb) < 5e-3, n
+
+
+def test_training_under_autocast_and_gradscaler(cuda):
+    """The reference's `--use_fp16` loop (train.py:358,441,485): forward under torch.cuda.amp.autocast, loss scaled by a
+    GradScaler.  The tower ignores autocast (it is bf16/fp32 already); scaled gradients pass through the backward kernels
+    linearly, so after unscale_ they must equal the plain gradients."""
+    import torch.nn.functional as Fn
+    video = fx.make_inputs("tiny")["video"].to(cuda)
+    labels = torch.tensor([2, 0], device=cuda)
+    plain, _, _ = build_model("tiny", device=cuda)
+    plain.train()
+    Fn.cross_entropy(plain(video)[0], labels).backward()
+    amp, _, _ = build_model("tiny", device=cuda)
+    amp.train()
+    opt = torch.optim.AdamW([p for p in amp.parameters() if p.requires_grad], lr=1e-3)
+    # init_scale 2^10: the default 2^16 overflows the fp16 head gradients on the first steps (ordinary AMP behaviour: the
+    # scaler then skips the step and backs off), which would make this comparison meaningless
+    scaler = torch.amp.GradScaler("cuda", enabled=True, init_scale=2.0 ** 10)
+    with torch.autocast("cuda", dtype=torch.float16):
+        logits = amp(video)[0]
+        loss = Fn.cross_entropy(logits.float(), labels)
+    scaler.scale(loss).backward()
+    scaler.unscale_(opt)
+    pp, pa = dict(plain.named_parameters()), dict(amp.named_parameters())
+    for n in ("visual.global_prompts", "visual.time_embed", "visual.blocks.0.local_prompts", "prompt_learner.ctx"):
+        assert torch.isfinite(pa[n].grad).all(), n
+        assert rel_l2(pa[n].grad, pp[n].grad) < 3e-2 and _cos(pa[n].grad, pp[n].grad) > 0.999, n
+    scaler.step(opt)
+    scaler.update()
+    assert all(torch.isfinite(p).all() for p in amp.parameters())
