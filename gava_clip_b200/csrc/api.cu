@@ -109,6 +109,10 @@ int gava_split_bf16_fwd(const float* x, int64_t in_row_stride, void* hi, void* l
   return split_bf16(x, in_row_stride, hi, lo, out_row_stride, rows, D, (cudaStream_t)stream);
 }
 
+int gava_split3_bf16_fwd(const float* x, int64_t in_row_stride, void* out, int64_t rows, int32_t D, void* stream) {
+  return split3_bf16(x, in_row_stride, out, rows, D, (cudaStream_t)stream);
+}
+
 int gava_patch_gather_split_fwd(const float* video, void* hi, void* lo, int32_t B, int32_t T, int32_t H, int32_t W,
                                 int32_t P, int32_t Kpad, void* stream) {
   return patch_gather_split(video, hi, lo, B, T, H, W, P, Kpad, (cudaStream_t)stream);

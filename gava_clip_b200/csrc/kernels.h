@@ -61,6 +61,7 @@ int head(const float* frame_feat, const float* summary_tok, const float* text_ha
 // ---- fp32-accuracy path (precise.cu)
 int split_bf16(const float* x, long long in_row_stride, void* hi, void* lo, long long out_row_stride, long long rows,
                int D, cudaStream_t stream);
+int split3_bf16(const float* x, long long in_row_stride, void* out, long long rows, int D, cudaStream_t stream);
 int patch_gather_split(const float* video, void* hi, void* lo, int B, int T, int H, int W, int P, int Kpad,
                        cudaStream_t stream);
 int embed_assemble(const float* tmp, float* x, const float* pos, const float* time_embed, int BT, int T, int Np, int D,

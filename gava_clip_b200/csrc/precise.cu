@@ -13,7 +13,8 @@ namespace gava {
 // ---------------------------------------------------------------- split: fp32 rows -> hi / lo bf16 rows
 __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, long long in_stride,
                                                          __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                                         long long out_stride, long long rows, int d4n) {
+                                                         __nv_bfloat16* __restrict__ hi2, long long out_stride,
+                                                         long long rows, int d4n) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * d4n) return;
   const long long r = idx / d4n;
@@ -27,6 +28,18 @@ __global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict
   ol.y = pack_bf16x2(v.z - __bfloat162float(h2), v.w - __bfloat162float(h3));
   *reinterpret_cast<uint2*>(hi + r * out_stride + 4 * d4) = oh;
   *reinterpret_cast<uint2*>(lo + r * out_stride + 4 * d4) = ol;
+  if (hi2 != nullptr) *reinterpret_cast<uint2*>(hi2 + r * out_stride + 4 * d4) = oh;
+}
+
+// out[r, :] = [hi | lo | hi] (3D wide): with weights packed as [w_hi | w_hi | w_lo] along K, ONE GEMM with K' = 3D evaluates
+// the 3-term product a_hi w_hi + a_lo w_hi + a_hi w_lo (used where launches, not bytes, are the cost: the text side)
+int split3_bf16(const float* x, long long in_row_stride, void* out, long long rows, int D, cudaStream_t stream) {
+  if (!x || !out || rows < 0 || D <= 0 || (D & 3) || (in_row_stride & 3)) { set_error("split3_bf16: bad arguments"); return GAVA_ERR_ARG; }
+  if (rows == 0) return GAVA_OK;
+  const long long total = rows * (D / 4);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  split_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, in_row_stride, o, o + D, o + 2 * D, 3LL * D, rows, D / 4);
+  return check_launch("split3_bf16");
 }
 
 int split_bf16(const float* x, long long in_row_stride, void* hi, void* lo, long long out_row_stride, long long rows,
@@ -38,7 +51,7 @@ int split_bf16(const float* x, long long in_row_stride, void* hi, void* lo, long
   if (rows == 0) return GAVA_OK;
   const long long total = rows * (D / 4);
   split_bf16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-      x, in_row_stride, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), out_row_stride, rows, D / 4);
+      x, in_row_stride, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), nullptr, out_row_stride, rows, D / 4);
   return check_launch("split_bf16");
 }
 

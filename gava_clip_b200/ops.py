@@ -224,6 +224,25 @@ def split_bf16(x: Tensor, hi: Tensor, lo: Tensor, *, rows: int, D: int, in_row_s
     _lib.check(rc, "gava_split_bf16_fwd")
 
 
+def split3_bf16(x: Tensor, out: Tensor, *, rows: int, D: int, in_row_stride: Optional[int] = None) -> Tensor:
+    """out[r] = [hi | lo | hi] of x[r] (bf16, 3D wide): the A operand of a K-concatenated 3-term product (see pack3)."""
+    _req(x, torch.float32, "split3 x"); _req(out, torch.bfloat16, "split3 out")
+    in_row_stride = D if in_row_stride is None else in_row_stride
+    assert out.is_contiguous() and out.numel() >= rows * 3 * D and x.numel() >= (rows - 1) * in_row_stride + D
+    rc = _lib.load().gava_split3_bf16_fwd(x.data_ptr(), in_row_stride, out.data_ptr(), rows, D, _stream())
+    _lib.check(rc, "gava_split3_bf16_fwd")
+    return out
+
+
+def pack3(w32: Tensor) -> Tensor:
+    """[w_hi | w_hi | w_lo] along K (bf16 [N, 3K]): the weight operand matching split3_bf16's [hi | lo | hi] rows, so that
+    A' @ W'^T = a_hi w_hi + a_lo w_hi + a_hi w_lo (the a_lo w_lo term, ~2^-18 relative, is dropped as in gemm3)."""
+    w32 = w32.detach().float().contiguous()
+    hi = w32.to(torch.bfloat16)
+    lo = (w32 - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, hi, lo], dim=1).contiguous()
+
+
 def patch_gather_split(video: Tensor, hi: Tensor, lo: Tensor, patch: int) -> None:
     _req(video, torch.float32, "patch_gather_split video"); _req(hi, torch.bfloat16, "hi"); _req(lo, torch.bfloat16, "lo")
     assert video.is_contiguous() and hi.is_contiguous() and lo.is_contiguous() and hi.shape == lo.shape

@@ -46,10 +46,8 @@ class TextTrainer:
         bf = lambda w: w.detach().to(dev, torch.bfloat16).contiguous()
         bft = lambda w: w.detach().t().to(dev, torch.bfloat16).contiguous()
 
-        def pair(w):      # w = hi + lo up to 2^-17: operands of the 3-term forward products
-            w = w.detach().to(dev, torch.float32).contiguous()
-            hi = w.to(torch.bfloat16)
-            return hi, (w - hi.float()).to(torch.bfloat16)
+        def pair(w):      # [w_hi | w_hi | w_lo] along K: operand of the K-concatenated 3-term forward products
+            return ops.pack3(w.detach().to(dev, torch.float32))
 
         f32 = lambda v: v.detach().to(dev, torch.float32).contiguous()
         Wd, E = t.text_projection.shape
@@ -78,7 +76,7 @@ class TextTrainer:
             return self.ws[key]
         t, dev = self.textual, self.device
         Wd = t.text_projection.shape[0]
-        Ep = self.P["proj.wT"][0].shape[0]
+        Ep = self.P["proj.wT"].shape[0]
         nl = len(t.transformer.resblocks)
         M = R * L
         bf, f32 = torch.bfloat16, torch.float32
@@ -86,7 +84,7 @@ class TextTrainer:
         W = {"x_in": [z(M, Wd, dt=f32) for _ in range(nl + 1)], "x_mid": [z(M, Wd, dt=f32) for _ in range(nl)],
              "qkv": [z(M, 3 * Wd, dt=f32) for _ in range(nl)], "a1": [z(M, 4 * Wd, dt=bf) for _ in range(nl)],
              "tn": z(M, Wd, dt=f32), "att": z(M, Wd, dt=f32), "h": z(M, 4 * Wd, dt=f32),
-             "hi": z(M * 4 * Wd, dt=bf), "lo": z(M * 4 * Wd, dt=bf),
+             "a3": z(M * 12 * Wd, dt=bf),
              "rows": z(R, Wd, dt=f32), "rn": z(R, Wd, dt=f32), "feat": z(R, Ep, dt=f32),
              "dx": z(M, Wd, dt=f32), "dxb": z(M, Wd, dt=bf), "g4": z(M, 4 * Wd, dt=bf), "gD": z(M, Wd, dt=bf),
              "dqkv": z(M, 3 * Wd, dt=bf), "dfeat": z(R, Ep, dt=f32), "dfeat_bf": z(R, Ep, dt=bf), "drn": z(R, Wd, dt=bf),
@@ -107,11 +105,14 @@ class TextTrainer:
         M = R * L
         torch.add(W["prompts_in"], W["pos_rep"], out=W["x_in"][0])                          # :157 (memory plumbing)
 
-        def mm(a32: Tensor, rows: int, K: int, w, out: Tensor, bias=None, resid=None) -> None:
-            """out(f32) = [resid +] a32 @ (w_hi + w_lo)^T + bias as a 3-term split-bf16 product."""
-            ah, al = W["hi"][: rows * K].view(rows, K), W["lo"][: rows * K].view(rows, K)
-            ops.split_bf16(a32, ah, al, rows=rows, D=K)
-            ops.gemm3(ah, al, w[0], w[1], out, bias=bias, resid=resid)
+        def mm(a32: Tensor, rows: int, K: int, w: Tensor, out: Tensor, bias=None, resid=None) -> None:
+            """out(f32) = [resid +] a32 @ (w_hi + w_lo)^T + bias as a 3-term split-bf16 product in ONE GEMM (K' = 3K)."""
+            a3 = W["a3"][: rows * 3 * K].view(rows, 3 * K)
+            ops.split3_bf16(a32, a3, rows=rows, D=K)
+            if resid is not None:
+                ops.gemm(a3, w, out, mode=ops.EPI_BIAS_RESID_F32, bias=bias, resid=resid)
+            else:
+                ops.gemm(a3, w, out, mode=ops.EPI_BIAS_F32, bias=bias)
 
         for i, b in enumerate(P["blocks"]):
             xin, xmid, xnext = W["x_in"][i], W["x_mid"][i], W["x_in"][i + 1]

@@ -147,6 +147,11 @@ int gava_head_fwd(const float* frame_feat, const float* summary_tok, const float
 int gava_split_bf16_fwd(const float* x, int64_t in_row_stride, void* hi, void* lo, int64_t out_row_stride, int64_t rows,
                         int32_t D, void* stream);
 
+/* out[r, :] = [hi | lo | hi] (bf16, 3D wide, contiguous rows): with a weight packed as [w_hi | w_hi | w_lo] along K, a single
+ * gava_gemm_bf16_fwd with K' = 3D evaluates the same 3-term product (one launch instead of three; used on the text side,
+ * where rows are few and launches are the cost). */
+int gava_split3_bf16_fwd(const float* x, int64_t in_row_stride, void* out, int64_t rows, int32_t D, void* stream);
+
 /* gava_patch_gather_fwd with a hi/lo bf16 pair as output (same row/column layout). */
 int gava_patch_gather_split_fwd(const float* video, void* hi, void* lo, int32_t B, int32_t T, int32_t H, int32_t W,
                                 int32_t P, int32_t Kpad, void* stream);
