@@ -54,6 +54,7 @@ SIGNATURES = {
     "gava_version": [],
     "gava_last_error_string": [],
     "gava_init": [],
+    "gava_workspace_bytes": [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32],
     "gava_gemm_bf16_fwd": [_p, _i64, _p, _i64, _i64, _i64, _i64, C.POINTER(GemmEpilogue), _p],
     "gava_layernorm_fwd": [_p, _i64, _p, _p, _p, _i64, _i32, _i64, _i32, _f32, _p],
     "gava_layernorm_resid_fwd": [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i32, _i64, _i32, _f32, _p],
@@ -85,7 +86,7 @@ SIGNATURES = {
                                C.POINTER(C.c_float), C.POINTER(C.c_float), _p],
     "gava_adamw_step": [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _p],
 }
-_RESTYPES = {"gava_last_error_string": C.c_char_p}
+_RESTYPES = {"gava_last_error_string": C.c_char_p, "gava_workspace_bytes": C.c_int64}
 
 _lib = None
 

@@ -44,6 +44,31 @@ int gava_init(void) {
   return GAVA_OK;
 }
 
+int64_t gava_workspace_bytes(int32_t B, int32_t T, int32_t N0, int32_t D, int32_t Dm, int32_t G, int32_t Kpad, int32_t Epad,
+                             int32_t train_layers) {
+  // mirror of TowerEngine.workspace / TowerTrainer.train_ws (vision_encoder.py, train_engine.py): what a caller has to
+  // allocate for one clip shape.  Sizes in bytes; bf16 = 2, f32 = 4.
+  if (B <= 0 || T <= 0 || N0 <= 1 || D <= 0 || Dm <= 0 || G < 0 || Kpad <= 0 || Epad <= 0 || train_layers < 0) return -1;
+  const int64_t BT = (int64_t)B * T, M = BT * N0, R = G + 2 * BT;
+  int64_t infer = 0;
+  infer += BT * (N0 - 1) * Kpad * 2;            // patches
+  infer += M * D * 4 + M * D * 2 * 2;           // x, xn, delta
+  infer += M * 3 * D * 2 + M * Dm * 2;          // qkv, h
+  infer += BT * D * (2 + 2 + 4 + 4 + 2 + 2 + 4) + BT * 3 * D * 2;   // cls_bf, cls_bf2, cls_proj, x_cls, sum_n, smix, summary, sqkv
+  infer += R * D * 2 + R * 2 * D * 2;           // aux_n, kvaux
+  infer += BT * Epad * 4;                       // frame_feat
+  if (train_layers == 0) return infer;
+  const int64_t L = train_layers;
+  int64_t tape = M * D * 4;                                                     // x0_pre
+  tape += L * (M * D * 4) + (L - 1) * (M * D * 4);                              // x_in, x_mid
+  tape += L * (M * 3 * D * 2 + R * 2 * D * 2 + M * D * 2 + BT * (D / 64) * N0 * 4);   // qkv, kvaux, o, lse
+  tape += (L - 1) * (M * Dm * 2);                                               // a1
+  tape += L * (BT * D * (4 + 4 + 2 + 2) + BT * 3 * D * 2);                      // cls_proj, summary, sum_n, smix, sqkv
+  int64_t scratch = M * D * 4 + M * D * 2 * 2 + M * Dm * 2 + M * 3 * D * 2;     // dx, dxb, gD, g4, dqkv
+  scratch += R * 2 * D * (4 + 2) + R * D * 2 + BT * (D / 64) * (G + T + 1) * 128 * 4;  // dkvaux (+bf16), daux_n, slots
+  return infer + tape + scratch;
+}
+
 int gava_gemm_bf16_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
                        const gava_gemm_epilogue* epi, void* stream) {
   return gemm_bf16(A, lda, W, ldw, M, N, K, epi, (cudaStream_t)stream);

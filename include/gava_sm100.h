@@ -66,6 +66,13 @@ const char* gava_last_error_string(void);
 /* one-time per-process setup (kernel attributes); optional, every entry point self-initialises */
 int gava_init(void);
 
+/* Bytes of caller-owned workspace one clip shape needs (the library itself never allocates): B clips of T frames, N0 live
+ * tokens per frame (cls + patches), width D, MLP width Dm, G global prompts, patch-row pitch Kpad, projected width Epad.
+ * train_layers == 0: inference buffers only; > 0: plus the activation tape and backward scratch of a fine-tune step over
+ * that many blocks.  Returns -1 on invalid arguments.  (Sizing aid: mirrors TowerEngine.workspace / TowerTrainer.train_ws.) */
+int64_t gava_workspace_bytes(int32_t B, int32_t T, int32_t N0, int32_t D, int32_t Dm, int32_t G, int32_t Kpad, int32_t Epad,
+                             int32_t train_layers);
+
 /* C[M,N] = A[M,K] * W[N,K]^T with a fused epilogue.  A: bf16 [M,K] pitch lda; W: bf16 [N,K] pitch ldw
  * (nn.Linear weight layout).  tcgen05.mma / TMEM accumulators / TMA operand loads.
  * Needs K % 64 == 0, N % 128 == 0, 16-byte aligned pointers and pitches.

@@ -39,3 +39,15 @@ def test_no_oracle_in_product():
     for p in pathlib.Path(f"{ROOT}/gava_clip_b200").rglob("*.py"):
         src = p.read_text()
         assert "import oracle" not in src and "from oracle" not in src, p
+
+
+def test_workspace_bytes_matches_design_numbers():
+    """gava_workspace_bytes is pure host arithmetic: config 2 (B=64, T=8, ViT-B/16) needs ~1.9 GB for inference (+ clip and weights) and
+    ~1.9 GB of tape per block for a fine-tune step."""
+    from gava_clip_b200 import _lib
+    lib = _lib.load()
+    infer = lib.gava_workspace_bytes(64, 8, 197, 768, 3072, 8, 768, 512, 0)
+    train = lib.gava_workspace_bytes(64, 8, 197, 768, 3072, 8, 768, 512, 12)
+    assert 1.7e9 < infer < 2.1e9
+    assert 20e9 < train - infer < 30e9
+    assert lib.gava_workspace_bytes(0, 8, 197, 768, 3072, 8, 768, 512, 0) == -1
