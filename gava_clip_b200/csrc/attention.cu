@@ -177,6 +177,111 @@ __global__ void __launch_bounds__(128, 3) attention_kernel(const AttnArgs p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Single-query attention (n_q == 1): the last block only needs the cls row of every frame (vision_encoder.py:126), i.e. one
+// query against the frame's ~214 keys per (frame, head) -- 110 KB of K/V traffic for 55 kFLOP.  The tensor-core kernels
+// above still stage whole 128-row query tiles for it (178 us at config 2); this one is a plain bandwidth kernel: one warp per
+// (frame, head), lanes over keys for the scores (each lane reads whole 128-byte K rows), lanes over channels for P V.
+__global__ void __launch_bounds__(256) attention_q1_kernel(const AttnArgs p) {
+  __shared__ float s_sc[8][320];   // scores / probabilities of the warp's item (S <= 320)
+  const int wid = threadIdx.x >> 5;
+  const int item = blockIdx.x * 8 + wid;
+  if (item >= p.BT * p.H) return;
+  const int f = item / p.H, h = item - f * p.H;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane >> 3, ch = lane & 7;   // 4 key rows per step, 8 lanes (16 bytes each) per 128-byte row
+  const int D = p.H * 64;
+  const long long ldq = 3LL * D, lda = 2LL * D;
+  const int b = f / p.T;
+  float* sc = s_sc[wid];
+  // this lane's 8 channels of the query row (cls) of the frame / head
+  float q[8];
+  {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p.qkv + (long long)f * p.N0 * ldq + h * 64) + ch);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+      q[2 * j] = __bfloat162float(v.x); q[2 * j + 1] = __bfloat162float(v.y);
+    }
+  }
+  auto key_ptr = [&](int row) -> const __nv_bfloat16* {
+    if (row < p.N0) return p.qkv + ((long long)f * p.N0 + row) * ldq + D + h * 64;
+    const int a = row - p.N0;
+    int arow;
+    if (a < p.G) arow = a;
+    else if (a < p.G + p.T) arow = p.G + b * p.T + (a - p.G);
+    else arow = p.G + p.BT + f;
+    return p.kv_aux + (long long)arow * lda + h * 64;
+  };
+  const float scale_log2 = 0.125f * 1.4426950408889634f;
+  const int steps = (p.S + 3) >> 2;
+  // ---- scores: every warp instruction reads 4 whole K rows (512 contiguous-by-row bytes)
+  float mx = -INFINITY;
+#pragma unroll 4
+  for (int st = 0; st < steps; ++st) {
+    const int row = 4 * st + sub;
+    float d = 0.f;
+    if (row < p.S) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(key_ptr(row)) + ch);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+        d += __bfloat162float(v.x) * q[2 * j] + __bfloat162float(v.y) * q[2 * j + 1];
+      }
+    }
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 4);
+    const float v = (row < p.S) ? d * scale_log2 : -INFINITY;
+    if (ch == 0 && row < p.S) sc[row] = v;
+    mx = fmaxf(mx, v);
+  }
+  mx = warp_max(mx);
+  __syncwarp();
+  float sum = 0.f;
+  for (int r = lane; r < p.S; r += 32) {
+    const float e = exp2f(sc[r] - mx);
+    sc[r] = e;
+    sum += e;
+  }
+  sum = warp_sum(sum);
+  __syncwarp();
+  // ---- O = P V with the same 4-rows-per-instruction access; the 4 row sub-groups are combined at the end
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = 0.f;
+#pragma unroll 4
+  for (int st = 0; st < steps; ++st) {
+    const int row = 4 * st + sub;
+    if (row < p.S) {
+      const float pk = sc[row];
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(key_ptr(row) + D) + ch);
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+        o[2 * j] += pk * __bfloat162float(v.x); o[2 * j + 1] += pk * __bfloat162float(v.y);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    o[j] += __shfl_xor_sync(0xffffffffu, o[j], 8);
+    o[j] += __shfl_xor_sync(0xffffffffu, o[j], 16);
+  }
+  if (sub == 0) {
+    const float inv = 1.0f / sum;
+    uint4 w;
+    w.x = pack_bf16x2(o[0] * inv, o[1] * inv); w.y = pack_bf16x2(o[2] * inv, o[3] * inv);
+    w.z = pack_bf16x2(o[4] * inv, o[5] * inv); w.w = pack_bf16x2(o[6] * inv, o[7] * inv);
+    *(reinterpret_cast<uint4*>(p.out + (long long)f * p.N0 * D + h * 64) + ch) = w;
+  }
+  if (p.lse != nullptr && lane == 0) p.lse[((long long)f * p.H + h) * p.N0] = mx + log2f(sum);
+}
+
 template <int CT>
 static int launch_attention(const AttnArgs& a, int frames, size_t smem_bytes, cudaStream_t stream) {
   static size_t attr_bytes = 0;
@@ -198,6 +303,17 @@ int attention(const void* qkv, const void* kv_aux, void* out, float* lse, int B,
   }
   // tcgen05 path for every shape inside its specialisation (G = 8, T % 8 == 0, <= 256 keys); the mma.sync kernel
   // below covers the remaining shapes (ViT-L/14: 282 keys, long clips).  GAVA_ATTN_TC=0 forces the latter (A/B tests).
+  static const bool use_q1 = [] { const char* e = getenv("GAVA_ATTN_Q1"); return !(e && e[0] == '0'); }();
+  if (use_q1 && n_q == 1 && N0 + G + T + 1 <= 320) {
+    AttnArgs a;
+    a.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
+    a.kv_aux = reinterpret_cast<const __nv_bfloat16*>(kv_aux);
+    a.out = reinterpret_cast<__nv_bfloat16*>(out);
+    a.lse = lse;
+    a.T = T; a.N0 = N0; a.G = G; a.H = H; a.n_q = 1; a.BT = B * T; a.S = N0 + G + T + 1; a.n_chunks = 0;
+    attention_q1_kernel<<<(unsigned)((B * T * H + 7) / 8), 256, 0, stream>>>(a);
+    return check_launch("attention_q1");
+  }
   static const bool use_tc = [] { const char* e = getenv("GAVA_ATTN_TC"); return !(e && e[0] == '0'); }();
   if (use_tc && G == 8 && (T % 8) == 0 && ((N0 + 7) / 8 * 8 + 16 + T) <= 256) return attention_tc(qkv, kv_aux, out, lse, B, T, N0, G, H, n_q, stream);
   AttnArgs a;

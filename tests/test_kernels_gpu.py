@@ -214,10 +214,10 @@ def test_attention(cuda, T, N0, H):
     assert _rel(out.float(), ref) < 1.5e-2   # P is rounded to bf16 before PV
 
 
-def test_attention_cls_only(cuda):
+@pytest.mark.parametrize("B,T,N0,G,H", [(2, 8, 197, 8, 12), (1, 70, 197, 8, 2), (3, 3, 17, 8, 2), (1, 16, 257, 8, 16)])
+def test_attention_cls_only(cuda, B, T, N0, G, H):
     from gava_clip_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(5)
-    B, T, N0, G, H = 2, 8, 197, 8, 12
     D = H * 64
     qkv = torch.randn(B * T * N0, 3 * D, device=cuda, generator=g).bfloat16()
     kv_aux = torch.randn(G + 2 * B * T, 2 * D, device=cuda, generator=g).bfloat16()
@@ -227,6 +227,13 @@ def test_attention_cls_only(cuda):
     o = out.float().view(B * T, N0, D)
     assert _rel(o[:, 0], ref[:, 0]) < 1.5e-2
     assert (o[:, 1:] == 0).all()
+    # the single-query kernel also saves the log-sum-exp row for the backward; must agree with the full-tile kernels
+    lse1 = torch.zeros(B * T, H, N0, device=cuda); lse_full = torch.zeros(B * T, H, N0, device=cuda)
+    out2 = torch.zeros_like(out)
+    ops.attention_train(qkv, kv_aux, out2, lse1, B=B, T=T, N0=N0, G=G, H=H, n_q=1)
+    ops.attention_train(qkv, kv_aux, torch.zeros_like(out), lse_full, B=B, T=T, N0=N0, G=G, H=H)
+    assert torch.equal(out2, out)
+    assert float((lse1[:, :, 0] - lse_full[:, :, 0]).abs().max()) < 2e-3
 
 
 @pytest.mark.parametrize("n_kv", [1, 5])
