@@ -1,18 +1,22 @@
 // Backward of the prompt-prefixed multi-head self-attention core (attention.cu / attention_tc.cu), flash-style: the score
 // matrix is never written to HBM; it is recomputed on the SM from the saved q/k/v.
 //
-// One CTA per (frame, head).  Q, dO (the frame's N0 live query rows) and K, V (N0 live rows + G global + T local + 1
-// summary row, gathered exactly as in the forward) are staged once in swizzled shared memory (cp.async).  Then
-//   phase 0: delta[q] = <dO[q], O[q]>                                    (O read once from global)
-//   phase 1: each warp owns 16-query tiles:  lse[q] (online max/sum over keys), then per 16-key tile
-//            S = QK^T, P = exp2(S - lse), dP = dO V^T, dS = P (dP - delta), dQ += dS K          -> dq  (bf16)
-//   phase 2: each warp owns 16-key tiles, loops over 16-query tiles:
-//            S^T = KQ^T, P^T, dV += P^T dO, dP^T = V dO^T, dS^T, dK += dS^T Q
-//            live key rows -> dk, dv (bf16, plain stores); K/V-only rows (global / local / summary prompts, shared by
-//            several frames) -> f32 atomics into d_kv_aux.
-// All five (seven with the recomputation) contractions run on the tensor cores (mma.sync m16n8k16 bf16, f32 accumulate).
+// One CTA per (frame, head).  Q, dO (the first n_q live query rows of the frame: all N0, or 1 in the last block) and K, V
+// (N0 live rows + G global + T local + 1 summary row, gathered exactly as in the forward) are staged once in swizzled
+// shared memory (cp.async).  Then
+//   prologue : delta[q] = <dO[q], O[q]> (O read once from global); lse[q] from the forward's saved rows, or -- without
+//              them -- an extra pass over the keys (online max/sum per 16-query tile) followed by a CTA barrier
+//   work units, dealt round-robin to the 4 warps (independent of each other once lse / delta sit in shared memory):
+//     16-query tile : per 16-key tile  S = QK^T, P = exp2(S - lse), dP = dO V^T, dS = P (dP - delta), dQ += dS K  -> dq (bf16)
+//     16-key tile   : per 16-query tile  S^T = KQ^T, P^T, dV += P^T dO, dP^T = V dO^T, dS^T, dK += dS^T Q
+//                     live key rows -> dk, dv (bf16, plain stores); K/V-only rows (global / local / summary prompts,
+//                     shared by several frames) -> this CTA's slot of `scratch`, summed in a fixed order by
+//                     attention_bwd_reduce_kernel (reproducible), or f32 atomics into d_kv_aux when scratch == NULL.
+// All seven contractions (S and dP are formed twice, once per unit type) run on the tensor cores (mma.sync m16n8k16 bf16, f32 accumulate).
 // Padding rows are zero-filled, which makes their contributions vanish without masks: K_pad = 0 => dS K_pad = 0,
 // dO_pad = 0 => P^T dO_pad = 0 and dP = delta = 0 => dS = 0.  Only the lse pass masks padded keys.
+// Measured (config 2, 6144 items of 197 x 214): 0.96 ms per launch, HMMA pipe 42 % busy; 8 warps with <= 128 registers
+// (GAVA_AB_WARPS=8) is slower (1.08 ms), see DESIGN.md.
 //
 // Restates autograd of Attention.forward core, training/VitaCLIP_vision_encoder_utils.py:71-77.
 #include "common.cuh"
