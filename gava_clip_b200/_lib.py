@@ -57,6 +57,7 @@ SIGNATURES = {
     "gava_workspace_bytes": [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32],
     "gava_gemm_bf16_fwd": [_p, _i64, _p, _i64, _i64, _i64, _i64, C.POINTER(GemmEpilogue), _p],
     "gava_layernorm_fwd": [_p, _i64, _p, _p, _p, _i64, _i32, _i64, _i32, _f32, _p],
+    "gava_layernorm2_fwd": [_p, _i64, _p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _i32, _f32, _p],
     "gava_layernorm_resid_fwd": [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i32, _i64, _i32, _f32, _p],
     "gava_patch_gather_fwd": [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p],
     "gava_patch_gather_u8_fwd": [_p, _p, _p, C.POINTER(C.c_float), C.POINTER(C.c_float), _i32, _i32, _i32, _i32, _i32, _i32, _p],

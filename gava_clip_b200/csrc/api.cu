@@ -79,6 +79,13 @@ int gava_layernorm_fwd(const float* x, int64_t in_row_stride, const float* weigh
   return layernorm(x, in_row_stride, weight, bias, out, out_row_stride, out_bf16, rows, D, eps, (cudaStream_t)stream);
 }
 
+int gava_layernorm2_fwd(const float* x, int64_t in_row_stride, const float* weight, const float* bias, float* out,
+                        int64_t out_row_stride, const float* weight2, const float* bias2, void* out2, int64_t out2_row_stride,
+                        int64_t rows, int32_t D, float eps, void* stream) {
+  return layernorm2(x, in_row_stride, weight, bias, out, out_row_stride, weight2, bias2, out2, out2_row_stride, rows, D, eps,
+                    (cudaStream_t)stream);
+}
+
 int gava_layernorm_resid_fwd(const float* x, int64_t in_row_stride, const void* delta, int64_t delta_row_stride,
                              const float* weight, const float* bias, void* out, int64_t out_row_stride, int32_t out_bf16,
                              int64_t rows, int32_t D, float eps, void* stream) {

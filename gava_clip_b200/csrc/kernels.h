@@ -28,6 +28,10 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
 int layernorm(const float* x, long long in_row_stride, const float* w, const float* b, void* out,
               long long out_row_stride, int out_bf16, long long rows, int D, float eps, cudaStream_t stream);
 
+int layernorm2(const float* x, long long in_row_stride, const float* w, const float* b, float* out, long long out_row_stride,
+               const float* w2, const float* b2, void* out2, long long out2_row_stride, long long rows, int D, float eps,
+               cudaStream_t stream);
+
 // LayerNorm(x + delta), delta bf16 (may be null)
 int layernorm_resid(const float* x, long long in_row_stride, const void* delta, long long delta_row_stride, const float* w,
                     const float* b, void* out, long long out_row_stride, int out_bf16, long long rows, int D, float eps,

@@ -12,7 +12,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const __nv_bfloat16* __restrict__ delta, long long delta_stride,
                                                         const float* __restrict__ w, const float* __restrict__ b,
                                                         void* out, long long out_stride, int out_bf16, long long rows,
-                                                        float eps) {
+                                                        float eps, const float* __restrict__ w2 = nullptr,
+                                                        const float* __restrict__ b2 = nullptr,
+                                                        __nv_bfloat16* out2 = nullptr, long long out2_stride = 0) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = lane_id();
@@ -33,6 +35,29 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   if (w != nullptr) ln_normalize<V>(v, w, b, eps);
   char* o = reinterpret_cast<char*>(out) + row * out_stride * (out_bf16 ? 2 : 4);
   store_row<V>(v, o, out_bf16);
+  if (w2 != nullptr) {   // a second LayerNorm of the values just produced (ln_pre followed by block 0's norm1): no re-read
+    ln_normalize<V>(v, w2, b2, eps);
+    store_row<V>(v, out2 + row * out2_stride, 1);
+  }
+}
+
+// out = LN(x; w, b) (f32) and out2 = LN(out; w2, b2) (bf16) in one pass over the rows
+int layernorm2(const float* x, long long in_row_stride, const float* w, const float* b, float* out, long long out_row_stride,
+               const float* w2, const float* b2, void* out2, long long out2_row_stride, long long rows, int D, float eps,
+               cudaStream_t stream) {
+  if (!x || !out || !w || !b || !w2 || !b2 || !out2 || rows < 0) { set_error("layernorm2: bad arguments"); return GAVA_ERR_ARG; }
+  if (rows == 0) return GAVA_OK;
+  if ((in_row_stride & 3) || (out_row_stride & 3) || (out2_row_stride & 3)) { set_error("layernorm2: row strides must be multiples of 4"); return GAVA_ERR_ARG; }
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(out2);
+#define GAVA_LN2_CASE(V) \
+  case 128 * V: layernorm_kernel<V><<<grid, 256, 0, stream>>>(x, in_row_stride, nullptr, 0, w, b, out, out_row_stride, 0, rows, eps, w2, b2, o2, out2_row_stride); break;
+  switch (D) {
+    GAVA_LN2_CASE(1) GAVA_LN2_CASE(2) GAVA_LN2_CASE(3) GAVA_LN2_CASE(4) GAVA_LN2_CASE(6) GAVA_LN2_CASE(8)
+    default: set_error("layernorm2: unsupported width D=%d", D); return GAVA_ERR_SHAPE;
+  }
+#undef GAVA_LN2_CASE
+  return check_launch("layernorm2");
 }
 
 int layernorm_resid(const float* x, long long in_row_stride, const void* delta, long long delta_row_stride, const float* w,

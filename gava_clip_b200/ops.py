@@ -137,6 +137,20 @@ def layernorm(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], out: 
     return out
 
 
+def layernorm2(x: Tensor, w: Tensor, b: Tensor, out: Tensor, w2: Tensor, b2: Tensor, out2: Tensor, *, rows: int,
+               eps: float = 1e-5) -> None:
+    """out (f32, may alias x) = LN(x; w, b); out2 (bf16) = LN(out; w2, b2) -- one pass over contiguous [rows, D] tensors."""
+    for t in (x, w, b, out, w2, b2):
+        _req(t, torch.float32, "layernorm2")
+    _req(out2, torch.bfloat16, "layernorm2 out2")
+    D = out.shape[-1]
+    assert x.is_contiguous() and out.is_contiguous() and out2.is_contiguous() and out2.shape[-1] == D
+    assert min(x.numel(), out.numel(), out2.numel()) >= rows * D and w.numel() == D and w2.numel() == D
+    rc = _lib.load().gava_layernorm2_fwd(x.data_ptr(), D, w.data_ptr(), b.data_ptr(), out.data_ptr(), D, w2.data_ptr(),
+                                         b2.data_ptr(), out2.data_ptr(), D, rows, D, eps, _stream())
+    _lib.check(rc, "gava_layernorm2_fwd")
+
+
 def patch_gather(video: Tensor, out: Tensor, patch: int) -> Tensor:
     """video fp32 [B,3,T,H,W] contiguous -> bf16 [B*T*gh*gw, Kpad] patch rows (conv-weight column order)."""
     _req(video, torch.float32, "patch_gather video"); _req(out, torch.bfloat16, "patch_gather out")

@@ -175,7 +175,7 @@ class TowerTrainer(TowerEngine):
         ops.gemm(W["patches"], P["patch.w"], x0, mode=ops.EPI_PATCH_F32, bias=P["patch.b"], pos=P["pos_embed"],
                  time_embed=te, group=N0 - 1, group_stride=N0, row_offset=1, T=T)
         ops.cls_rows(x0, N0, P["cls_token"], P["pos_embed"], te, BT, T)
-        ops.layernorm(x0, P["ln_pre.w"], P["ln_pre.b"], W["x_in"][0], rows=M, in_row_stride=D)
+        ops.layernorm2(x0, P["ln_pre.w"], P["ln_pre.b"], W["x_in"][0], P["b0.norm1.w"], P["b0.norm1.b"], xn, rows=M)
 
         L = len(e.blocks)
         for i in range(L):
@@ -193,8 +193,9 @@ class TowerTrainer(TowerEngine):
             ops.prompt_rows(P["global_prompts"][i], P[k + "local"], cp, sm, P[k + "norm1.w"], P[k + "norm1.b"], W["aux_n"],
                             B, T, LN_EPS)
             ops.gemm(W["aux_n"], P[k + "qkv.w"][D:], W["kvaux"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:])
-            # x = x + attn(norm1(x))   (utils.py:190-191)
-            ops.layernorm(xin, P[k + "norm1.w"], P[k + "norm1.b"], xn, rows=M, in_row_stride=D)
+            # x = x + attn(norm1(x))   (utils.py:190-191); block 0's norm1 came out of the ln_pre pass
+            if i > 0:
+                ops.layernorm(xin, P[k + "norm1.w"], P[k + "norm1.b"], xn, rows=M, in_row_stride=D)
             if i == L - 1:
                 # Last layer: only the cls row of each frame reaches the output, so -- exactly as in the inference
                 # schedule -- K/V are projected for all rows, Q / attention query / out-proj / MLP for the cls rows alone.

@@ -401,12 +401,13 @@ class TowerEngine:
         ops.gemm(W["patches"], P["patch.w"], x, mode=ops.EPI_PATCH_F32, bias=P["patch.b"], pos=P["pos_embed"],
                  time_embed=te, group=N0 - 1, group_stride=N0, row_offset=1, T=T)
         ops.cls_rows(x, N0, P["cls_token"], P["pos_embed"], te, BT, T)
-        ops.layernorm(x, P["ln_pre.w"], P["ln_pre.b"], x, rows=M, in_row_stride=D)
+        # ln_pre and block 0's norm1 in one pass (the second LayerNorm works on the values still in registers)
+        ops.layernorm2(x, P["ln_pre.w"], P["ln_pre.b"], x, P["b0.norm1.w"], P["b0.norm1.b"], xn, rows=M)
 
         L = len(e.blocks)
         main = torch.cuda.current_stream(self.device)
         side = self.side_stream if self.overlap_chain else None
-        norm1_done = False      # True when the previous block's fc2 already produced norm1(x) in xn (LayerNorm tail)
+        norm1_done = True       # True when xn already holds norm1(x) of the coming block (here; or the fc2 LayerNorm tail)
         for i in range(L):
             k = f"b{i}."
             # ---- temporal message: cls_proj -> summary attention -> K/V-only prompt rows   utils.py:160-188

@@ -88,6 +88,12 @@ int gava_gemm_bf16_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, i
 int gava_layernorm_fwd(const float* x, int64_t in_row_stride, const float* weight, const float* bias, void* out,
                        int64_t out_row_stride, int32_t out_bf16, int64_t rows, int32_t D, float eps, void* stream);
 
+/* Two consecutive LayerNorms in one pass: out (f32, may alias x) = LN(x; weight, bias), out2 (bf16) = LN(out; weight2,
+ * bias2).  ln_pre followed by block 0's norm1, VitaCLIP_vision_encoder.py:113 + ..._utils.py:190. */
+int gava_layernorm2_fwd(const float* x, int64_t in_row_stride, const float* weight, const float* bias, float* out,
+                        int64_t out_row_stride, const float* weight2, const float* bias2, void* out2, int64_t out2_row_stride,
+                        int64_t rows, int32_t D, float eps, void* stream);
+
 /* gava_layernorm_fwd of (x + delta): delta is a bf16 [rows, D] tensor (row pitch delta_row_stride) holding a residual branch
  * that was not yet added to the f32 stream -- `x + attn(...)` of VitaCLIP_vision_encoder_utils.py:191 with the out_proj result
  * kept in bf16; the MLP's fc2 epilogue later adds the same delta (gava_gemm_bf16_fwd, RESID mode with `aux`). */

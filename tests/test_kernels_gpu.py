@@ -389,3 +389,17 @@ def test_gemm_resid_with_layernorm_tail(cuda, M, N, K):
     assert torch.isfinite(xn.float()).all()
     assert _rel(xn.float(), ref) < 1e-2
     assert torch.equal(xn, ref.bfloat16()) or float((xn.float() - ref).abs().max()) < 0.05
+
+
+def test_layernorm2_two_stage(cuda):
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(31)
+    M, D = 1000, 768
+    x = torch.randn(M, D, device=cuda, generator=g) * 3 + 1
+    w1, b1, w2, b2 = (torch.randn(D, device=cuda, generator=g) for _ in range(4))
+    ref1 = F.layer_norm(x, (D,), w1, b1, 1e-5)
+    ref2 = F.layer_norm(ref1, (D,), w2, b2, 1e-5)
+    out2 = torch.empty(M, D, device=cuda, dtype=torch.bfloat16)
+    ops.layernorm2(x, w1, b1, x, w2, b2, out2, rows=M)          # in place for the f32 output, as the engine uses it
+    assert _rel(x, ref1) < 1e-5
+    assert _rel(out2.float(), ref2) < 1e-2
