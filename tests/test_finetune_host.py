@@ -78,3 +78,45 @@ def test_two_rank_bucketed_gradient_allreduce():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert ret.get(0) is True and ret.get(1) is True
+
+
+def test_tower_gradient_layout_covers_trainable_set():
+    """TowerTrainer's flat gradient buffer (host logic, no kernels): one view per trainable tower parameter of the
+    reference's recipe (VitaCLIP_model.py:230-235), right shapes, no overlap, per-layer slices contiguous (the all-reduce
+    units), q|k|v of a summary attention adjacent (one wgrad GEMM fills all three)."""
+    from tests.util import build_model
+    from gava_clip_b200.train_engine import TowerTrainer, is_trainable_name
+    model, kw, _ = build_model("tiny")
+    enc = model.visual
+    eng = TowerTrainer(enc, torch.device("cpu"))
+    eng._alloc_grads()
+    named = eng.trainable_named()
+    assert [n for n, _ in named] == [n for n, p in enc.named_parameters() if p.requires_grad]
+    assert all(is_trainable_name(n) for n, _ in named)
+    base, end = eng.grad_flat.data_ptr(), eng.grad_flat.data_ptr() + eng.grad_flat.numel() * 4
+    spans = []
+    for n, p in named:
+        g = eng.grads[n]
+        assert g.numel() == p.numel() and g.view_as(p).shape == p.shape, n
+        assert g.is_contiguous() and base <= g.data_ptr() and g.data_ptr() + g.numel() * 4 <= end, n
+        spans.append((g.data_ptr(), g.data_ptr() + g.numel() * 4))
+    spans.sort()
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))                    # disjoint
+    assert sum(e - s for s, e in spans) == eng.grad_flat.numel() * 4                 # and they tile the whole buffer
+    L, D = len(enc.blocks), enc.feature_dim
+    assert len(eng.layer_slices) == L
+    per_layer = sum(p.numel() for n, p in named if n.startswith("blocks.0."))
+    assert all(s.numel() == per_layer and s.is_contiguous() for s in eng.layer_slices)
+    assert eng.head_slice.numel() == enc.time_embed.numel() + enc.global_prompts.numel()
+    assert eng.head_slice.numel() + L * per_layer == eng.grad_flat.numel()
+    w = eng.grads["blocks.0.sqkv.weight"]
+    for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
+        v = eng.grads[f"blocks.0.summary_attn_layer.{nm}.weight"]
+        assert v.data_ptr() == w.data_ptr() + j * D * D * 4
+    # a backbone weight that requires grad has no backward kernel: refused loudly
+    enc.blocks[0].mlp.fc1.weight.requires_grad_(True)
+    try:
+        eng.check_trainable()
+        raise AssertionError("expected NotImplementedError")
+    except NotImplementedError:
+        pass
