@@ -301,8 +301,9 @@ int attention(const void* qkv, const void* kv_aux, void* out, float* lse, int B,
     set_error("attention: bad arguments");
     return GAVA_ERR_ARG;
   }
-  // tcgen05 path for every shape inside its specialisation (G = 8, T % 8 == 0, <= 256 keys); the mma.sync kernel
-  // below covers the remaining shapes (ViT-L/14: 282 keys, long clips).  GAVA_ATTN_TC=0 forces the latter (A/B tests).
+  // tcgen05 path for every shape inside its specialisation (G = 8, <= 320 smem key rows: all BASELINE configs incl.
+  // ViT-L/14 T=16 and the 70-frame recipe); the mma.sync kernel below covers what is left (other G, longer clips).
+  // GAVA_ATTN_TC=0 forces the latter (A/B tests).
   static const bool use_q1 = [] { const char* e = getenv("GAVA_ATTN_Q1"); return !(e && e[0] == '0'); }();
   if (use_q1 && n_q == 1 && N0 + G + T + 1 <= 320) {
     AttnArgs a;
@@ -315,7 +316,7 @@ int attention(const void* qkv, const void* kv_aux, void* out, float* lse, int B,
     return check_launch("attention_q1");
   }
   static const bool use_tc = [] { const char* e = getenv("GAVA_ATTN_TC"); return !(e && e[0] == '0'); }();
-  if (use_tc && G == 8 && (T % 8) == 0 && ((N0 + 7) / 8 * 8 + 16 + T) <= 256) return attention_tc(qkv, kv_aux, out, lse, B, T, N0, G, H, n_q, stream);
+  if (use_tc && attention_tc_keys(T, N0, G) != 0 && n_q <= 384) return attention_tc(qkv, kv_aux, out, lse, B, T, N0, G, H, n_q, stream);
   AttnArgs a;
   a.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
   a.kv_aux = reinterpret_cast<const __nv_bfloat16*>(kv_aux);

@@ -53,7 +53,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// spin with a deadline: out of line so that every wait site costs a try_wait + a predicated call, not ~40 instructions
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
 #if GAVA_BOUNDED_WAIT
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
@@ -66,6 +67,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 #endif
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
 // ----------------------------------------------------------------------------- TMA
@@ -81,6 +85,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(x), "r"(y)
       : "memory");
 }
+
+// 3-D tiled store shared -> global (bulk async group); out-of-bounds parts of the box are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int32_t x, int32_t y, int32_t z) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(x), "r"(y), "r"(z)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING shared memory (the source may be reused)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {  // whole warp

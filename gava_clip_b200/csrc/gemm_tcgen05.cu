@@ -640,6 +640,27 @@ int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long co
   return GAVA_OK;
 }
 
+// 3-D bf16 [planes, rows, cols] (row pitch ld, plane pitch ld_plane elements); box = [1, box_rows, 64 cols], 128B swizzle.
+// Used for TMA STORES of per-frame tiles: rows beyond `rows` are clipped instead of spilling into the next plane.
+int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, long long planes, long long rows, long long cols, long long ld,
+                      long long ld_plane, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return GAVA_ERR_DRIVER; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || ((ld * 2) & 15) || ((ld_plane * 2) & 15)) {
+    set_error("TMA operand must be 16-byte aligned (ptr %p, ld %lld, plane %lld)", ptr, ld, ld_plane);
+    return GAVA_ERR_ARG;
+  }
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld_plane * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(3d) failed (%d)", (int)r); return GAVA_ERR_DRIVER; }
+  return GAVA_OK;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -22,6 +22,9 @@ int num_sms();
 // 2-D bf16 row-major [rows, cols] (row pitch ld elements) TMA map, box = [box_rows, 64 cols], 128-byte swizzle
 int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows);
 
+int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, long long planes, long long rows, long long cols, long long ld,
+                      long long ld_plane, int box_rows);
+
 int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long long M, long long N, long long K,
               const gava_gemm_epilogue* epi, cudaStream_t stream);
 
@@ -53,6 +56,7 @@ int prompt_rows(const float* global_prompts, const float* local_prompts, const f
                 float eps, cudaStream_t stream);
 
 // tcgen05/TMEM/TMA attention (attention_tc.cu); returns GAVA_ERR_SHAPE when the shape is outside its specialisation
+int attention_tc_keys(int T, int N0, int G);   // smem key rows needed; 0 = outside the specialisation
 int attention_tc(const void* qkv, const void* kv_aux, void* out, float* lse, int B, int T, int N0, int G, int H, int n_q,
                  cudaStream_t stream);
 

@@ -119,6 +119,9 @@ class FineTuner:
         self.loss_fn = loss_fn
         self.step_count = 0
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        # False = skip every gradient all-reduce (ranks then diverge): only for measuring how much NCCL time a step
+        # leaves exposed (bench.py) and for comparing the overlapped reduction with a plain one
+        self.communicate = True
 
     # ---- per-layer overlap: the tower backward calls this as soon as a contiguous slice of its gradient buffer is final
     def _tower_slice_ready(self, grad_slice: Tensor):
@@ -140,7 +143,7 @@ class FineTuner:
         micro-batch with loss_scale = 1 / batch_split); returns the un-scaled loss."""
         self.model.train()
         eng = self.model.visual.engine(video.device)
-        eng.grad_ready_hook = self._tower_slice_ready if self.world > 1 else None
+        eng.grad_ready_hook = self._tower_slice_ready if (self.world > 1 and self.communicate) else None
         tf32_prev = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = tf32_prev or self.text_tf32
         try:
@@ -161,12 +164,21 @@ class FineTuner:
     def reduce_gradients(self) -> None:
         """Tower gradients were already SUM-reduced slice by slice inside backward (before autograd added them into the
         flat buffer); reduce the rest: text side, logit_scale, memory / NTE heads."""
-        if self.world == 1:
+        if self.world == 1 or not self.communicate:
             return
         if self._n_tower < self.flat_g.numel():
             allreduce_flat(self.flat_g[self._n_tower:], self.group)
 
+    def _check_param_aliasing(self) -> None:
+        lo = self.flat_p.data_ptr()
+        hi = lo + self.flat_p.numel() * 4
+        for p in self.params:
+            if not (lo <= p.data_ptr() < hi):
+                raise RuntimeError("a trainable parameter no longer lives in FineTuner's flat buffer (model.to()/.float()/"
+                                   ".half() after FineTuner(...) re-allocates parameters): build the FineTuner last")
+
     def optimizer_step(self) -> None:
+        self._check_param_aliasing()
         self.step_count += 1
         lr = self.lr_schedule(self.step_count) if self.lr_schedule is not None else self.lr
         ops.adamw_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, lr=lr, beta1=self.betas[0],
@@ -175,6 +187,46 @@ class FineTuner:
         # the flat kernel writes the parameters' storage directly: bump their version counters so packed bf16 copies and
         # cached text features are refreshed on the next forward
         torch.autograd.graph.increment_version(self.params)
+
+    # ---- checkpointing: same layout as torch.optim.AdamW.state_dict() over `self.params` (one param group), so the
+    # reference's checkpoint.save_checkpoint / resume_from_checkpoint (optimizer.state_dict() / load_state_dict()) and
+    # checkpoints written with torch.optim.AdamW interoperate
+    def state_dict(self) -> Dict:
+        state, off = {}, 0
+        for i, p in enumerate(self.params):
+            n = p.numel()
+            state[i] = {"step": torch.tensor(float(self.step_count)),
+                        "exp_avg": self.exp_avg[off: off + n].view(p.shape).clone(),
+                        "exp_avg_sq": self.exp_avg_sq[off: off + n].view(p.shape).clone()}
+            off += n
+        group = {"lr": self.lr, "betas": tuple(self.betas), "eps": self.eps, "weight_decay": self.wd, "amsgrad": False,
+                 "maximize": False, "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                 "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd: Dict) -> None:
+        groups = sd["param_groups"]
+        ids = [i for g in groups for i in g["params"]]
+        if len(ids) != len(self.params):
+            raise ValueError(f"optimizer state holds {len(ids)} parameters, this FineTuner has {len(self.params)}")
+        g0 = groups[0]
+        self.lr, self.betas, self.eps, self.wd = g0["lr"], tuple(g0["betas"]), g0["eps"], g0["weight_decay"]
+        off, steps = 0, set()
+        for pid, p in zip(ids, self.params):
+            n = p.numel()
+            st = sd["state"].get(pid)
+            if st is None:                      # parameter never stepped: zero moments
+                self.exp_avg[off: off + n].zero_(); self.exp_avg_sq[off: off + n].zero_()
+            else:
+                if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                    raise ValueError(f"optimizer state {pid}: shape {tuple(st['exp_avg'].shape)} != parameter {tuple(p.shape)}")
+                self.exp_avg[off: off + n].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off: off + n].copy_(st["exp_avg_sq"].reshape(-1))
+                steps.add(int(float(st["step"])))
+            off += n
+        if len(steps) > 1:
+            raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): the fused AdamW keeps one step count")
+        self.step_count = steps.pop() if steps else 0
 
     def run(self, host_batches, memory: Optional[Tensor] = None, memory_labels: Optional[Tensor] = None):
         """Training loop over (clip, labels) batches that live in (pinned) HOST memory -- what the reference's DataLoader
@@ -192,6 +244,8 @@ class FineTuner:
             clip, labels = batch
             if stage[k] is None or stage[k][0].shape != clip.shape or stage[k][0].dtype != clip.dtype:
                 stage[k] = (torch.empty(clip.shape, device=dev, dtype=clip.dtype), torch.empty(labels.shape, device=dev, dtype=labels.dtype))
+                # the caching allocator may hand back a block whose last use on the compute stream is still in flight
+                copy_stream.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(consumed[k])
                 stage[k][0].copy_(clip, non_blocking=True)

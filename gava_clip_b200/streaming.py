@@ -32,6 +32,8 @@ class ClipStreamer:
     def _upload(self, k: int, host: Tensor) -> None:
         if self._stage[k] is None or self._stage[k].shape != host.shape or self._stage[k].dtype != host.dtype:
             self._stage[k] = torch.empty(host.shape, device=self.device, dtype=host.dtype)   # fp32 (B,3,T,H,W) or uint8 (B,T,H,W,3)
+            # the caching allocator may hand back a block whose last use on the compute stream is still in flight
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._consumed[k])            # slot free again?
             self._stage[k].copy_(host, non_blocking=True)

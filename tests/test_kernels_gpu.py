@@ -200,7 +200,8 @@ def _attention_ref(qkv, kv_aux, B, T, N0, G, H):
     return torch.stack(outs).reshape(BT * N0, D)
 
 
-@pytest.mark.parametrize("T,N0,H", [(8, 197, 12), (16, 197, 12), (16, 257, 16), (3, 50, 2)])
+@pytest.mark.parametrize("T,N0,H", [(8, 197, 12), (16, 197, 12), (16, 257, 16), (3, 50, 2), (70, 197, 2), (24, 197, 4),
+                                    (32, 257, 2), (5, 129, 3)])
 def test_attention(cuda, T, N0, H):
     from gava_clip_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(T * N0)
@@ -212,6 +213,58 @@ def test_attention(cuda, T, N0, H):
     ops.attention(qkv, kv_aux, out, B=B, T=T, N0=N0, G=G, H=H)
     ref = _attention_ref(qkv, kv_aux, B, T, N0, G, H)
     assert _rel(out.float(), ref) < 1.5e-2   # P is rounded to bf16 before PV
+
+
+def _lse_ref(qkv, kv_aux, B, T, N0, G, H):
+    """log2-domain log-sum-exp of every query row, [BT, H, N0]"""
+    D, BT = H * 64, B * T
+    q, k, _ = qkv.float().view(BT, N0, 3, H, 64).unbind(2)
+    ka = kv_aux.float().view(-1, 2, H, 64)[:, 0]
+    rows = []
+    for f in range(BT):
+        b = f // T
+        idx = list(range(G)) + list(range(G + b * T, G + (b + 1) * T)) + [G + BT + f]
+        kk = torch.cat([k[f], ka[idx]])
+        aff = torch.einsum("qhc,khc->hqk", q[f] / 8.0, kk)
+        rows.append(torch.logsumexp(aff, dim=-1) * math.log2(math.e))
+    return torch.stack(rows)
+
+
+@pytest.mark.parametrize("T,N0,H", [(8, 197, 12), (16, 257, 4)])
+def test_attention_single_pass_overflow_rows(cuda, T, N0, H):
+    """The tcgen05 kernel shifts every row by the maximum of its FIRST 32 scores; rows where a later key beats that by
+    more than 2^100 are recomputed exactly on the CUDA cores.  Craft such rows (a late key aligned with the query at a
+    huge norm), moderately peaked rows (stale shift, no overflow) and ordinary rows; output and log-sum-exp must match."""
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(77)
+    B, G = 2, 8
+    D, BT = H * 64, B * T
+    qkv = torch.randn(BT * N0, 3 * D, device=cuda, generator=g)
+    v5 = qkv.view(BT, N0, 3, H, 64)
+    # frame 1, head 0: query rows 3, 130 and (ViT-L) 256 see key 150 with logit 64*6*48 = 18432 (x0.18 = 3300 log2 units: overflow)
+    hot_rows = [3, 130] + ([256] if N0 > 256 else [])
+    for r in hot_rows:
+        v5[1, r, 0, 0] = 6.0
+    v5[1, 150, 1, 0] = 6.0 * 8.0
+    # frame 2, head 1: key 180 beats the first chunk by ~40 log2 units for every row (stale shift, still exact)
+    v5[2, :, 0, 1] = 1.0
+    v5[2, 180, 1, 1] = 3.5
+    # frame 0, last head: a PROMPT key (summary token) dominates rows 0..9
+    kv_aux = torch.randn(G + 2 * BT, 2 * D, device=cuda, generator=g)
+    v5[0, :10, 0, H - 1] = 5.0
+    kv_aux.view(-1, 2, H, 64)[G + BT + 0, 0, H - 1] = 40.0
+    qkv, kv_aux = qkv.bfloat16(), kv_aux.bfloat16()
+    out = torch.zeros(BT * N0, D, device=cuda, dtype=torch.bfloat16)
+    lse = torch.zeros(BT, H, N0, device=cuda)
+    ops.attention_train(qkv, kv_aux, out, lse, B=B, T=T, N0=N0, G=G, H=H)
+    ref = _attention_ref(qkv, kv_aux, B, T, N0, G, H)
+    assert torch.isfinite(out.float()).all()
+    assert _rel(out.float(), ref) < 1.5e-2
+    lref = _lse_ref(qkv, kv_aux, B, T, N0, G, H)
+    assert float(((lse - lref).abs() / lref.abs().clamp_min(1.0)).max()) < 2e-3
+    for r in hot_rows:     # the recomputed rows individually
+        a = out.float().view(BT, N0, H, 64)[1, r, 0]
+        assert _rel(a, ref.view(BT, N0, H, 64)[1, r, 0]) < 1.5e-2
 
 
 @pytest.mark.parametrize("B,T,N0,G,H", [(2, 8, 197, 8, 12), (1, 70, 197, 8, 2), (3, 3, 17, 8, 2), (1, 16, 257, 8, 16)])
