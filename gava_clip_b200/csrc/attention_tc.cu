@@ -117,6 +117,7 @@ struct KeyMask {
   int v0, v1, v2, v3;
   // bit i = key j0 + i is valid (i < 16)
   __device__ __forceinline__ uint32_t bits16(int j0) const {
+    if (j0 + 16 <= v0) return 0xFFFFu;          // the common case: a chunk of live rows
     auto low = [](int n) -> uint32_t { n = n < 0 ? 0 : (n > 16 ? 16 : n); return (1u << n) - 1u; };
     uint32_t m = low(v0 - j0) | (low(v2 - j0) & ~low(v1 - j0));
     const int d = v3 - j0;
@@ -440,6 +441,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           { ATC_T0(); mbar_wait(&s_full[s], n_blk & 1u); ATC_ACC(d_sfull); }
           ++n_blk;                                   // this is key block n_blk - 1 of the slot
           tc_fence_after();
+          if (blk == 0 && storer && pending_qs >= 0) {
+            // The previous unit's TMA store has finished reading its staging tile by now (a whole S MMA round trip
+            // later): hand that Q tile back to the producer.  Not later than here: with two key blocks the other
+            // group's next unit may need this very ring slot before it can hand over the token this unit's second
+            // block waits for.
+            tma_store_wait_read();
+            mbar_arrive(&q_empty[pending_qs]);
+            pending_qs = -1;
+          }
           uint32_t va[16], vb[16];
           tmem_ld_32x16(t_mine, va);
           const int kbase = blk * KB + hh * HALF;    // smem key row of this thread's first column
@@ -464,18 +474,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #if GAVA_ATTN_DEBUG
           const long long t_exp0 = clock64();
 #endif
+          int n_fast = (km.v0 - kbase) >> 4;            // leading chunks of live rows only (no masked key)
+          n_fast = n_fast < 0 ? 0 : (n_fast > NCH ? NCH : n_fast);
+          int ch = 0;
 #pragma unroll 1
-          for (int ch = 0; ch < NCH; ch += 2) {         // two chunks per trip: the TMEM load of one overlaps the exps of the other
-            uint32_t pk[8];
+          for (; ch + 2 <= n_fast; ch += 2) {           // branch-free body, two chunks per trip: the TMEM load of one
+            uint32_t pk[8];                             // overlaps the exps of the other
             tmem_ld_wait();
+            tmem_ld_32x16(t_mine + (uint32_t)((ch + 1) * 16), vb);
+            sum += chunk16_exp<false>(va, pk, 0xFFFFu, c, mc);
+            tmem_st_32x8(t_mine + (uint32_t)(ch * 8), pk);
+            tmem_ld_wait();
+            if (ch + 2 < NCH) tmem_ld_32x16(t_mine + (uint32_t)((ch + 2) * 16), va);
+            sum += chunk16_exp<false>(vb, pk, 0xFFFFu, c, mc);
+            tmem_st_32x8(t_mine + (uint32_t)((ch + 1) * 8), pk);
+          }
+#pragma unroll 1
+          for (; ch < NCH; ++ch) {                      // the odd chunk out and the chunks that may hold masked keys
+            uint32_t pk[8];
+            tmem_ld_wait();                             // va holds chunk ch
             if (ch + 1 < NCH) tmem_ld_32x16(t_mine + (uint32_t)((ch + 1) * 16), vb);
             sum += chunk16_pass(va, pk, km.bits16(kbase + ch * 16), c, mc);
             tmem_st_32x8(t_mine + (uint32_t)(ch * 8), pk);
             if (ch + 1 < NCH) {
               tmem_ld_wait();
-              if (ch + 2 < NCH) tmem_ld_32x16(t_mine + (uint32_t)((ch + 2) * 16), va);
-              sum += chunk16_pass(vb, pk, km.bits16(kbase + ch * 16 + 16), c, mc);
-              tmem_st_32x8(t_mine + (uint32_t)((ch + 1) * 8), pk);
+#pragma unroll
+              for (int q = 0; q < 16; ++q) va[q] = vb[q];
             }
           }
           mbar_arrive(&turn[s ^ 1]);          // exp pass done: the other group's turn
@@ -486,12 +510,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #endif
           tc_fence_before();
           mbar_arrive(&p_ready[s]);
-        }
-        // the previous unit's TMA store has long finished reading its staging tile: hand that Q tile back to the producer
-        if (storer && pending_qs >= 0) {
-          tma_store_wait_read();
-          mbar_arrive(&q_empty[pending_qs]);
-          pending_qs = -1;
         }
         // ---- O = P V done: normalise, cast, store this thread's 32 of the row's 64 output values
         { ATC_T0(); mbar_wait(&o_full[s], n_unit & 1u); ATC_ACC(d_ofull); }
