@@ -284,7 +284,8 @@ __global__ void __launch_bounds__(256) attention_q1_kernel(const AttnArgs p) {
 
 template <int CT>
 static int launch_attention(const AttnArgs& a, int frames, size_t smem_bytes, cudaStream_t stream) {
-  static size_t attr_bytes = 0;
+  static size_t attr_bytes_dev[64] = {0};
+  size_t& attr_bytes = attr_bytes_dev[device_slot()];
   auto kern = attention_kernel<CT>;
   if (smem_bytes > attr_bytes) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);

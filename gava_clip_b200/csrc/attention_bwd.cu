@@ -414,7 +414,8 @@ int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const vo
   a.s_pad = (a.S + 15) / 16 * 16;
   const size_t smem_bytes = (size_t)(2 * a.q_pad + 2 * a.s_pad) * 128 + (size_t)a.q_pad * 8;
   if (smem_bytes > 226 * 1024) { set_error("attention_bwd: %d keys x %d queries exceed the shared-memory budget", a.S, N0); return GAVA_ERR_SHAPE; }
-  static size_t attr_bytes = 0;
+  static size_t attr_bytes_dev[64] = {0};
+  size_t& attr_bytes = attr_bytes_dev[device_slot()];
   if (smem_bytes > attr_bytes) {
     cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);

@@ -584,7 +584,8 @@ static int launch_attention_tc(const CUtensorMap& tq, const CUtensorMap& tkv, co
                                const CUtensorMap& tout, const AttnTcArgs& a, cudaStream_t stream) {
   constexpr int smem_bytes = 2 * (2 * KB * NB * 128) + QR * ATC_QTILE_BYTES + 1024 + (18 + 2 * QR) * 8 + 2 * 2 * 2 * 128 * 4;
   static_assert(smem_bytes <= 227 * 1024, "attention_tc: shared memory budget");
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};
+  bool& attr_set = attr_set_dev[device_slot()];
   auto kern = attention_tc_kernel<KB, NB, QR>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);

@@ -478,7 +478,9 @@ static int launch_seq_attention_bwd(const void* qkv, const void* dout, void* dqk
   if (!qkv || !dout || !dqkv || n_seq <= 0 || T <= 0 || H <= 0) { set_error("%s: bad arguments", what); return GAVA_ERR_ARG; }
   if (T > 128) { set_error("%s: sequence length %d > 128 unsupported", what, T); return GAVA_ERR_SHAPE; }
   const size_t smem = sizeof(float) * ((size_t)4 * T * 65 + (size_t)T * (T + 1));
-  static size_t attr_bytes = 48 * 1024;
+  static size_t attr_bytes_dev[64] = {0};
+  size_t& attr_bytes = attr_bytes_dev[device_slot()];
+  if (attr_bytes == 0) attr_bytes = 48 * 1024;
   auto kern = seq_attention_bwd_kernel<IN_F32, CAUSAL>;
   if (smem > attr_bytes) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -661,21 +661,28 @@ int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, long long planes, long lo
   return GAVA_OK;
 }
 
+int device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 ? 0 : (dev > 63 ? 63 : dev);
+}
+
 int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {0};
+  const int d = device_slot();
+  if (n[d] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d);
+    n[d] = v > 0 ? v : 148;
   }
-  return n;
+  return n[d];
 }
 
 template <int BN, int MODE>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};
+  bool& attr_set = attr_set_dev[device_slot()];
   auto kern = gemm_tcgen05_kernel<BN, MODE>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -691,7 +698,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
 template <int MODE>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream, int max_ctas = 0) {
   using Cfg = Gemm2Cfg;
-  static bool attr_set = false;
+  static bool attr_set_dev[64] = {false};
+  bool& attr_set = attr_set_dev[device_slot()];
   auto kern = gemm2_tcgen05_kernel<MODE>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);

@@ -17,7 +17,8 @@ enum : int {
   EPI_BIAS_RESID_LN_F32 = GAVA_EPI_BIAS_RESID_LN_F32,
 };
 
-int num_sms();
+int num_sms();         // of the CURRENT device
+int device_slot();     // cudaGetDevice(), clamped to [0, 64): index for per-device caches (kernel attributes are per device)
 
 // 2-D bf16 row-major [rows, cols] (row pitch ld elements) TMA map, box = [box_rows, 64 cols], 128-byte swizzle
 int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows);

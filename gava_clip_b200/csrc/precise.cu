@@ -244,7 +244,8 @@ static int attention_f32_impl(const float* qkv, const float* kv_aux, float* out,
   a.S = kv_aux ? N0 + G + T + 1 : N0;       // kv_aux == NULL: plain self-attention over the N0 rows (summary attention)
   const size_t smem = (size_t)(2 * a.S * 65 + 8 * 64 + 8 * a.S) * sizeof(float);
   if (smem > 220 * 1024) { set_error("attention_f32: %d keys exceed shared memory", a.S); return GAVA_ERR_SHAPE; }
-  static size_t attr = 0;
+  static size_t attr_dev[64] = {0};
+  size_t& attr = attr_dev[device_slot()];
   if (smem > attr) {
     cudaError_t e = cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(attention_f32): %s", cudaGetErrorString(e)); return (int)e; }

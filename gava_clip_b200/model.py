@@ -244,6 +244,12 @@ class VitaCLIP(nn.Module):
     def forward(self, x: Tensor, memory=None, video_nte=None, desc_wise=False):
         """x: fp32 clip (B,3,T,H,W) as in the reference, or -- after self.visual.set_input_norm(mean, std) -- the
         decoder's uint8 frames (B,T,H,W,3), normalised on the fly inside the patch gather."""
+        if x.is_cuda and x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(x.device):        # the kernels launch on the current device / stream
+                return self._forward(x, memory, video_nte, desc_wise)
+        return self._forward(x, memory, video_nte, desc_wise)
+
+    def _forward(self, x: Tensor, memory=None, video_nte=None, desc_wise=False):
         text_ahead = None
         if self.use_text_prompt_learning and x.is_cuda and self._text_side_needs_grad() and self.text_side_stream:
             # fine-tune step: the text side (a few hundred small library kernels, launch-bound) is issued FIRST on a side

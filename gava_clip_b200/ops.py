@@ -35,6 +35,11 @@ def _stream() -> int:
 def _req(t: Tensor, dtype, name: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor (the sm_100a path has no CPU fallback)")
+    if t.device.index != torch.cuda.current_device():
+        # kernels launch on the CURRENT device and stream; a tensor living elsewhere would be read through a wrong
+        # context (or fault).  The towers wrap their schedules in torch.cuda.device(...), direct callers must too.
+        raise RuntimeError(f"{name}: tensor is on {t.device} but the current CUDA device is {torch.cuda.current_device()} "
+                           "(use `with torch.cuda.device(t.device):`)")
     if t.dtype != dtype:
         raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
 

@@ -275,7 +275,16 @@ class TextTower:
                 if getattr(self, "_trainer", None) is None or self._trainer.device != device:
                     self._trainer = TextTrainer(self.textual, device)
                 raw = TextTrainFunction.apply(self._trainer, torch.cat(prompts, dim=0).to(device), tok)
-            else:       # host-side tests, or a trainable text transformer: the module's own PyTorch forward
+            elif device.type == "cuda":
+                # No PyTorch fallback on the GPU: the sm_100a text backward covers what the reference trains (prompt
+                # learner / KAPT projector through a FROZEN text transformer, VitaCLIP_model.py:230-239).
+                bad = [n for n, p in self.textual.named_parameters() if p.requires_grad][:4]
+                raise NotImplementedError(
+                    "gava_clip_b200 has no PyTorch fallback on CUDA: the text side of the fine-tune step runs on the sm_100a "
+                    "kernels with the text transformer frozen (the reference's recipe); "
+                    + (f"these textual parameters require grad: {bad}" if bad else
+                       "GAVA_TEXT_NATIVE_TRAIN=0 disabled that path"))
+            else:       # host-side (CPU) tests of the module logic only: the module's own PyTorch forward
                 raw = self.textual(torch.cat(prompts, dim=0).to(device), tok).float()
             t_hat = raw / raw.norm(dim=-1, keepdim=True)
             offs = torch.tensor([0] + list(torch.tensor(counts).cumsum(0)), dtype=torch.int32, device=device)

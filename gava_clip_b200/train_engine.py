@@ -163,6 +163,9 @@ class TowerTrainer(TowerEngine):
         D, N0, G, H = e.feature_dim, int(e.num_patches), e.num_global_prompts, e.num_heads
         BT, M = B * T, B * T * N0
         W = self.train_ws(B, T)
+        # every forward stamps its tape: backward() refuses a tape that a later forward of the same shape overwrote
+        self.tape_generation = getattr(self, "tape_generation", 0) + 1
+        W["generation"] = self.tape_generation
         te = self.time_embed_for(T)
         xn, h = W["xn"], W["h"]
         n0 = ops.launch_count()
@@ -227,11 +230,20 @@ class TowerTrainer(TowerEngine):
         return W["frame_feat"], W["summary"][L - 1]
 
     # ------------------------------------------------------------------ backward
-    def backward(self, B: int, T: int, d_frame_feat: Optional[Tensor], d_summary: Optional[Tensor]) -> Dict[str, Tensor]:
+    def backward(self, B: int, T: int, d_frame_feat: Optional[Tensor], d_summary: Optional[Tensor],
+                 generation: Optional[int] = None) -> Dict[str, Tensor]:
         """Gradients of the trainable tower parameters given d(frame_feat) [BT, E(+pad)] and d(summary tokens) [BT, D]
         (either may be None = zero).  Returns self.grads (views into self.grad_flat); uses the tape of the last
-        forward_train call for this (B, T)."""
+        forward_train call for this (B, T) -- `generation` (the stamp that forward returned) guards against a tape that
+        was evicted or overwritten by a later forward in between."""
         e, P = self.enc, self.packed
+        tape = self.ws.get(("train", B, T))
+        if tape is None:
+            raise RuntimeError(f"backward: the activation tape of the ({B},{T}) forward was evicted (more than two clip "
+                               "shapes in flight); run forward and backward of one batch back to back")
+        if generation is not None and tape.get("generation") != generation:
+            raise RuntimeError("backward: the activation tape was overwritten by a later train-mode forward of the same clip "
+                               "shape (two forwards before one backward are not supported: the tape is per shape)")
         self._alloc_grads()
         D, N0, G, H = e.feature_dim, int(e.num_patches), e.num_global_prompts, e.num_heads
         BT, M = B * T, B * T * N0
@@ -346,6 +358,7 @@ class TowerFunction(torch.autograd.Function):
         ff, st = trainer.forward_train(video)
         B, T, _, _ = _clip_dims(video)
         ctx.trainer, ctx.B, ctx.T, ctx.E = trainer, B, T, E
+        ctx.generation = trainer.tape_generation
         ctx.names = [n for n, _ in trainer.trainable_named()]
         # clones: the workspace is overwritten by the next forward while autograd may still hold these outputs
         return ff[:, :E].clone(), st.clone()
@@ -353,7 +366,7 @@ class TowerFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_ff: Optional[Tensor], d_st: Optional[Tensor]):
         tr: TowerTrainer = ctx.trainer
-        grads = tr.backward(ctx.B, ctx.T, d_ff, d_st)
+        grads = tr.backward(ctx.B, ctx.T, d_ff, d_st, generation=ctx.generation)
         out = []
         for (name, p), need in zip(tr.trainable_named(), ctx.needs_input_grad[3:]):
             # clones: autograd may adopt the returned tensor as .grad; the flat buffer is rewritten by the next backward

@@ -153,6 +153,10 @@ class TowerEngine:
         self.ln_tail = os.environ.get("GAVA_LN_TAIL", "0") == "1"
         self.side_stream = torch.cuda.Stream(device) if device.type == "cuda" else None
         self.launches_last_call = 0      # sm_100a kernels launched (or replayed) by the last run()
+        # parity instrument (tests): a dict here receives, per layer, clones of the cls rows of the residual stream and of the
+        # summary tokens -- the tensors the reference's per-block forward hooks see (VitaCLIP_vision_encoder.py:116-121).
+        # Only honoured by eager runs (a replayed graph cannot clone per layer).
+        self.taps: Optional[Dict[str, list]] = None
 
     # ------------------------------------------------------------------ weights
     def _sig(self):
@@ -480,6 +484,9 @@ class TowerEngine:
                 ops.gemm(W["cls_bf"], P[k + "fc1.w"], h[:BT], mode=ops.EPI_BIAS_GELU_BF16, bias=P[k + "fc1.b"])
                 ops.gemm(h[:BT], P[k + "fc2.w"], W["x_cls"], mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"],
                          resid=W["x_cls"])
+            if self.taps is not None and not torch.cuda.is_current_stream_capturing():
+                self.taps.setdefault("layer_cls", []).append((x.view(BT, N0 * D)[:, :D] if i < L - 1 else W["x_cls"]).clone())
+                self.taps.setdefault("layer_summary", []).append(W["summary"].clone())
 
         # ln_post(cls) @ proj per frame                                   vision_encoder.py:126-127
         ops.layernorm(W["x_cls"], P["ln_post.w"], P["ln_post.b"], W["cls_bf"], rows=BT, in_row_stride=D)
@@ -623,6 +630,10 @@ class CLIPVisionEncoder(nn.Module):
         if len(mean) == 1:
             mean, std = mean * 3, std * 3
         assert len(mean) == 3 and len(std) == 3 and all(v > 0 for v in std)
+        if self.input_norm != (mean, std) and self._engine is not None:
+            # mean/std are passed BY VALUE to the uint8 patch gather and therefore baked into captured graphs
+            for k in [k for k, v in self._engine.graphs.items() if v[1].dtype == torch.uint8]:
+                del self._engine.graphs[k]
         self.input_norm = (mean, std)
 
     # -- engine plumbing ---------------------------------------------------------------------------
@@ -675,6 +686,9 @@ class CLIPVisionEncoder(nn.Module):
         return ff, st, B, T
 
     def forward(self, x: Tensor):
+        if x.is_cuda and x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(x.device):        # the kernels launch on the current device / stream
+                return self.forward(x)
         ff, st, B, T = self.frames_forward(x)
         E = self.embed_dim
         # temporal means (vision_encoder.py:128-130); the fused head kernel does the same inside VitaCLIP.forward

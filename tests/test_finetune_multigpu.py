@@ -67,9 +67,9 @@ def test_two_rank_step_equals_single_process_full_batch(cuda):
     for n in ref:
         assert torch.equal(ret[0][1][n], ret[1][1][n]), f"ranks diverged on {n}"
         assert torch.equal(ret[0][0][n], ret[1][0][n]), f"reduced gradients differ between ranks on {n}"
-        if "k_proj" in n:
-            continue      # cancellation-dominated (exact k bias gradient is 0: softmax shift invariance)
-        assert rel_l2(ret[0][0][n], ref[n]) < 2e-2, n
+        if n.endswith("k_proj.bias"):
+            continue      # exact k bias gradient is 0 (softmax shift invariance): pure rounding noise on both sides
+        assert rel_l2(ret[0][0][n], ref[n]) < (1e-1 if "k_proj.weight" in n else 2e-2), n
 
 
 def _ddp_worker(rank, world, port, ret):

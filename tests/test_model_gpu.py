@@ -23,7 +23,7 @@ def _run(name, cuda, **fw):
     return model, out
 
 
-@pytest.mark.parametrize("name", ["tiny", "b16_t8", "b16_t16_k400", "l14_t16", "kapt_b16_t8"])
+@pytest.mark.parametrize("name", ["tiny", "b16_t8", "b16_t8_b8", "b16_t16_k400", "l14_t16", "kapt_b16_t8"])
 def test_logits_match_reference(cuda, name):
     g = load_golden(name)
     model, (logits, logits_mt, logits_vm) = _run(name, cuda)
@@ -68,6 +68,37 @@ def test_visual_tower_standalone_and_layer_taps(cuda):
         cls_x, summary = model.visual(video)
     assert cls_x.shape == (B, 512) and summary.shape == (B, 768)
     assert rel_l2(cls_x, g["video_features"]) < TOL and rel_l2(summary, g["summary"]) < TOL
+
+
+@pytest.mark.parametrize("name", ["tiny", "b16_t8"])
+def test_layer_taps_match_reference(cuda, name):
+    """Per-layer localisation: cls rows of the residual stream and summary tokens after EVERY block against the
+    reference's own per-block outputs (goldens `layer_cls` / `layer_summary`, VitaCLIP_vision_encoder.py:116-121).  A
+    regression shows up at the first layer it enters instead of only in the logits.  bf16 operand rounding accumulates
+    with depth, so the budget is per layer: rel-L2 <= 2.5e-3 * (layer + 1) + 2e-3, and the last layer within TOL."""
+    g = load_golden(name)
+    model, kw, B = build_model(name, device=cuda)
+    video = fx.make_inputs(name)["video"].to(cuda)
+    eng = model.visual.engine(cuda)
+    eng.use_graph, eng.taps = False, {}
+    try:
+        with torch.no_grad():
+            model.visual(video)
+        torch.cuda.synchronize()
+        taps = eng.taps
+    finally:
+        eng.use_graph, eng.taps = True, None
+    L = len(model.visual.blocks)
+    assert len(taps["layer_cls"]) == L and len(taps["layer_summary"]) == L
+    errs = []
+    for i in range(L):
+        e_cls = rel_l2(taps["layer_cls"][i], g["layer_cls"][i])
+        e_sum = rel_l2(taps["layer_summary"][i].view_as(g["layer_summary"][i]), g["layer_summary"][i])
+        errs.append((e_cls, e_sum))
+        budget = 2.5e-3 * (i + 1) + 2e-3
+        assert e_cls < budget and e_sum < budget, f"layer {i}: cls {e_cls:.3e} summary {e_sum:.3e} (budget {budget:.3e})"
+    print(f"\n[{name}] per-layer rel-L2 (cls, summary): " + " ".join(f"{a:.1e}/{b:.1e}" for a, b in errs))
+    assert errs[-1][0] < TOL and errs[-1][1] < TOL
 
 
 def test_zeroshot_branch(cuda, tmp_path):
@@ -515,10 +546,13 @@ def test_finetune_config5_model_gradients(cuda):
     for n in names:
         g, r = params[n].grad, sd[n].grad
         assert g is not None and torch.isfinite(g).all(), n
-        if r is None or float(r.abs().max()) == 0.0 or "k_proj" in n:
-            continue
+        if r is None or float(r.abs().max()) == 0.0 or n.endswith("k_proj.bias"):
+            continue              # k biases only: softmax is invariant to a shift of all keys, their exact gradient is 0
         c, e = _cos(g, r), rel_l2(g, r)
-        if c < 0.995 or e > 1e-1:
+        # k_proj WEIGHTS are compared too; their gradient is what survives the per-row cancellation sum_k dS[q,k] = 0 over
+        # T = 8 keys, so bf16 rounding of dS weighs more: looser budget
+        lim_c, lim_e = (0.98, 2e-1) if "k_proj.weight" in n else (0.995, 1e-1)
+        if c < lim_c or e > lim_e:
             bad[n] = (round(e, 4), round(c, 5))
     assert not bad, f"gradient mismatch (rel-L2, cosine): {bad}"
 

@@ -9,7 +9,7 @@ from tests.util import build_model, fx, load_golden, rel_err
 from oracle import vita_oracle as vo
 
 FAST = ["tiny", "b16_t8", "kapt_b16_t8"]
-SLOW = ["l14_t16", "b16_t16_k400"]
+SLOW = ["l14_t16", "b16_t16_k400", "b16_t8_b8"]
 
 
 @pytest.mark.parametrize("name", FAST + SLOW)
