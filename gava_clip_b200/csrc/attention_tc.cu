@@ -23,6 +23,11 @@
 // (attn_row_exact).  With the same stale m for every key block, long rows (NB = 2 blocks: 257..320 keys, ViT-L/14 and
 // the 70-frame recipe) need no rescaling of O either.
 //
+// Key masking costs the softmax warps nothing: invalid smem key rows (padding between the live rows and the prompt rows,
+// the tails of the 8-row prompt boxes) get a score of -1e30 from a FIFTH k-step of the S MMA, whose A operand is a constant
+// tile with a column of ones and whose B operand holds 0 / -1e30 per key row (the pattern is the same for every item).
+// Both are tiny no-swizzle K-major tiles built once per CTA.  exp2 then returns exact zeros for those keys.
+//
 // The two softmax groups take TURNS on the exp pass (mbarrier token, one key block each): left alone they run in lock
 // step -- both in the MUFU-bound exp pass, then both in the epilogue, then both waiting for their MMAs -- and the MUFU
 // pipe idles two thirds of the time; alternating, one group's exp pass covers the other's MMA round trips and epilogue.
@@ -115,53 +120,42 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_bmn(uint32_t M, uint32_t 
 // valid keys of the smem row space: live rows [0,v0) | global + local prompts [v1,v2) | summary token at v3
 struct KeyMask {
   int v0, v1, v2, v3;
-  // bit i = key j0 + i is valid (i < 16)
-  __device__ __forceinline__ uint32_t bits16(int j0) const {
-    if (j0 + 16 <= v0) return 0xFFFFu;          // the common case: a chunk of live rows
-    auto low = [](int n) -> uint32_t { n = n < 0 ? 0 : (n > 16 ? 16 : n); return (1u << n) - 1u; };
-    uint32_t m = low(v0 - j0) | (low(v2 - j0) & ~low(v1 - j0));
-    const int d = v3 - j0;
-    if (d >= 0 && d < 16) m |= 1u << d;
-    return m;
-  }
+  __device__ __forceinline__ bool ok(int k) const { return k < v0 || (k >= v1 && k < v2) || k == v3; }
 };
 
-__device__ __forceinline__ float chunk16_max(const uint32_t (&v)[16], uint32_t bits) {
+__device__ __forceinline__ float chunk16_max(const uint32_t (&v)[16]) {
   float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
-    const float a0 = (bits >> j) & 1u ? __uint_as_float(v[j]) : -INFINITY;
-    const float a1 = (bits >> (j + 1)) & 1u ? __uint_as_float(v[j + 1]) : -INFINITY;
-    m0 = fmaxf(m0, a0); m1 = fmaxf(m1, a1);
+    m0 = fmaxf(m0, __uint_as_float(v[j])); m1 = fmaxf(m1, __uint_as_float(v[j + 1]));
   }
   return fmaxf(m0, m1);
 }
-// p = exp2(s c - mc) for 16 scores -> 8 packed bf16 pairs; returns their fp32 sum.  MASK: keys whose bit is 0 get p = 0.
-template <bool MASK>
-__device__ __forceinline__ float chunk16_exp(const uint32_t (&v)[16], uint32_t (&pk)[8], uint32_t bits, float c, float mc) {
+// p = exp2(s c - mc) for 16 scores -> 8 packed bf16 pairs; returns their fp32 sum (masked keys arrive as s = -1e30: p = 0)
+__device__ __forceinline__ float chunk16_exp(const uint32_t (&v)[16], uint32_t (&pk)[8], float c, float mc) {
   float s0 = 0.f, s1 = 0.f;
 #pragma unroll
   for (int j = 0; j < 16; j += 2) {
-    float p0 = exp2f(fmaf(__uint_as_float(v[j]), c, -mc));
-    float p1 = exp2f(fmaf(__uint_as_float(v[j + 1]), c, -mc));
-    if (MASK) {
-      if (!((bits >> j) & 1u)) p0 = 0.f;
-      if (!((bits >> (j + 1)) & 1u)) p1 = 0.f;
-    }
+    const float p0 = exp2f(fmaf(__uint_as_float(v[j]), c, -mc));
+    const float p1 = exp2f(fmaf(__uint_as_float(v[j + 1]), c, -mc));
     s0 += p0; s1 += p1;
     pk[j >> 1] = pack_bf16x2(p0, p1);
   }
   return s0 + s1;
 }
-// one 16-key chunk of the exp pass: all keys valid (the common case), some, or none
-__device__ __forceinline__ float chunk16_pass(const uint32_t (&v)[16], uint32_t (&pk)[8], uint32_t bits, float c, float mc) {
-  if (bits == 0xFFFFu) return chunk16_exp<false>(v, pk, bits, c, mc);
-  if (bits == 0u) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) pk[q] = 0u;
-    return 0.f;
-  }
-  return chunk16_exp<true>(v, pk, bits, c, mc);
+
+// K-major tile WITHOUT swizzle, 16 bf16 wide: rows in groups of 8; a group is [k-chunk 0: 8 rows x 16 B][k-chunk 1: 8 rows x
+// 16 B] = 256 B.  Canonical layout ((8,n),(8,2)):((16 B, SBO),(2 B, LBO)) with LBO = 128 B, SBO = 256 B.
+__device__ __forceinline__ uint64_t make_nosw_kmajor_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(128u >> 4) << 16;                    // leading byte offset: between the two 16-byte k-chunks
+  d |= (uint64_t)(256u >> 4) << 32;                    // stride byte offset: between 8-row groups
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+  return d;                                            // layout type 0 = no swizzle
+}
+__device__ __forceinline__ uint32_t nosw_offset(int row, int col) {   // byte offset of element (row, col < 16) in such a tile
+  return (uint32_t)((row >> 3) * 256 + (col >> 3) * 128 + (row & 7) * 16 + (col & 7) * 2);
 }
 
 // Exact two-pass attention of ONE query row on the CUDA cores, straight from global memory: the cold path for rows whose
@@ -227,7 +221,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_q = smem + 2 * kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_q + QR * ATC_QTILE_BYTES);
+  uint8_t* a_ext = smem_q + QR * ATC_QTILE_BYTES;      // [128 x 16] ones column (A operand of the masking k-step), 4 KB
+  uint8_t* b_ext = a_ext + 4096;                       // [NKT x 16] 0 / -1e30 per key row (B operand), NKT * 32 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ext + NKT * 32);
   uint64_t* kv_full = bars;         // [2] TMA -> MMA
   uint64_t* kv_empty = bars + 2;    // [2] MMA -> TMA (n_units commits)
   uint64_t* s_full = bars + 4;      // [2] MMA -> softmax group of slot s (once per key block)
@@ -239,7 +235,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   uint64_t* q_full = bars + 16;     // [QR] TMA -> MMA
   uint64_t* q_empty = bars + 16 + QR;   // [QR] softmax group (after its TMA store read the staged O tile) -> TMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16 + 2 * QR);
-  float* xch = reinterpret_cast<float*>(bars + 18 + 2 * QR);   // [slot 2][max|sum 2][half 2][row 128] row statistics exchange
+  float* xch = reinterpret_cast<float*>(bars + 18 + 2 * QR);   // [slot 2][half 2][row 128] row statistics exchange (max, later sum)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = p.n_units;
@@ -247,6 +243,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   // K/V rows that no TMA box covers must still be finite (their probabilities are exact zeros): zero both stages once
   for (int i = threadIdx.x; i < 2 * kStageBytes / 16; i += ATC_THREADS)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  {   // the masking operands
+    KeyMask km0;
+    km0.v0 = p.N0; km0.v1 = p.kb_live; km0.v2 = p.kb_live + 8 + p.T; km0.v3 = p.kb_live + 8 + p.t_pad;
+    const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f), neg = __float2bfloat16_rn(-1e30f);
+    for (int i = threadIdx.x; i < 128 * 16; i += ATC_THREADS)
+      *reinterpret_cast<__nv_bfloat16*>(a_ext + nosw_offset(i >> 4, i & 15)) = (i & 15) == 0 ? one : zero;
+    for (int i = threadIdx.x; i < NKT * 16; i += ATC_THREADS)
+      *reinterpret_cast<__nv_bfloat16*>(b_ext + nosw_offset(i >> 4, i & 15)) = ((i & 15) == 0 && !km0.ok(i >> 4)) ? neg : zero;
+  }
   fence_proxy_async();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -343,9 +348,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           const uint64_t dq = make_sw128_kmajor_desc(smem_u32(smem_q + qs * ATC_QTILE_BYTES));
           const uint64_t dk = make_sw128_kmajor_desc(smem_u32(sK));
           const uint64_t dv = make_sw128_mnmajor_desc(smem_u32(sV), (uint32_t)kKVBytes);
+          const uint64_t dae = make_nosw_kmajor_desc(smem_u32(a_ext));
+          const uint64_t dbe = make_nosw_kmajor_desc(smem_u32(b_ext));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16_ss(t_slot, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
+          umma_bf16_ss(t_slot, dae, dbe, idesc_s, 1u);       // + (-1e30) on the invalid key columns
           umma_commit(&s_full[s]);
 #pragma unroll
           for (int blk = 0; blk < NB; ++blk) {
@@ -369,6 +377,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16_ss(t_slot, dq + (uint64_t)(2 * k), dkb + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
+              umma_bf16_ss(t_slot, dae, dbe + (uint64_t)((blk + 1) * KB * 32 / 16), idesc_s, 1u);
               umma_commit(&s_full[s]);
             }
             ++n_blk;
@@ -397,10 +406,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const float c = 0.125f * 1.4426950408889634f;  // dh^-0.5 * log2(e)
     KeyMask km;
     km.v0 = p.N0; km.v1 = p.kb_live; km.v2 = p.kb_live + 8 + p.T; km.v3 = p.kb_live + 8 + p.t_pad;
-    float* my_max = xch + ((s * 2 + 0) * 2 + hh) * 128 + row_in_tile;
-    float* ot_max = xch + ((s * 2 + 0) * 2 + (hh ^ 1)) * 128 + row_in_tile;
-    float* my_sum = xch + ((s * 2 + 1) * 2 + hh) * 128 + row_in_tile;
-    float* ot_sum = xch + ((s * 2 + 1) * 2 + (hh ^ 1)) * 128 + row_in_tile;
+    // one slot per (group, half, row): holds the first-chunk maximum until the named barrier, the row sum afterwards
+    float* my_max = xch + (s * 2 + hh) * 128 + row_in_tile;
+    float* ot_max = xch + (s * 2 + (hh ^ 1)) * 128 + row_in_tile;
+    float* my_sum = my_max;
+    float* ot_sum = ot_max;
     const bool storer = quarter == 0 && hh == 0 && lane == 0;   // issues the unit's TMA store (quarter 0 is never dead)
     int pending_qs = -1;                    // Q tile whose TMA store (by this thread) may still be reading shared memory
     uint32_t n_unit = 0, n_blk = 0;
@@ -456,7 +466,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           if (blk == 0) {
             // the row's shift: maximum of the first 16 scores of each key half (key 0, the cls token, is always valid)
             tmem_ld_wait();
-            float mx = chunk16_max(va, km.bits16(kbase));
+            float mx = chunk16_max(va);
             *my_max = mx;
             { ATC_T0(); asm volatile("bar.sync %0, 256;" ::"r"(1 + s) : "memory"); ATC_ACC(d_bar); }
             mx = fmaxf(mx, *ot_max);
@@ -474,33 +484,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #if GAVA_ATTN_DEBUG
           const long long t_exp0 = clock64();
 #endif
-          int n_fast = (km.v0 - kbase) >> 4;            // leading chunks of live rows only (no masked key)
-          n_fast = n_fast < 0 ? 0 : (n_fast > NCH ? NCH : n_fast);
+          int n_live = (km.v3 + 16 - kbase) >> 4;       // chunks that hold at least one valid key (the rest: P = 0, no exps)
+          n_live = n_live < 0 ? 0 : (n_live > NCH ? NCH : n_live);
           int ch = 0;
 #pragma unroll 1
-          for (; ch + 2 <= n_fast; ch += 2) {           // branch-free body, two chunks per trip: the TMEM load of one
+          for (; ch + 2 <= n_live; ch += 2) {           // branch-free body, two chunks per trip: the TMEM load of one
             uint32_t pk[8];                             // overlaps the exps of the other
             tmem_ld_wait();
             tmem_ld_32x16(t_mine + (uint32_t)((ch + 1) * 16), vb);
-            sum += chunk16_exp<false>(va, pk, 0xFFFFu, c, mc);
+            sum += chunk16_exp(va, pk, c, mc);
             tmem_st_32x8(t_mine + (uint32_t)(ch * 8), pk);
             tmem_ld_wait();
-            if (ch + 2 < NCH) tmem_ld_32x16(t_mine + (uint32_t)((ch + 2) * 16), va);
-            sum += chunk16_exp<false>(vb, pk, 0xFFFFu, c, mc);
+            if (ch + 2 < n_live) tmem_ld_32x16(t_mine + (uint32_t)((ch + 2) * 16), va);
+            sum += chunk16_exp(vb, pk, c, mc);
             tmem_st_32x8(t_mine + (uint32_t)((ch + 1) * 8), pk);
           }
-#pragma unroll 1
-          for (; ch < NCH; ++ch) {                      // the odd chunk out and the chunks that may hold masked keys
+          tmem_ld_wait();
+          if (ch < n_live) {                            // the odd chunk out
             uint32_t pk[8];
-            tmem_ld_wait();                             // va holds chunk ch
-            if (ch + 1 < NCH) tmem_ld_32x16(t_mine + (uint32_t)((ch + 1) * 16), vb);
-            sum += chunk16_pass(va, pk, km.bits16(kbase + ch * 16), c, mc);
+            sum += chunk16_exp(va, pk, c, mc);
             tmem_st_32x8(t_mine + (uint32_t)(ch * 8), pk);
-            if (ch + 1 < NCH) {
-              tmem_ld_wait();
-#pragma unroll
-              for (int q = 0; q < 16; ++q) va[q] = vb[q];
-            }
+            ++ch;
+          }
+#pragma unroll 1
+          for (; ch < NCH; ++ch) {
+            const uint32_t zz[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            tmem_st_32x8(t_mine + (uint32_t)(ch * 8), zz);
           }
           mbar_arrive(&turn[s ^ 1]);          // exp pass done: the other group's turn
           if (blk == NB - 1) *my_sum = sum;
@@ -582,7 +591,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 template <int KB, int NB, int QR>
 static int launch_attention_tc(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& taux,
                                const CUtensorMap& tout, const AttnTcArgs& a, cudaStream_t stream) {
-  constexpr int smem_bytes = 2 * (2 * KB * NB * 128) + QR * ATC_QTILE_BYTES + 1024 + (18 + 2 * QR) * 8 + 2 * 2 * 2 * 128 * 4;
+  constexpr int smem_bytes = 2 * (2 * KB * NB * 128) + QR * ATC_QTILE_BYTES + 1024 + 4096 + KB * NB * 32 + (18 + 2 * QR) * 8 + 2 * 2 * 128 * 4;
   static_assert(smem_bytes <= 227 * 1024, "attention_tc: shared memory budget");
   static bool attr_set_dev[64] = {false};
   bool& attr_set = attr_set_dev[device_slot()];

@@ -75,7 +75,7 @@ def test_layer_taps_match_reference(cuda, name):
     """Per-layer localisation: cls rows of the residual stream and summary tokens after EVERY block against the
     reference's own per-block outputs (goldens `layer_cls` / `layer_summary`, VitaCLIP_vision_encoder.py:116-121).  A
     regression shows up at the first layer it enters instead of only in the logits.  bf16 operand rounding accumulates
-    with depth, so the budget is per layer: rel-L2 <= 2.5e-3 * (layer + 1) + 2e-3, and the last layer within TOL."""
+    with depth, so the budget is per layer: rel-L2 <= 4e-3 + 5e-4 * layer (measured: 1.7e-3 ... 5.6e-3), and the last layer within TOL."""
     g = load_golden(name)
     model, kw, B = build_model(name, device=cuda)
     video = fx.make_inputs(name)["video"].to(cuda)
@@ -95,7 +95,7 @@ def test_layer_taps_match_reference(cuda, name):
         e_cls = rel_l2(taps["layer_cls"][i], g["layer_cls"][i])
         e_sum = rel_l2(taps["layer_summary"][i].view_as(g["layer_summary"][i]), g["layer_summary"][i])
         errs.append((e_cls, e_sum))
-        budget = 2.5e-3 * (i + 1) + 2e-3
+        budget = 4e-3 + 5e-4 * i
         assert e_cls < budget and e_sum < budget, f"layer {i}: cls {e_cls:.3e} summary {e_sum:.3e} (budget {budget:.3e})"
     print(f"\n[{name}] per-layer rel-L2 (cls, summary): " + " ".join(f"{a:.1e}/{b:.1e}" for a, b in errs))
     assert errs[-1][0] < TOL and errs[-1][1] < TOL
