@@ -6,11 +6,12 @@
 //                live rows of the frame | 8 global prompts | T local prompts | summary token), Q tiles [128 x 64]
 //   TMEM       : two SLOTS of 256 columns; unit u runs in slot u & 1:
 //                S = Q K_blk^T (128 x KB fp32) at columns [0, KB) of the slot, one key block (KB keys) at a time;
-//                P (bf16, unnormalised probabilities) overwrites S in place, each key-column half inside its own columns
-//                (keys [0,KB/2) -> cols [0,KB/4), keys [KB/2,KB) -> cols [KB/2, 3KB/4));
+//                P (bf16, unnormalised probabilities) overwrites S in place: the 16 scores of key chunk k (columns
+//                [16k, 16k+16)) become 8 columns of packed bf16 pairs at [16k, 16k+8);
 //                O += P V_blk (128 x 64 fp32) at columns [192, 256) of the slot
 //   roles      : warp 0 TMA producer, warps 1/2 MMA issuers of slot 0/1 (warp 2 also allocates TMEM), warps 3-18
-//                softmax/output: 8 warps per slot, TWO threads per query row (each owns one half of the key columns)
+//                softmax/output: 8 warps per slot, TWO threads per query row (thread hh owns the 16-key chunks of parity hh,
+//                so valid, masked and dead chunks split evenly between the two)
 // QK^T is an SS MMA (both operands K-major in smem); P V is a TS MMA (A = P from TMEM, B = V MN-major in smem).
 //
 // ONE pass over S.  The kernel is bound by MUFU.EX2 (16 exp2 per clock per SM, tools/cuda/tmem_bw.cu) and by the chain of
@@ -36,7 +37,6 @@
 // clip the rows beyond n_q (32 scattered 16-byte stores per warp instruction made the epilogue LSU-bound before).
 //
 // Restates Attention.forward core, training/VitaCLIP_vision_encoder_utils.py:71-77 (see attention.cu).
-#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -361,12 +361,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             { ATC_T0(); mbar_wait(&p_ready[s], n_blk & 1u); ATC_ACC(d_pready); }
             tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < KB / 16; ++k) {  // 16 keys per MMA; V advances 16 rows (2048 B); P of key half 0 sits
-              // at columns 8k, P of key half 1 at KB/2 + 8(k - KB/32) (each half writes P inside its own S columns)
-              const int pcol = k < KB / 32 ? 8 * k : KB / 2 + 8 * (k - KB / 32);
-              umma_bf16_ts(t_slot + 192u, t_slot + (uint32_t)pcol, dv + (uint64_t)(128 * (blk * (KB / 16) + k)), idesc_o,
+            for (int k = 0; k < KB / 16; ++k)    // 16 keys per MMA; V advances 16 rows (2048 B); P of chunk k sits at columns 16k
+              umma_bf16_ts(t_slot + 192u, t_slot + (uint32_t)(16 * k), dv + (uint64_t)(128 * (blk * (KB / 16) + k)), idesc_o,
                            (uint32_t)(blk != 0 || k != 0));
-            }
             if (blk + 1 < NB) {
 #if GAVA_ATTN_SAFE_ORDER
               umma_commit(&pv_done[s]);
@@ -400,10 +397,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int hh = (idx >> 2) & 1;          // key-column half owned by this thread
     const int quarter = warp & 3;           // TMEM lane quarter (hardware rule: warp % 4)
     const int row_in_tile = quarter * 32 + lane;
-    constexpr int HALF = KB / 2;            // keys per half and block: HALF/16 chunks of 16
-    constexpr int NCH = HALF / 16;
+    constexpr int NCH = KB / 32;            // 16-key chunks per thread and block: chunks 2 ch + hh of the block
     const uint32_t t_slot = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 256);
-    const uint32_t t_mine = t_slot + (uint32_t)(hh * HALF);
+    const uint32_t t_mine = t_slot + (uint32_t)(hh * 16);      // chunk ch of this thread: columns [t_mine + 32 ch, + 16)
     const float c = 0.125f * 1.4426950408889634f;  // dh^-0.5 * log2(e)
     KeyMask km;
     km.v0 = p.N0; km.v1 = p.kb_live; km.v2 = p.kb_live + 8 + p.T; km.v3 = p.kb_live + 8 + p.t_pad;
@@ -463,9 +459,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
           uint32_t va[16], vb[16];
           tmem_ld_32x16(t_mine, va);
-          const int kbase = blk * KB + hh * HALF;    // smem key row of this thread's first column
+          const int kbase = blk * KB + hh * 16;      // smem key row of this thread's first column
           if (blk == 0) {
-            // the row's shift: maximum of the first 16 scores of each key half (key 0, the cls token, is always valid)
+            // the row's shift: maximum of the first 32 scores, 16 per thread (key 0, the cls token, is always valid)
             tmem_ld_wait();
             float mx = chunk16_max(va);
             *my_max = mx;
@@ -485,32 +481,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #if GAVA_ATTN_DEBUG
           const long long t_exp0 = clock64();
 #endif
-          int n_live = (km.v3 + 16 - kbase) >> 4;       // chunks that hold at least one valid key (the rest: P = 0, no exps)
+          int n_live = (km.v3 + 32 - kbase) >> 5;       // own chunks that hold at least one valid key (the rest: P = 0, no exps)
           n_live = n_live < 0 ? 0 : (n_live > NCH ? NCH : n_live);
           int ch = 0;
 #pragma unroll 1
           for (; ch + 2 <= n_live; ch += 2) {           // branch-free body, two chunks per trip: the TMEM load of one
             uint32_t pk[8];                             // overlaps the exps of the other
             tmem_ld_wait();
-            tmem_ld_32x16(t_mine + (uint32_t)((ch + 1) * 16), vb);
+            tmem_ld_32x16(t_mine + (uint32_t)((ch + 1) * 32), vb);
             sum += chunk16_exp(va, pk, c, mc);
-            tmem_st_32x8(t_mine + (uint32_t)(ch * 8), pk);
+            tmem_st_32x8(t_mine + (uint32_t)(ch * 32), pk);
             tmem_ld_wait();
-            if (ch + 2 < n_live) tmem_ld_32x16(t_mine + (uint32_t)((ch + 2) * 16), va);
+            if (ch + 2 < n_live) tmem_ld_32x16(t_mine + (uint32_t)((ch + 2) * 32), va);
             sum += chunk16_exp(vb, pk, c, mc);
-            tmem_st_32x8(t_mine + (uint32_t)((ch + 1) * 8), pk);
+            tmem_st_32x8(t_mine + (uint32_t)((ch + 1) * 32), pk);
           }
           tmem_ld_wait();
           if (ch < n_live) {                            // the odd chunk out
             uint32_t pk[8];
             sum += chunk16_exp(va, pk, c, mc);
-            tmem_st_32x8(t_mine + (uint32_t)(ch * 8), pk);
+            tmem_st_32x8(t_mine + (uint32_t)(ch * 32), pk);
             ++ch;
           }
 #pragma unroll 1
           for (; ch < NCH; ++ch) {
             const uint32_t zz[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-            tmem_st_32x8(t_mine + (uint32_t)(ch * 8), zz);
+            tmem_st_32x8(t_mine + (uint32_t)(ch * 32), zz);
           }
           mbar_arrive(&turn[s ^ 1]);          // exp pass done: the other group's turn
           if (blk == NB - 1) *my_sum = sum;
@@ -589,370 +585,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Double-buffered variant for up to 288 smem key rows (ViT-B/16 up to 48 frames): key blocks of 96, TWO S buffers per
-// slot (columns [0,96) and [96,192); O at [192,256) never overlaps S), so per slot
-//   * S of block g+1 is computed while the softmax group works on block g (no MMA round trip between blocks or units),
-//   * P V of block g runs underneath the exp pass of block g+1 (only the last block's P V is exposed),
-//   * the next unit's first S needs no s_free: only its first P V waits for the previous unit's O to be read out.
-// Barriers that may complete twice before the waiter looks (s_full, p_ready) exist once per S buffer.
-constexpr int ADB_KB = 96, ADB_NB = 3, ADB_QR = 4, ADB_NKT = ADB_KB * ADB_NB;
-
-struct UnitCursor {         // walks the (item, query tile, key block) sequence of one TMEM slot of one CTA
-  int item, j, tile, blk;
-  __device__ __forceinline__ bool valid(int num_items) const { return item < num_items; }
-  __device__ __forceinline__ void to_first(int s, int n_units, int num_items) {
-    item = blockIdx.x; j = 0; tile = 0; blk = 0;
-    while (item < num_items && ((j * n_units + tile) & 1) != s) step_unit(n_units);
-  }
-  __device__ __forceinline__ void step_unit(int n_units) {
-    if (++tile == n_units) { tile = 0; ++j; item += gridDim.x; }
-  }
-  __device__ __forceinline__ void advance(int s, int n_units, int num_items) {
-    if (++blk < ADB_NB) return;
-    blk = 0;
-    do { step_unit(n_units); } while (item < num_items && ((j * n_units + tile) & 1) != s);
-  }
-};
-
-__global__ void __launch_bounds__(ATC_THREADS, 1)
-attention_tc_db_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
-                       const __grid_constant__ CUtensorMap tm_aux, const __grid_constant__ CUtensorMap tm_out,
-                       const AttnTcArgs p) {
-  constexpr int KB = ADB_KB, NB = ADB_NB, QR = ADB_QR, NKT = ADB_NKT;
-  constexpr int kKVBytes = NKT * 128;
-  constexpr int kStageBytes = 2 * kKVBytes;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_q = smem + 2 * kStageBytes;
-  uint8_t* a_ext = smem_q + QR * ATC_QTILE_BYTES;
-  uint8_t* b_ext = a_ext + 4096;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ext + NKT * 32);
-  uint64_t* kv_full = bars;         // [2]
-  uint64_t* kv_empty = bars + 2;    // [2] n_units commits
-  uint64_t* s_full = bars + 4;      // [slot 2][buffer 2]
-  uint64_t* p_ready = bars + 8;     // [slot 2][buffer 2]
-  uint64_t* o_full = bars + 12;     // [2]
-  uint64_t* s_free = bars + 14;     // [2] O read out
-  uint64_t* turn = bars + 16;       // [2]
-  uint64_t* q_full = bars + 18;     // [QR]
-  uint64_t* q_empty = bars + 18 + QR;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18 + 2 * QR);
-  float* xch = reinterpret_cast<float*>(bars + 20 + 2 * QR);   // [max | sum][slot 2][half 2][row 128]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_units = p.n_units;
-
-  for (int i = threadIdx.x; i < 2 * kStageBytes / 16; i += ATC_THREADS)
-    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  {
-    KeyMask km0;
-    km0.v0 = p.N0; km0.v1 = p.kb_live; km0.v2 = p.kb_live + 8 + p.T; km0.v3 = p.kb_live + 8 + p.t_pad;
-    const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f), neg = __float2bfloat16_rn(-1e30f);
-    for (int i = threadIdx.x; i < 128 * 16; i += ATC_THREADS)
-      *reinterpret_cast<__nv_bfloat16*>(a_ext + nosw_offset(i >> 4, i & 15)) = (i & 15) == 0 ? one : zero;
-    for (int i = threadIdx.x; i < NKT * 16; i += ATC_THREADS)
-      *reinterpret_cast<__nv_bfloat16*>(b_ext + nosw_offset(i >> 4, i & 15)) = ((i & 15) == 0 && !km0.ok(i >> 4)) ? neg : zero;
-  }
-  fence_proxy_async();
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm_q);
-    tma_prefetch_desc(&tm_kv);
-    tma_prefetch_desc(&tm_aux);
-    tma_prefetch_desc(&tm_out);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], n_units);
-      mbar_init(&o_full[i], 1);
-      mbar_init(&s_free[i], 256);
-      mbar_init(&turn[i], 256);
-    }
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_ready[i], 256);
-    }
-    for (int i = 0; i < QR; ++i) {
-      mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================== TMA producer (same as attention_tc_kernel) =====================
-    if (lane == 0) {
-      int j = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++j) {
-        const int f = item / p.H, h = item - f * p.H;
-        const int b = f / p.T;
-        const int st = j & 1;
-        uint8_t* sK = smem + st * kStageBytes;
-        uint8_t* sV = sK + kKVBytes;
-        mbar_wait(&kv_empty[st], ((uint32_t)(j >> 1) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(&kv_full[st], p.kv_tx_bytes);
-        const int xk = p.D + h * 64, xv = 2 * p.D + h * 64;
-        const int row = f * p.N0;
-        for (int r = 0; r < p.kb_live; r += p.live_box) {
-          tma_load_2d(sK + r * 128, &tm_kv, &kv_full[st], xk, row + r);
-          tma_load_2d(sV + r * 128, &tm_kv, &kv_full[st], xv, row + r);
-        }
-        int r = p.kb_live;
-        tma_load_2d(sK + r * 128, &tm_aux, &kv_full[st], h * 64, 0);
-        tma_load_2d(sV + r * 128, &tm_aux, &kv_full[st], p.D + h * 64, 0);
-        r += 8;
-        for (int i = 0; i < p.T; i += 8, r += 8) {
-          tma_load_2d(sK + r * 128, &tm_aux, &kv_full[st], h * 64, p.G + b * p.T + i);
-          tma_load_2d(sV + r * 128, &tm_aux, &kv_full[st], p.D + h * 64, p.G + b * p.T + i);
-        }
-        tma_load_2d(sK + r * 128, &tm_aux, &kv_full[st], h * 64, p.G + p.BT + f);
-        tma_load_2d(sV + r * 128, &tm_aux, &kv_full[st], p.D + h * 64, p.G + p.BT + f);
-        for (int tile = 0; tile < n_units; ++tile) {
-          const int u = j * n_units + tile;
-          const int qs = u % QR;
-          mbar_wait(&q_empty[qs], ((uint32_t)(u / QR) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&q_full[qs], ATC_QTILE_BYTES);
-          tma_load_2d(smem_q + qs * ATC_QTILE_BYTES, &tm_q, &q_full[qs], h * 64, row + tile * 128);
-        }
-      }
-    }
-    __syncwarp();
-  } else if (warp == 1 || warp == 2) {
-    // ===================== MMA issuer of slot s: S runs two key blocks ahead of P V =====================
-    const int s = warp - 1;
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, KB);
-      constexpr uint32_t idesc_o = make_idesc_bf16_bmn(128, 64);
-      const uint32_t t_slot = tmem_base + (uint32_t)(s * 256);
-      const uint64_t dae = make_nosw_kmajor_desc(smem_u32(a_ext));
-      const uint64_t dbe = make_nosw_kmajor_desc(smem_u32(b_ext));
-      UnitCursor cs, cp;
-      cs.to_first(s, n_units, p.num_items);
-      cp = cs;
-      uint32_t g_s = 0, g_p = 0, n_unit = 0;
-      auto issue_s = [&]() {          // S of block g_s of this slot into buffer g_s & 1
-        const int u = cs.j * n_units + cs.tile;
-        const int st = cs.j & 1, qs = u % QR;
-        if (cs.blk == 0) {
-          mbar_wait(&kv_full[st], (uint32_t)(cs.j >> 1) & 1u);
-          mbar_wait(&q_full[qs], (uint32_t)(u / QR) & 1u);
-          tc_fence_after();
-        }
-        const uint64_t dq = make_sw128_kmajor_desc(smem_u32(smem_q + qs * ATC_QTILE_BYTES));
-        const uint64_t dk = make_sw128_kmajor_desc(smem_u32(smem + st * kStageBytes)) + (uint64_t)(cs.blk * KB * 128 / 16);
-        const uint32_t t_buf = t_slot + (g_s & 1u) * (uint32_t)KB;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16_ss(t_buf, dq + (uint64_t)(2 * k), dk + (uint64_t)(2 * k), idesc_s, (uint32_t)(k != 0));
-        umma_bf16_ss(t_buf, dae, dbe + (uint64_t)(cs.blk * KB * 32 / 16), idesc_s, 1u);    // -1e30 on invalid key columns
-        umma_commit(&s_full[s * 2 + (int)(g_s & 1u)]);
-        ++g_s;
-        cs.advance(s, n_units, p.num_items);
-      };
-      for (int i = 0; i < 2; ++i)
-        if (cs.valid(p.num_items)) issue_s();
-      while (cp.valid(p.num_items)) {
-        const int st = cp.j & 1;
-        mbar_wait(&p_ready[s * 2 + (int)(g_p & 1u)], (g_p >> 1) & 1u);
-        if (cp.blk == 0) mbar_wait(&s_free[s], (n_unit & 1u) ^ 1u);     // the previous unit's O has been read out
-        tc_fence_after();
-        const uint64_t dv = make_sw128_mnmajor_desc(smem_u32(smem + st * kStageBytes + kKVBytes), (uint32_t)kKVBytes);
-        const uint32_t t_buf = t_slot + (g_p & 1u) * (uint32_t)KB;
-#pragma unroll
-        for (int k = 0; k < KB / 16; ++k) {
-          const int pcol = k < KB / 32 ? 8 * k : KB / 2 + 8 * (k - KB / 32);
-          umma_bf16_ts(t_slot + 192u, t_buf + (uint32_t)pcol, dv + (uint64_t)(128 * (cp.blk * (KB / 16) + k)), idesc_o,
-                       (uint32_t)(cp.blk != 0 || k != 0));
-        }
-        if (cp.blk == NB - 1) {
-          umma_commit(&o_full[s]);
-          umma_commit(&kv_empty[st]);
-          ++n_unit;
-        }
-        ++g_p;
-        cp.advance(s, n_units, p.num_items);
-        if (cs.valid(p.num_items)) issue_s();       // into the buffer whose P the MMAs above (in issue order) have consumed
-      }
-    }
-    __syncwarp();
-  } else if (warp >= 3) {
-    // ===================== softmax + output =====================
-    const int idx = warp - 3;
-    const int s = idx >> 3;
-    const int hh = (idx >> 2) & 1;
-    const int quarter = warp & 3;
-    const int row_in_tile = quarter * 32 + lane;
-    constexpr int HALF = KB / 2;            // 48 keys = 3 chunks
-    constexpr int NCH = HALF / 16;
-    const uint32_t t_slot = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 256);
-    const float c = 0.125f * 1.4426950408889634f;
-    const int v3 = p.kb_live + 8 + p.t_pad;           // last valid smem key row (the summary token)
-    float* my_max = xch + (s * 2 + hh) * 128 + row_in_tile;
-    float* ot_max = xch + (s * 2 + (hh ^ 1)) * 128 + row_in_tile;
-    // separate slots for the row sums: with S running ahead, this thread may start the next unit (and publish its next
-    // maximum) before the partner has read this unit's sum
-    float* my_sum = my_max + 512;
-    float* ot_sum = ot_max + 512;
-    const bool storer = quarter == 0 && hh == 0 && lane == 0;
-    int pending_qs = -1;
-    uint32_t n_unit = 0, n_blk = 0;
-    const int my_items = (p.num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const uint32_t blocks_b = (uint32_t)((my_items * n_units) / 2) * NB;
-    int j = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++j) {
-      const int f = item / p.H, h = item - f * p.H;
-      for (int tile = 0; tile < n_units; ++tile) {
-        if (((j * n_units + tile) & 1) != s) continue;
-        const bool dead = tile * 128 + quarter * 32 >= p.n_q;      // all 32 rows of this warp beyond n_q: protocol only
-        float mc = 0.f, sum = 0.f;
-#pragma unroll 1
-        for (int blk = 0; blk < NB; ++blk) {
-          const uint32_t g = n_blk;
-          mbar_wait(&s_full[s * 2 + (int)(g & 1u)], (g >> 1) & 1u);
-          ++n_blk;
-          tc_fence_after();
-          const uint32_t t_mine = t_slot + (g & 1u) * (uint32_t)KB + (uint32_t)(hh * HALF);
-          uint32_t va[16], vb[16];
-          if (!dead) tmem_ld_32x16(t_mine, va);
-          if (blk == 0) {
-            if (storer && pending_qs >= 0) {          // the previous unit's TMA store has read its staging tile by now
-              tma_store_wait_read();
-              mbar_arrive(&q_empty[pending_qs]);
-              pending_qs = -1;
-            }
-            float mx = -INFINITY;
-            if (!dead) {
-              tmem_ld_wait();
-              mx = chunk16_max(va);
-              *my_max = mx;
-            }
-            asm volatile("bar.sync %0, 256;" ::"r"(1 + s) : "memory");
-            if (!dead) mc = fmaxf(mx, *ot_max) * c;
-          }
-          if (s == 0) { if (g > 0 && g - 1u < blocks_b) mbar_wait(&turn[0], (g - 1u) & 1u); }
-          else mbar_wait(&turn[1], g & 1u);
-          if (!dead) {
-            const int kbase = blk * KB + hh * HALF;
-            int n_live = (v3 + 16 - kbase) >> 4;
-            n_live = n_live < 0 ? 0 : (n_live > NCH ? NCH : n_live);
-            int ch = 0;
-#pragma unroll 1
-            for (; ch + 2 <= n_live; ch += 2) {
-              uint32_t pk[8];
-              tmem_ld_wait();
-              tmem_ld_32x16(t_mine + (uint32_t)((ch + 1) * 16), vb);
-              sum += chunk16_exp(va, pk, c, mc);
-              tmem_st_32x8(t_mine + (uint32_t)(ch * 8), pk);
-              tmem_ld_wait();
-              if (ch + 2 < n_live) tmem_ld_32x16(t_mine + (uint32_t)((ch + 2) * 16), va);
-              sum += chunk16_exp(vb, pk, c, mc);
-              tmem_st_32x8(t_mine + (uint32_t)((ch + 1) * 8), pk);
-            }
-            tmem_ld_wait();
-            if (ch < n_live) {
-              uint32_t pk[8];
-              sum += chunk16_exp(va, pk, c, mc);
-              tmem_st_32x8(t_mine + (uint32_t)(ch * 8), pk);
-              ++ch;
-            }
-#pragma unroll 1
-            for (; ch < NCH; ++ch) {
-              const uint32_t zz[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-              tmem_st_32x8(t_mine + (uint32_t)(ch * 8), zz);
-            }
-          }
-          mbar_arrive(&turn[s ^ 1]);
-          if (!dead) {
-            if (blk == NB - 1) *my_sum = sum;
-            tmem_st_wait();
-            tc_fence_before();
-          }
-          mbar_arrive(&p_ready[s * 2 + (int)(g & 1u)]);
-        }
-        mbar_wait(&o_full[s], n_unit & 1u);
-        ++n_unit;
-        tc_fence_after();
-        if (dead) {
-          mbar_arrive(&s_free[s]);
-          asm volatile("bar.sync %0, 256;" ::"r"(3 + s) : "memory");
-          continue;
-        }
-        const float tot = sum + *ot_sum;
-        const float inv = 1.0f / tot;
-        const int qrow = tile * 128 + row_in_tile;
-        const bool exact = !(tot < ATC_SUM_LIMIT) && qrow < p.n_q;
-        if (p.lse != nullptr && hh == 0 && qrow < p.n_q && !exact) p.lse[((long long)f * p.H + h) * p.N0 + qrow] = mc + log2f(tot);
-        uint32_t o0[16], o1[16];
-        tmem_ld_32x16(t_slot + 192u + (uint32_t)(hh * 32), o0);
-        tmem_ld_32x16(t_slot + 192u + (uint32_t)(hh * 32 + 16), o1);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&s_free[s]);
-        const int qs = (j * n_units + tile) % QR;
-        uint8_t* stage = smem_q + qs * ATC_QTILE_BYTES;
-        uint8_t* stage_row = stage + row_in_tile * 128;
-        if (!exact) {
-          const int sw = row_in_tile & 7;
-#define GAVA_PK(v, i) pack_bf16x2(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv)
-          st_shared_v4(stage_row + (((hh * 4 + 0) ^ sw) << 4), GAVA_PK(o0, 0), GAVA_PK(o0, 2), GAVA_PK(o0, 4), GAVA_PK(o0, 6));
-          st_shared_v4(stage_row + (((hh * 4 + 1) ^ sw) << 4), GAVA_PK(o0, 8), GAVA_PK(o0, 10), GAVA_PK(o0, 12), GAVA_PK(o0, 14));
-          st_shared_v4(stage_row + (((hh * 4 + 2) ^ sw) << 4), GAVA_PK(o1, 0), GAVA_PK(o1, 2), GAVA_PK(o1, 4), GAVA_PK(o1, 6));
-          st_shared_v4(stage_row + (((hh * 4 + 3) ^ sw) << 4), GAVA_PK(o1, 8), GAVA_PK(o1, 10), GAVA_PK(o1, 12), GAVA_PK(o1, 14));
-#undef GAVA_PK
-        } else {
-          ExactRowDims dm;
-          dm.T = p.T; dm.N0 = p.N0; dm.G = p.G; dm.H = p.H; dm.BT = p.BT; dm.D = p.D;
-          attn_row_exact(p.qkv, p.kvaux, stage_row, p.lse, dm, f, h, qrow, hh);
-        }
-        fence_proxy_async();
-        asm volatile("bar.sync %0, 256;" ::"r"(3 + s) : "memory");
-        if (storer) {
-          tma_store_3d(&tm_out, stage, h * 64, tile * 128, f);
-          tma_store_commit();
-          pending_qs = qs;
-        }
-      }
-    }
-    if (storer) {
-      if (pending_qs >= 0) {
-        tma_store_wait_read();
-        mbar_arrive(&q_empty[pending_qs]);
-      }
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-static int launch_attention_tc_db(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& taux,
-                                  const CUtensorMap& tout, const AttnTcArgs& a, cudaStream_t stream) {
-  constexpr int smem_bytes = 2 * (2 * ADB_NKT * 128) + ADB_QR * ATC_QTILE_BYTES + 1024 + 4096 + ADB_NKT * 32 +
-                             (20 + 2 * ADB_QR) * 8 + 2 * 2 * 2 * 128 * 4;
-  static_assert(smem_bytes <= 227 * 1024, "attention_tc_db: shared memory budget");
-  static bool attr_set_dev[64] = {false};
-  bool& attr_set = attr_set_dev[device_slot()];
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(attention_tc_db): %s", cudaGetErrorString(e)); return (int)e; }
-    attr_set = true;
-  }
-  const int grid = a.num_items < num_sms() ? a.num_items : num_sms();
-  attention_tc_db_kernel<<<grid, ATC_THREADS, smem_bytes, stream>>>(tq, tkv, taux, tout, a);
-  return check_launch("attention_tc_db");
-}
-
 template <int KB, int NB, int QR>
 static int launch_attention_tc(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& taux,
                                const CUtensorMap& tout, const AttnTcArgs& a, cudaStream_t stream) {
@@ -1008,9 +640,6 @@ int attention_tc(const void* qkv, const void* kv_aux, void* out, float* lse, int
   a.num_items = BT * H;
   a.n_units = (n_q + 127) / 128;
   a.kv_tx_bytes = (uint32_t)(2 * 128 * keys);
-  // GAVA_ATTN_DB=0: single-buffered kernels for every shape (A/B runs)
-  static const bool use_db = [] { const char* e = getenv("GAVA_ATTN_DB"); return !(e && e[0] == '0'); }();
-  if (use_db && keys <= ADB_NKT) return launch_attention_tc_db(tq, tkv, taux, tout, a, stream);
   if (keys <= 224) return launch_attention_tc<224, 1, 4>(tq, tkv, taux, tout, a, stream);
   if (keys <= 256) return launch_attention_tc<256, 1, 4>(tq, tkv, taux, tout, a, stream);
   return launch_attention_tc<160, 2, 3>(tq, tkv, taux, tout, a, stream);
