@@ -157,8 +157,9 @@ class Dist:
             self.saved_stdout = os.dup(1)
             os.dup2(2, 1)
             dist.init_process_group("nccl", device_id=self.dev)
-        from gava_clip_b200 import _lib
+        from gava_clip_b200 import _lib, tokenizer
         _lib.check(_lib.load().gava_init(), "gava_init")
+        tokenizer.register_tokens(json.loads(TOKENS.read_text()))      # prompt text -> CLIP ids (no merge table on the GPU box)
 
     def barrier(self):
         if self.world > 1:
