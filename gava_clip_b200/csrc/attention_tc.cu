@@ -6,12 +6,11 @@
 //                live rows of the frame | 8 global prompts | T local prompts | summary token), Q tiles [128 x 64]
 //   TMEM       : two SLOTS of 256 columns; unit u runs in slot u & 1:
 //                S = Q K_blk^T (128 x KB fp32) at columns [0, KB) of the slot, one key block (KB keys) at a time;
-//                P (bf16, unnormalised probabilities) overwrites S in place: the 16 scores of key chunk k (columns
-//                [16k, 16k+16)) become 8 columns of packed bf16 pairs at [16k, 16k+8);
+//                P (bf16, unnormalised probabilities) overwrites S in place, each key-column half inside its own columns
+//                (keys [0,KB/2) -> cols [0,KB/4), keys [KB/2,KB) -> cols [KB/2, 3KB/4));
 //                O += P V_blk (128 x 64 fp32) at columns [192, 256) of the slot
 //   roles      : warp 0 TMA producer, warps 1/2 MMA issuers of slot 0/1 (warp 2 also allocates TMEM), warps 3-18
-//                softmax/output: 8 warps per slot, TWO threads per query row (thread hh owns the 16-key chunks of parity hh,
-//                so valid, masked and dead chunks split evenly between the two)
+//                softmax/output: 8 warps per slot, TWO threads per query row (each owns one half of the key columns)
 // QK^T is an SS MMA (both operands K-major in smem); P V is a TS MMA (A = P from TMEM, B = V MN-major in smem).
 //
 // ONE pass over S.  The kernel is bound by MUFU.EX2 (16 exp2 per clock per SM, tools/cuda/tmem_bw.cu) and by the chain of
@@ -361,9 +360,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
             { ATC_T0(); mbar_wait(&p_ready[s], n_blk & 1u); ATC_ACC(d_pready); }
             tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < KB / 16; ++k)    // 16 keys per MMA; V advances 16 rows (2048 B); P of chunk k sits at columns 16k
-              umma_bf16_ts(t_slot + 192u, t_slot + (uint32_t)(16 * k), dv + (uint64_t)(128 * (blk * (KB / 16) + k)), idesc_o,
+            for (int k = 0; k < KB / 16; ++k) {  // 16 keys per MMA; V advances 16 rows (2048 B); P of key half 0 sits
+              // at columns 8k, P of key half 1 at KB/2 + 8(k - KB/32) (each half writes P inside its own S columns)
+              const int pcol = k < KB / 32 ? 8 * k : KB / 2 + 8 * (k - KB / 32);
+              umma_bf16_ts(t_slot + 192u, t_slot + (uint32_t)pcol, dv + (uint64_t)(128 * (blk * (KB / 16) + k)), idesc_o,
                            (uint32_t)(blk != 0 || k != 0));
+            }
             if (blk + 1 < NB) {
 #if GAVA_ATTN_SAFE_ORDER
               umma_commit(&pv_done[s]);
@@ -397,9 +399,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const int hh = (idx >> 2) & 1;          // key-column half owned by this thread
     const int quarter = warp & 3;           // TMEM lane quarter (hardware rule: warp % 4)
     const int row_in_tile = quarter * 32 + lane;
-    constexpr int NCH = KB / 32;            // 16-key chunks per thread and block: chunks 2 ch + hh of the block
+    constexpr int HALF = KB / 2;            // keys per half and block: HALF/16 chunks of 16
+    constexpr int NCH = HALF / 16;
     const uint32_t t_slot = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * 256);
-    const uint32_t t_mine = t_slot + (uint32_t)(hh * 16);      // chunk ch of this thread: columns [t_mine + 32 ch, + 16)
+    const uint32_t t_mine = t_slot + (uint32_t)(hh * HALF);
     const float c = 0.125f * 1.4426950408889634f;  // dh^-0.5 * log2(e)
     KeyMask km;
     km.v0 = p.N0; km.v1 = p.kb_live; km.v2 = p.kb_live + 8 + p.T; km.v3 = p.kb_live + 8 + p.t_pad;
@@ -459,9 +462,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           }
           uint32_t va[16], vb[16];
           tmem_ld_32x16(t_mine, va);
-          const int kbase = blk * KB + hh * 16;      // smem key row of this thread's first column
+          const int kbase = blk * KB + hh * HALF;    // smem key row of this thread's first column
           if (blk == 0) {
-            // the row's shift: maximum of the first 32 scores, 16 per thread (key 0, the cls token, is always valid)
+            // the row's shift: maximum of the first 16 scores of each key half (key 0, the cls token, is always valid)
             tmem_ld_wait();
             float mx = chunk16_max(va);
             *my_max = mx;
@@ -481,32 +484,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #if GAVA_ATTN_DEBUG
           const long long t_exp0 = clock64();
 #endif
-          int n_live = (km.v3 + 32 - kbase) >> 5;       // own chunks that hold at least one valid key (the rest: P = 0, no exps)
+          int n_live = (km.v3 + 16 - kbase) >> 4;       // chunks that hold at least one valid key (the rest: P = 0, no exps)
           n_live = n_live < 0 ? 0 : (n_live > NCH ? NCH : n_live);
           int ch = 0;
 #pragma unroll 1
           for (; ch + 2 <= n_live; ch += 2) {           // branch-free body, two chunks per trip: the TMEM load of one
             uint32_t pk[8];                             // overlaps the exps of the other
             tmem_ld_wait();
-            tmem_ld_32x16(t_mine + (uint32_t)((ch + 1) * 32), vb);
+            tmem_ld_32x16(t_mine + (uint32_t)((ch + 1) * 16), vb);
             sum += chunk16_exp(va, pk, c, mc);
-            tmem_st_32x8(t_mine + (uint32_t)(ch * 32), pk);
+            tmem_st_32x8(t_mine + (uint32_t)(ch * 8), pk);
             tmem_ld_wait();
-            if (ch + 2 < n_live) tmem_ld_32x16(t_mine + (uint32_t)((ch + 2) * 32), va);
+            if (ch + 2 < n_live) tmem_ld_32x16(t_mine + (uint32_t)((ch + 2) * 16), va);
             sum += chunk16_exp(vb, pk, c, mc);
-            tmem_st_32x8(t_mine + (uint32_t)((ch + 1) * 32), pk);
+            tmem_st_32x8(t_mine + (uint32_t)((ch + 1) * 8), pk);
           }
           tmem_ld_wait();
           if (ch < n_live) {                            // the odd chunk out
             uint32_t pk[8];
             sum += chunk16_exp(va, pk, c, mc);
-            tmem_st_32x8(t_mine + (uint32_t)(ch * 32), pk);
+            tmem_st_32x8(t_mine + (uint32_t)(ch * 8), pk);
             ++ch;
           }
 #pragma unroll 1
           for (; ch < NCH; ++ch) {
             const uint32_t zz[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-            tmem_st_32x8(t_mine + (uint32_t)(ch * 32), zz);
+            tmem_st_32x8(t_mine + (uint32_t)(ch * 8), zz);
           }
           mbar_arrive(&turn[s ^ 1]);          // exp pass done: the other group's turn
           if (blk == NB - 1) *my_sum = sum;
