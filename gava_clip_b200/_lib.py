@@ -76,8 +76,7 @@ SIGNATURES = {
     "gava_prompt_rows_f32_fwd": [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p],
     "gava_layernorm_bwd": [_p, _i64, _i32, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _f32, _p],
     "gava_attention_train_fwd": [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p],
-    "gava_attention_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _p],
-    "gava_attention_bwd_scratch_floats": [_i32, _i32, _i32, _i32, _i32],
+    "gava_attention_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p],
     "gava_temporal_attention_bwd": [_p, _p, _p, _i32, _i32, _i32, _p],
     "gava_causal_attention_bwd": [_p, _p, _p, _i32, _i32, _i32, _p],
     "gava_prompt_rows_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p],
@@ -88,8 +87,7 @@ SIGNATURES = {
                                C.POINTER(C.c_float), C.POINTER(C.c_float), _p],
     "gava_adamw_step": [_p, _p, _p, _p, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _p],
 }
-_RESTYPES = {"gava_last_error_string": C.c_char_p, "gava_workspace_bytes": C.c_int64,
-             "gava_attention_bwd_scratch_floats": C.c_int64}
+_RESTYPES = {"gava_last_error_string": C.c_char_p, "gava_workspace_bytes": C.c_int64}
 
 _lib = None
 

@@ -182,14 +182,9 @@ int gava_layernorm_bwd(const void* dy, int64_t dy_stride, int32_t dy_bf16, const
 }
 
 int gava_attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, const float* lse,
-                       void* dqkv, float* dkv_aux, float* scratch, int64_t scratch_floats, int32_t B, int32_t T, int32_t N0,
-                       int32_t G, int32_t H, int32_t n_q, void* stream) {
-  return attention_bwd(qkv, kv_aux, out, dout, lse, dqkv, dkv_aux, scratch, scratch_floats, B, T, N0, G, H, n_q,
-                       (cudaStream_t)stream);
-}
-
-int64_t gava_attention_bwd_scratch_floats(int32_t B, int32_t T, int32_t N0, int32_t G, int32_t H) {
-  return attention_bwd_scratch_floats(B, T, N0, G, H);
+                       void* dqkv, float* dkv_aux, float* scratch, int32_t B, int32_t T, int32_t N0, int32_t G, int32_t H,
+                       int32_t n_q, void* stream) {
+  return attention_bwd(qkv, kv_aux, out, dout, lse, dqkv, dkv_aux, scratch, B, T, N0, G, H, n_q, (cudaStream_t)stream);
 }
 
 int gava_temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int32_t B, int32_t T, int32_t H,

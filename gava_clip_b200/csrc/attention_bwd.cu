@@ -19,7 +19,6 @@
 // (GAVA_AB_WARPS=8) is slower (1.08 ms), see DESIGN.md.
 //
 // Restates autograd of Attention.forward core, training/VitaCLIP_vision_encoder_utils.py:71-77.
-#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 #include "mma_sync.cuh"
@@ -37,7 +36,6 @@ struct AttnBwdArgs {
   float* scratch;               // optional [BT, H, G+T+1, 128]: per-(frame, head) prompt-row gradients, reduced by a 2nd kernel
   int T, N0, G, H, S, BT, q_pad, s_pad;
   int n_q;   // query rows per frame that carry a gradient (N0, or 1 in the last layer: only the cls row reaches the output)
-  int skip_dq;   // 1: dq comes from the tcgen05 kernel (attention_bwd_tc.cu); only the key-tile units (dK, dV) run here
 };
 
 #ifndef GAVA_AB_WARPS
@@ -191,7 +189,7 @@ __global__ void __launch_bounds__(32 * AB_WARPS, AB_WARPS > 4 ? 2 : 2) attention
 
   // =========================================================== work units: 16-query tiles (dQ) and 16-key tiles (dK, dV),
   // independent of each other once lse / delta are in shared memory: dealt round-robin to the warps
-  for (int u = (p.skip_dq ? n_qt : 0) + warp; u < n_qt + n_kt; u += AB_WARPS) {
+  for (int u = warp; u < n_qt + n_kt; u += AB_WARPS) {
   if (u < n_qt) {
     const int mt = u;
     uint32_t qf[4][4], dof[4][4];
@@ -393,13 +391,8 @@ __global__ void __launch_bounds__(1024) attention_bwd_reduce_kernel(const float*
   dkv_aux[(long long)arow * 2 * D + (c < 64 ? h * 64 + c : D + h * 64 + (c - 64))] = v;
 }
 
-long long attention_bwd_scratch_floats(int B, int T, int N0, int G, int H) {
-  return (long long)B * T * H * ((long long)(G + T + 1) * 128 + N0);      // prompt-row slots | <dO, O> rows
-}
-
 int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, const float* lse, void* dqkv,
-                  float* dkv_aux, float* scratch, long long scratch_floats, int B, int T, int N0, int G, int H, int n_q,
-                  cudaStream_t stream) {
+                  float* dkv_aux, float* scratch, int B, int T, int N0, int G, int H, int n_q, cudaStream_t stream) {
   if (!qkv || !kv_aux || !out || !dout || !dqkv || !dkv_aux || B <= 0 || T <= 0 || N0 <= 0 || G < 0 || H <= 0 || n_q <= 0 ||
       n_q > N0) {
     set_error("attention_bwd: bad arguments");
@@ -417,11 +410,6 @@ int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const vo
   a.T = T; a.N0 = N0; a.G = G; a.H = H; a.BT = B * T;
   a.S = N0 + G + T + 1;
   a.n_q = n_q;
-  // dq on the tcgen05 kernel when the forward's lse rows exist, the shape fits and the workspace has room for <dO, O>
-  static const bool allow_tc = [] { const char* e = getenv("GAVA_ATTN_BWD_TC"); return e && e[0] == '1'; }();   // opt-in until validated
-  const long long slots = (long long)B * T * H * (long long)(G + T + 1) * 128;
-  a.skip_dq = (allow_tc && lse != nullptr && scratch != nullptr && n_q == N0 && attention_bwd_tc_supported(T, N0, G, n_q) &&
-               scratch_floats >= slots + (long long)B * T * H * N0) ? 1 : 0;
   a.q_pad = (n_q + 15) / 16 * 16;
   a.s_pad = (a.S + 15) / 16 * 16;
   const size_t smem_bytes = (size_t)(2 * a.q_pad + 2 * a.s_pad) * 128 + (size_t)a.q_pad * 8;
@@ -438,13 +426,6 @@ int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const vo
   if (scratch == nullptr) {   // atomics path: accumulate straight into dkv_aux
     cudaError_t e = cudaMemsetAsync(dkv_aux, 0, sizeof(float) * (size_t)(G + 2 * B * T) * 2 * D, stream);
     if (e != cudaSuccess) { set_error("attention_bwd memset: %s", cudaGetErrorString(e)); return (int)e; }
-  }
-  if (a.skip_dq) {
-    float* delta = scratch + slots;
-    int rc = attention_bwd_delta(out, dout, delta, B, T, N0, H, n_q, stream);
-    if (rc) return rc;
-    rc = attention_bwd_dq_tc(qkv, kv_aux, dout, lse, delta, dqkv, B, T, N0, G, H, n_q, stream);
-    if (rc) return rc;
   }
   if (lse) attention_bwd_kernel<true><<<dim3(H, B * T), 32 * AB_WARPS, smem_bytes, stream>>>(a);
   else attention_bwd_kernel<false><<<dim3(H, B * T), 32 * AB_WARPS, smem_bytes, stream>>>(a);

@@ -424,15 +424,9 @@ def attention_bwd(qkv: Tensor, kv_aux: Tensor, out: Tensor, dout: Tensor, dqkv: 
         _req(scratch, torch.float32, "attention_bwd scratch")
         assert scratch.is_contiguous() and scratch.numel() >= B * T * H * (G + T + 1) * 128
     rc = _lib.load().gava_attention_bwd(qkv.data_ptr(), kv_aux.data_ptr(), out.data_ptr(), dout.data_ptr(), _ptr(lse),
-                                        dqkv.data_ptr(), dkv_aux.data_ptr(), _ptr(scratch),
-                                        0 if scratch is None else scratch.numel(), B, T, N0, G, H,
+                                        dqkv.data_ptr(), dkv_aux.data_ptr(), _ptr(scratch), B, T, N0, G, H,
                                         N0 if n_q is None else n_q, _stream())
     _lib.check(rc, "gava_attention_bwd")
-
-
-def attention_bwd_scratch_floats(B: int, T: int, N0: int, G: int, H: int) -> int:
-    """f32 elements of `scratch` that let attention_bwd take its fastest path (prompt-row slots + <dO, O> rows)."""
-    return int(_lib.load().gava_attention_bwd_scratch_floats(B, T, N0, G, H))
 
 
 def temporal_attention_bwd(qkv: Tensor, dout: Tensor, dqkv: Tensor, B: int, T: int, H: int) -> Tensor:

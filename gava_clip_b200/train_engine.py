@@ -142,7 +142,7 @@ class TowerTrainer(TowerEngine):
             # ---- backward scratch
             "dx": z(M, D, dt=f32), "dxb": z(M, D, dt=bf), "g4": z(M, Dm, dt=bf), "gD": z(M, D, dt=bf),
             "dqkv": z(M, 3 * D, dt=bf), "dkvaux": z(R, 2 * D, dt=f32),
-            "dkv_slots": z(ops.attention_bwd_scratch_floats(B, T, N0, G, e.num_heads), dt=f32), "dkvaux_bf": z(R, 2 * D, dt=bf),
+            "dkv_slots": z(BT * e.num_heads * (G + T + 1) * 128, dt=f32), "dkvaux_bf": z(R, 2 * D, dt=bf),
             "daux_n": z(R, D, dt=bf), "d_lcp": z(BT, D, dt=f32), "d_sum": z(BT, D, dt=f32), "d_sum_bf": z(BT, D, dt=bf),
             "dsmix": z(BT, D, dt=bf), "dsqkv": z(BT, 3 * D, dt=bf), "dsn": z(BT, D, dt=bf), "d_cp": z(BT, D, dt=f32),
             "d_cp_bf": z(BT, D, dt=bf), "tA": z(3 * D, BTp, dt=bf), "tB": z(D, BTp, dt=bf),

@@ -225,17 +225,12 @@ int gava_attention_train_fwd(const void* qkv, const void* kv_aux, void* out, flo
  * out/dout: bf16 [B*T*N0, D] forward output and its gradient (rows >= n_q of a frame are not read).
  * lse: the rows saved by gava_attention_train_fwd, or NULL (recomputed inside, one more pass over the keys).
  * dqkv: bf16 [B*T*N0, 3D] = [dq | dk | dv] of the live rows; dkv_aux: f32 [G + 2*B*T, 2D] = [dk | dv] of the K/V-only rows
- * (global rows collect all frames, local rows the T frames of a video).  scratch: f32 workspace of scratch_floats elements.
- * Its first B*T*H*(G+T+1)*128 floats are per-(frame, head) slots: every (frame, head) writes its prompt-row contributions
- * to its own slot and a second kernel sums the slots in a fixed order (reproducible); scratch == NULL: f32 atomics straight
- * into dkv_aux (order-dependent rounding).  With lse given and scratch_floats >= gava_attention_bwd_scratch_floats(...)
- * the tail holds the <dO, O> rows and dq is computed by the tcgen05 kernel (shapes with <= 288 smem key rows); otherwise
- * the mma.sync kernel computes everything. */
+ * (global rows collect all frames, local rows the T frames of a video).  scratch: f32 [B*T, H, G+T+1, 128] workspace: every
+ * (frame, head) writes its prompt-row contributions to its own slot and a second kernel sums the slots in a fixed order
+ * (reproducible); scratch == NULL: f32 atomics straight into dkv_aux (order-dependent rounding). */
 int gava_attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, const float* lse,
-                       void* dqkv, float* dkv_aux, float* scratch, int64_t scratch_floats, int32_t B, int32_t T, int32_t N0,
-                       int32_t G, int32_t H, int32_t n_q, void* stream);
-/* floats of scratch that let gava_attention_bwd take its fastest path for this shape */
-int64_t gava_attention_bwd_scratch_floats(int32_t B, int32_t T, int32_t N0, int32_t G, int32_t H);
+                       void* dqkv, float* dkv_aux, float* scratch, int32_t B, int32_t T, int32_t N0, int32_t G, int32_t H,
+                       int32_t n_q, void* stream);
 
 /* Backward of gava_temporal_attention_fwd: qkv bf16 [B*T, 3D], dout bf16 [B*T, D] -> dqkv bf16 [B*T, 3D].  T <= 128. */
 int gava_temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int32_t B, int32_t T, int32_t H,
