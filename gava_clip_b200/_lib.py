@@ -17,7 +17,6 @@ EPI_BIAS_RESID_F32 = 2
 EPI_BIAS_F32 = 3
 EPI_PATCH_F32 = 4
 EPI_DGELU_BF16 = 5
-EPI_BIAS_RESID_LN_F32 = 6
 
 
 class GemmEpilogue(C.Structure):
@@ -39,11 +38,6 @@ class GemmEpilogue(C.Structure):
         ("ld_aux", C.c_int64),
         ("aux_out", C.c_void_p),
         ("max_ctas", C.c_int32),
-        ("ln_eps", C.c_float),
-        ("ln_weight", C.c_void_p),
-        ("ln_bias", C.c_void_p),
-        ("ln_out", C.c_void_p),
-        ("ln_ldo", C.c_int64),
     ]
 
 
@@ -107,8 +101,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing -> loud
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.gava_version() != 2:
-        raise RuntimeError(f"libgava_sm100 ABI version {lib.gava_version()} != 2")
+    if lib.gava_version() != 3:
+        raise RuntimeError(f"libgava_sm100 ABI version {lib.gava_version()} != 3")
     _lib = lib
     return lib
 

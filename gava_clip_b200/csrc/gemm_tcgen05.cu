@@ -55,13 +55,6 @@ struct GemmArgs {
   const __nv_bfloat16* aux;  // EPI_DGELU_BF16: fc1 pre-activations bf16 [M, ld_aux]
   __nv_bfloat16* aux_out;    // EPI_BIAS_GELU_BF16 (optional): also store the pre-activations acc + bias here, pitch ld_aux
   long long ld_aux;
-  // EPI_BIAS_RESID_LN_F32: LayerNorm tail over the freshly written rows (next layer's norm1 fused behind fc2)
-  const float* ln_w;
-  const float* ln_b;
-  __nv_bfloat16* ln_out;
-  long long ln_ldo;
-  float ln_eps;
-  int grouped_rounds;        // rounds in which a cluster owns ALL N tiles of an M block (then tile-granular remainder)
 };
 
 // ---- epilogue: TMEM -> registers (one row per thread) -> swizzled smem staging -> transposed, coalesced global access.
@@ -144,7 +137,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
       float4 a = *reinterpret_cast<const float4*>(stage + r * 128 + ((c ^ (r & 7)) << 4));
       a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
       if (grow < p.M) {
-        if constexpr (MODE == EPI_BIAS_RESID_F32 || MODE == EPI_BIAS_RESID_LN_F32) {
+        if constexpr (MODE == EPI_BIAS_RESID_F32) {
           a.x += resid[i].x; a.y += resid[i].y; a.z += resid[i].z; a.w += resid[i].w;
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)grow * p.ldo + col) = a;
         } else if constexpr (MODE == EPI_BIAS_F32) {
@@ -211,7 +204,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage,
     for (int cc = 0; cc < NCH; ++cc) {
       const int col0 = col_base + cc * 32;
       float4 resid[8];
-      if constexpr (MODE == EPI_BIAS_RESID_F32 || MODE == EPI_BIAS_RESID_LN_F32) {  // coalesced residual loads, in flight while TMEM is read
+      if constexpr (MODE == EPI_BIAS_RESID_F32) {  // coalesced residual loads, in flight while TMEM is read
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int grow = row0 + 4 * i + (lane >> 3);
@@ -412,27 +405,12 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const int num_tiles = num_m * num_n;
   const int num_kb = p.K / BK;
   const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
-  // Work enumeration of this cluster: iteration `it` -> (m_blk, n_blk).  First `grouped_rounds` rounds in which the cluster
-  // owns every N tile of one M block (so the LayerNorm tail can run as soon as the block's rows are complete), then the
-  // remaining M blocks tile by tile.  grouped_rounds == 0 (every mode but RESID_LN) is the plain round-robin over tiles.
-  constexpr bool kLnTail = (MODE == EPI_BIAS_RESID_LN_F32);
-  const int rounds_g = kLnTail ? p.grouped_rounds : 0;
-  const int grouped_iters = rounds_g * num_n;
-  const int rem_tiles = num_tiles - rounds_g * num_clusters * num_n;
-  auto tile_at = [&](int it, int& m_blk, int& n_blk, bool& tail) -> bool {
-    if (it < grouped_iters) {
-      const int r = it / num_n;
-      n_blk = it - r * num_n;
-      m_blk = r * num_clusters + cluster_id;
-      tail = (n_blk == num_n - 1);
-      return true;
-    }
-    const int t = cluster_id + (it - grouped_iters) * num_clusters;
-    if (t >= rem_tiles) return false;
-    const int mb = t / num_n;
-    n_blk = t - mb * num_n;
-    m_blk = rounds_g * num_clusters + mb;
-    tail = false;
+  // Work enumeration of this cluster: iteration `it` -> tile cluster_id + it * num_clusters (round-robin over the tiles)
+  auto tile_at = [&](int it, int& m_blk, int& n_blk) -> bool {
+    const int t = cluster_id + it * num_clusters;
+    if (t >= num_tiles) return false;
+    m_blk = t / num_n;
+    n_blk = t - m_blk * num_n;
     return true;
   };
 
@@ -463,8 +441,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       int m_blk, n_blk;
-      bool tail;
-      for (int it = 0; tile_at(it, m_blk, n_blk, tail); ++it) {
+      for (int it = 0; tile_at(it, m_blk, n_blk); ++it) {
         const int row_a = m_blk * 2 * BM + (int)rank * BM;
         const int row_b = n_blk * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -493,8 +470,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       long long w_empty = 0, w_full = 0, t_start = clock64();
 #endif
       int m_blk_, n_blk_;
-      bool tail_;
-      for (int it = 0; tile_at(it, m_blk_, n_blk_, tail_); ++it) {
+      for (int it = 0; tile_at(it, m_blk_, n_blk_); ++it) {
 #if GAVA_GEMM_DEBUG == 4
         long long t0 = clock64();
 #endif
@@ -546,8 +522,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #endif
     long long g_dbg_wait = 0;
     int m_blk, n_blk;
-    bool tail;
-    for (int it = 0; tile_at(it, m_blk, n_blk, tail); ++it) {
+    for (int it = 0; tile_at(it, m_blk, n_blk); ++it) {
       const int row0 = m_blk * 2 * BM + (int)rank * BM + quarter * 32;
       const int col_base = n_blk * BN + half * kChunksPerWarp * 32;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * kChunksPerWarp * 32);
@@ -557,37 +532,6 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // tell the leader this warp drained its part
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
-      if constexpr (kLnTail) {
-        if (tail) {
-          // Every column tile of this CTA's 128 rows has been written by its own epilogue warps: normalise the rows now,
-          // while they are still in L2 (the separate LayerNorm launch would re-read them from HBM).  The MMA warp is
-          // already filling the other accumulator stage; a K = 3072 mainloop (27 us per tile) hides this ~4 us tail.
-          asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-#if GAVA_GEMM_DEBUG == 7   // experiment: grouped tile order without the tail's work
-          continue;
-#endif
-          const long long rbase = (long long)m_blk * 2 * BM + (long long)rank * BM;
-          for (int r = ew; r < BM; r += EPI_WARPS) {
-            const long long row = rbase + r;
-            if (row >= p.M) break;
-            const float* xrow = reinterpret_cast<const float*>(p.out) + row * p.ldo;
-            __nv_bfloat16* orow = p.ln_out + row * p.ln_ldo;
-            if (p.N == 768) {
-              float4 v[6];
-#pragma unroll
-              for (int j = 0; j < 6; ++j) v[j] = reinterpret_cast<const float4*>(xrow)[lane + 32 * j];
-              ln_normalize<6>(v, p.ln_w, p.ln_b, p.ln_eps);
-              store_row<6>(v, orow, 1);
-            } else {   // N == 1024 (checked on the host)
-              float4 v[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) v[j] = reinterpret_cast<const float4*>(xrow)[lane + 32 * j];
-              ln_normalize<8>(v, p.ln_w, p.ln_b, p.ln_eps);
-              store_row<8>(v, orow, 1);
-            }
-          }
-        }
-      }
     }
 #if GAVA_GEMM_DEBUG == 4
     if ((blockIdx.x == 0 || blockIdx.x == 65) && lane == 0 && (ew == 0 || ew == 7))
@@ -710,19 +654,6 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
   int max_clusters = num_sms() / 2;
   if (max_ctas > 1 && max_ctas / 2 < max_clusters) max_clusters = max_ctas / 2;   // leave SMs to a concurrent stream
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  if constexpr (MODE == EPI_BIAS_RESID_LN_F32) {
-    GemmArgs a2 = args;
-    const int num_m = (args.M + 2 * BM - 1) / (2 * BM);
-    a2.grouped_rounds = num_m / clusters;          // whole M blocks per cluster; the rest goes tile by tile
-    kern<<<2 * clusters, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, a2);
-    int rc = check_launch("gemm2_tcgen05");
-    if (rc) return rc;
-    // rows of the tile-granular remainder did not get the in-kernel tail: one ordinary LayerNorm launch over them
-    const long long row0 = (long long)a2.grouped_rounds * clusters * 2 * BM;
-    if (row0 >= args.M) return GAVA_OK;
-    return layernorm(reinterpret_cast<const float*>(args.out) + row0 * args.ldo, args.ldo, args.ln_w, args.ln_b,
-                     args.ln_out + row0 * args.ln_ldo, args.ln_ldo, 1, args.M - row0, args.N, args.ln_eps, stream);
-  }
   kern<<<2 * clusters, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, args);
   return check_launch("gemm2_tcgen05");
 }
@@ -735,7 +666,6 @@ static int dispatch_mode2(int mode, const CUtensorMap& ta, const CUtensorMap& tb
     case EPI_BIAS_F32: return launch_gemm2<EPI_BIAS_F32>(ta, tb, a, s);
     case EPI_PATCH_F32: return launch_gemm2<EPI_PATCH_F32>(ta, tb, a, s);
     case EPI_DGELU_BF16: return launch_gemm2<EPI_DGELU_BF16>(ta, tb, a, s);
-    case EPI_BIAS_RESID_LN_F32: return launch_gemm2<EPI_BIAS_RESID_LN_F32>(ta, tb, a, s);
   }
   set_error("gemm: unknown epilogue mode %d", mode);
   return GAVA_ERR_ARG;
@@ -762,12 +692,7 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
     set_error("gemm: unsupported shape M=%lld N=%lld K=%lld (need K%%64==0, N%%128==0)", M, N, K);
     return GAVA_ERR_SHAPE;
   }
-  if ((epi->mode == EPI_BIAS_RESID_F32 || epi->mode == EPI_BIAS_RESID_LN_F32) && !epi->resid) { set_error("gemm: residual epilogue without resid"); return GAVA_ERR_ARG; }
-  if (epi->mode == EPI_BIAS_RESID_LN_F32 &&
-      (!epi->ln_weight || !epi->ln_bias || !epi->ln_out || (N != 768 && N != 1024) || (epi->ln_ldo & 3) || M <= 2048)) {
-    set_error("gemm: RESID_LN epilogue needs ln_weight/ln_bias/ln_out, N in {768, 1024} and the CTA-pair path (M > 2048)");
-    return GAVA_ERR_ARG;
-  }
+  if (epi->mode == EPI_BIAS_RESID_F32 && !epi->resid) { set_error("gemm: residual epilogue without resid"); return GAVA_ERR_ARG; }
   if (epi->mode == EPI_PATCH_F32 && (!epi->pos || !epi->time_embed || epi->group <= 0 || epi->T <= 0)) {
     set_error("gemm: patch epilogue needs pos/time_embed/group/T");
     return GAVA_ERR_ARG;
@@ -792,11 +717,9 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
   a.out = epi->out; a.ldo = epi->ldo;
   a.group = epi->group; a.group_stride = epi->group_stride; a.row_offset = epi->row_offset;
   a.pos = epi->pos; a.time_embed = epi->time_embed; a.T = epi->T;
-  a.aux = (epi->mode == EPI_DGELU_BF16 || epi->mode == EPI_BIAS_RESID_F32 || epi->mode == EPI_BIAS_RESID_LN_F32) ? reinterpret_cast<const __nv_bfloat16*>(epi->aux) : nullptr;
+  a.aux = (epi->mode == EPI_DGELU_BF16 || epi->mode == EPI_BIAS_RESID_F32) ? reinterpret_cast<const __nv_bfloat16*>(epi->aux) : nullptr;
   a.ld_aux = epi->ld_aux;
   a.aux_out = epi->mode == EPI_BIAS_GELU_BF16 ? reinterpret_cast<__nv_bfloat16*>(epi->aux_out) : nullptr;
-  a.ln_w = epi->ln_weight; a.ln_b = epi->ln_bias; a.ln_out = reinterpret_cast<__nv_bfloat16*>(epi->ln_out);
-  a.ln_ldo = epi->ln_ldo; a.ln_eps = epi->ln_eps; a.grouped_rounds = 0;
   if (pair) return dispatch_mode2(epi->mode, ta, tb, a, stream, epi->max_ctas);
   return bn_eff == 256 ? dispatch_mode<256>(epi->mode, ta, tb, a, stream) : dispatch_mode<128>(epi->mode, ta, tb, a, stream);
 }

@@ -14,7 +14,6 @@ enum : int {
   EPI_BIAS_F32 = GAVA_EPI_BIAS_F32,
   EPI_PATCH_F32 = GAVA_EPI_PATCH_F32,
   EPI_DGELU_BF16 = GAVA_EPI_DGELU_BF16,
-  EPI_BIAS_RESID_LN_F32 = GAVA_EPI_BIAS_RESID_LN_F32,
 };
 
 int num_sms();         // of the CURRENT device

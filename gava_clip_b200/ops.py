@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_BIAS_RESID_LN_F32,
+from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32,
                    EPI_DGELU_BF16, EPI_PATCH_F32, GemmEpilogue)
 
 Tensor = torch.Tensor
@@ -51,8 +51,7 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
 def gemm(a: Tensor, w: Tensor, out: Tensor, *, mode: int, bias: Optional[Tensor] = None,
          resid: Optional[Tensor] = None, pos: Optional[Tensor] = None, time_embed: Optional[Tensor] = None,
          group: int = 0, group_stride: int = 0, row_offset: int = 0, T: int = 0, aux: Optional[Tensor] = None,
-         aux_out: Optional[Tensor] = None, max_ctas: int = 0, ln_weight: Optional[Tensor] = None,
-         ln_bias: Optional[Tensor] = None, ln_out: Optional[Tensor] = None, ln_eps: float = 1e-5) -> Tensor:
+         aux_out: Optional[Tensor] = None, max_ctas: int = 0) -> Tensor:
     """out = epilogue(a @ w.T).  a: bf16 [M,K] (row stride free), w: bf16 [N,K], fp32 bias [N]."""
     _req(a, torch.bfloat16, "gemm a"); _req(w, torch.bfloat16, "gemm w")
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
@@ -70,7 +69,7 @@ def gemm(a: Tensor, w: Tensor, out: Tensor, *, mode: int, bias: Optional[Tensor]
     epi.out = out.data_ptr()
     epi.ldo = out.stride(0)
     epi.max_ctas = max_ctas
-    if mode in (EPI_BIAS_RESID_F32, EPI_BIAS_RESID_LN_F32):
+    if mode == EPI_BIAS_RESID_F32:
         _req(resid, torch.float32, "gemm resid")
         assert resid.dim() == 2 and resid.stride(1) == 1 and resid.shape[0] >= M
         epi.resid = resid.data_ptr(); epi.ldr = resid.stride(0)
@@ -92,14 +91,6 @@ def gemm(a: Tensor, w: Tensor, out: Tensor, *, mode: int, bias: Optional[Tensor]
         epi.aux = aux.data_ptr(); epi.ld_aux = aux.stride(0)
     else:
         assert out.shape[0] >= M
-    if mode == EPI_BIAS_RESID_LN_F32:   # LayerNorm of the finished rows as a tail of the GEMM (next block's norm1 behind fc2)
-        _req(ln_weight, torch.float32, "gemm ln_weight"); _req(ln_bias, torch.float32, "gemm ln_bias")
-        _req(ln_out, torch.bfloat16, "gemm ln_out")
-        assert ln_weight.numel() == N and ln_bias.numel() == N and ln_weight.is_contiguous() and ln_bias.is_contiguous()
-        assert ln_out.dim() == 2 and ln_out.stride(1) == 1 and ln_out.shape[0] >= M and ln_out.shape[1] >= N
-        assert out.stride(0) == N, "the tail reads whole rows of `out`"
-        epi.ln_weight, epi.ln_bias, epi.ln_out = ln_weight.data_ptr(), ln_bias.data_ptr(), ln_out.data_ptr()
-        epi.ln_ldo, epi.ln_eps = ln_out.stride(0), ln_eps
     if aux_out is not None:      # GELU epilogue of the training forward: keep the pre-activations too
         assert mode == EPI_BIAS_GELU_BF16
         _req(aux_out, torch.bfloat16, "gemm aux_out")

@@ -148,9 +148,6 @@ class TowerEngine:
         # which made that K=768 GEMM HBM-bound), norm2 normalises x + delta, and the fc2 epilogue -- hidden under a K=3072
         # mainloop -- adds delta together with the MLP output.  Same bytes overall, but none of them on a critical path.
         self.defer_resid = os.environ.get("GAVA_DEFER_RESID", "1") != "0"
-        # norm1 of block i+1 as a tail of block i's fc2 GEMM (GAVA_EPI_BIAS_RESID_LN_F32): the rows are normalised while they
-        # are still in L2 instead of being re-read from HBM by a separate LayerNorm launch
-        self.ln_tail = os.environ.get("GAVA_LN_TAIL", "0") == "1"
         self.side_stream = torch.cuda.Stream(device) if device.type == "cuda" else None
         self.launches_last_call = 0      # sm_100a kernels launched (or replayed) by the last run()
         # parity instrument (tests): a dict here receives, per layer, clones of the cls rows of the residual stream and of the
@@ -411,7 +408,7 @@ class TowerEngine:
         L = len(e.blocks)
         main = torch.cuda.current_stream(self.device)
         side = self.side_stream if self.overlap_chain else None
-        norm1_done = True       # True when xn already holds norm1(x) of the coming block (here; or the fc2 LayerNorm tail)
+        norm1_done = True       # True when xn already holds norm1(x) of the coming block (block 0: done by the ln_pre pass)
         for i in range(L):
             k = f"b{i}."
             # ---- temporal message: cls_proj -> summary attention -> K/V-only prompt rows   utils.py:160-188
@@ -452,13 +449,7 @@ class TowerEngine:
                     # ---- x = (x + delta) + fc2(QuickGELU(fc1(norm2(x + delta))))              utils.py:191,199
                     ops.layernorm(x, P[k + "norm2.w"], P[k + "norm2.b"], xn, rows=M, in_row_stride=D, delta=dl)
                     ops.gemm(xn, P[k + "fc1.w"], h, mode=ops.EPI_BIAS_GELU_BF16, bias=P[k + "fc1.b"])
-                    if self.ln_tail and D in (768, 1024) and M > 2048:
-                        kn = f"b{i + 1}."
-                        ops.gemm(h, P[k + "fc2.w"], x, mode=ops.EPI_BIAS_RESID_LN_F32, bias=P[k + "fc2.b"], resid=x, aux=dl,
-                                 ln_weight=P[kn + "norm1.w"], ln_bias=P[kn + "norm1.b"], ln_out=xn, ln_eps=LN_EPS)
-                        norm1_done = True
-                    else:
-                        ops.gemm(h, P[k + "fc2.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"], resid=x, aux=dl)
+                    ops.gemm(h, P[k + "fc2.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"], resid=x, aux=dl)
                 else:
                     ops.gemm(xn, P[k + "out.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "out.b"], resid=x)
                     # ---- x = x + fc2(QuickGELU(fc1(norm2(x))))                                    utils.py:199

@@ -21,15 +21,14 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(lib, s), f"{s} declared in include/gava_sm100.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in gava_clip_b200/_lib.py"
     assert sorted(_lib.SIGNATURES) == syms
-    assert lib.gava_version() == 2
+    assert lib.gava_version() == 3
 
 
 def test_epilogue_struct_layout():
     from gava_clip_b200._lib import GemmEpilogue
     # int32 mode (+4 pad), 2 ptr, i64, ptr, i64, 4 x i32, 2 ptr, ptr, i64, ptr  -> 104 bytes on LP64
-    assert ctypes.sizeof(GemmEpilogue) == 144 and GemmEpilogue.aux.offset == 80 and GemmEpilogue.aux_out.offset == 96
-    assert GemmEpilogue.max_ctas.offset == 104 and GemmEpilogue.ln_eps.offset == 108 and GemmEpilogue.ln_weight.offset == 112
-    assert GemmEpilogue.ln_ldo.offset == 136
+    assert ctypes.sizeof(GemmEpilogue) == 112 and GemmEpilogue.aux.offset == 80 and GemmEpilogue.aux_out.offset == 96
+    assert GemmEpilogue.max_ctas.offset == 104
     assert GemmEpilogue.out.offset == 32 and GemmEpilogue.group.offset == 48 and GemmEpilogue.pos.offset == 64
 
 

@@ -422,28 +422,6 @@ def test_deferred_residual_pair(cuda):
     assert _rel(x, want) < 2e-5
 
 
-@pytest.mark.parametrize("M,N,K", [(100864, 768, 3072), (30000, 1024, 512), (2049, 768, 64)])
-def test_gemm_resid_with_layernorm_tail(cuda, M, N, K):
-    """GAVA_EPI_BIAS_RESID_LN_F32: out = resid + aux + a w^T + bias, then ln_out = LayerNorm(out) produced inside the GEMM
-    (M-block-grouped rounds) plus the ordinary LayerNorm launch over the tile-granular remainder rows."""
-    from gava_clip_b200 import ops
-    g = torch.Generator(device="cuda").manual_seed(M + N)
-    a = torch.randn(M, K, device=cuda, generator=g).bfloat16()
-    w = (torch.randn(N, K, device=cuda, generator=g) * K ** -0.5).bfloat16()
-    bias = torch.randn(N, device=cuda, generator=g)
-    x = torch.randn(M, N, device=cuda, generator=g)
-    delta = torch.randn(M, N, device=cuda, generator=g).bfloat16()
-    lw = torch.randn(N, device=cuda, generator=g); lb = torch.randn(N, device=cuda, generator=g)
-    want = x + delta.float() + a.float() @ w.float().t() + bias
-    xn = torch.full((M, N), float("nan"), device=cuda, dtype=torch.bfloat16)
-    ops.gemm(a, w, x, mode=ops.EPI_BIAS_RESID_LN_F32, bias=bias, resid=x, aux=delta, ln_weight=lw, ln_bias=lb, ln_out=xn)
-    assert _rel(x, want) < 2e-5
-    ref = F.layer_norm(x, (N,), lw, lb, 1e-5)          # LayerNorm of the tensor the GEMM actually wrote
-    assert torch.isfinite(xn.float()).all()
-    assert _rel(xn.float(), ref) < 1e-2
-    assert torch.equal(xn, ref.bfloat16()) or float((xn.float() - ref).abs().max()) < 0.05
-
-
 def test_layernorm2_two_stage(cuda):
     from gava_clip_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(31)
