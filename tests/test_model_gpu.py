@@ -34,6 +34,9 @@ def test_logits_match_reference(cuda, name):
           f"summary rel-L2 {rel_l2(model.summary, g['summary']):.3e}; sub-margin samples {n_sub}")
     assert err < TOL
     assert ok, "top-1 differs on a sample with a decisive reference margin"
+    strict = bool((logits.argmax(-1).cpu() == g["logits"].argmax(-1)).all())
+    print(f"[{name}] strict top-1 agreement on all {logits.shape[0]} samples: {strict}")
+    assert strict        # holds on every golden (the margin-aware rule above is the contract, this is the observation)
     assert rel_l2(model.video_features, g["video_features"]) < TOL
     assert rel_l2(model.summary, g["summary"]) < TOL
     assert rel_err(model.text_features, g["text_features"]) < 1e-3          # fp32 text tower
@@ -344,7 +347,11 @@ def test_finetune_gradients_match_oracle(cuda, name):
             assert float(g.abs().max()) < 3e-2 * float(gq.abs().max()), n
             continue
         worst[n] = (rel_l2(g, ref[n]), _cos(g, ref[n]))
-    bad = {n: v for n, v in worst.items() if v[0] > 6e-2 or v[1] < 0.998}
+    # measured on the B200: worst rel-L2 2.1e-2, worst cosine 0.9998 (b16_t8); budget = 2x that
+    bad = {n: v for n, v in worst.items() if v[0] > 4e-2 or v[1] < 0.999}
+    wl2, wcos = max(worst.items(), key=lambda kv: kv[1][0]), min(worst.items(), key=lambda kv: kv[1][1])
+    print(f"\n[{name}] {len(worst)} gradient tensors vs fp32 oracle autograd: worst rel-L2 {wl2[1][0]:.3e} ({wl2[0]}), "
+          f"worst cosine {wcos[1][1]:.5f} ({wcos[0]}); median rel-L2 {sorted(v[0] for v in worst.values())[len(worst) // 2]:.3e}")
     assert not bad, f"gradient mismatch (rel-L2, cosine): {bad}"
     # A second pass WITHOUT zeroing reuses tape / scratch and must accumulate (micro-batch loop of train.py:426-485):
     # grad == 2 x the first pass.  The gradient stream is reproducible (the prompt rows' K/V gradients are summed in a
@@ -588,17 +595,22 @@ def test_finetune_config5_model_gradients(cuda):
     assert abs(float(loss.detach()) - float(ref_loss.detach())) < 2e-2 * max(1.0, abs(float(ref_loss.detach())))
     params = dict(model.named_parameters())
     bad = {}
+    stats = []
     for n in names:
         g, r = params[n].grad, sd[n].grad
         assert g is not None and torch.isfinite(g).all(), n
         if r is None or float(r.abs().max()) == 0.0 or n.endswith("k_proj.bias"):
             continue              # k biases only: softmax is invariant to a shift of all keys, their exact gradient is 0
         c, e = _cos(g, r), rel_l2(g, r)
-        # k_proj WEIGHTS are compared too; their gradient is what survives the per-row cancellation sum_k dS[q,k] = 0 over
-        # T = 8 keys, so bf16 rounding of dS weighs more: looser budget
-        lim_c, lim_e = (0.98, 2e-1) if "k_proj.weight" in n else (0.995, 1e-1)
+        # k_proj WEIGHTS are compared like everything else (only the k biases are shift-invariant)
+        lim_c, lim_e = 0.999, 4e-2      # measured: worst rel-L2 2.2e-2, worst cosine 0.9998, k_proj weights included
+        stats.append((e, c, n))
         if c < lim_c or e > lim_e:
             bad[n] = (round(e, 4), round(c, 5))
+    kp = [t for t in stats if "k_proj.weight" in t[2]]
+    rest = [t for t in stats if "k_proj.weight" not in t[2]]
+    print(f"\n[config 5] {len(stats)} gradient tensors: worst rel-L2 {max(rest)[0]:.3e} ({max(rest)[2]}), worst cosine "
+          f"{min(t[1] for t in rest):.5f}; k_proj weights: worst rel-L2 {max(kp)[0]:.3e}, worst cosine {min(t[1] for t in kp):.5f}")
     assert not bad, f"gradient mismatch (rel-L2, cosine): {bad}"
 
 
