@@ -256,6 +256,58 @@ def test_clip_streamer_uint8(cuda):
     assert st.h2d_bytes == sum(b.numel() for b in batches)
 
 
+def test_set_input_norm_again_takes_effect(cuda):
+    """mean / std are passed by value to the uint8 patch gather and baked into the captured graph: changing them after the
+    first uint8 forward must drop that graph, not replay the old normalisation."""
+    model, kw, B = build_model("tiny", device=cuda)
+    g = torch.Generator().manual_seed(9)
+    u8 = torch.randint(0, 256, (2, 3, 64, 64, 3), dtype=torch.uint8, generator=g).to(cuda)
+    with torch.no_grad():
+        model.visual.set_input_norm([0.45], [0.225])
+        a = model(u8)[0].clone()
+        a2 = model(u8)[0].clone()                      # replayed graph
+        model.visual.set_input_norm([0.30, 0.50, 0.40], [0.20, 0.25, 0.30])
+        b = model(u8)[0].clone()
+        fclip = ((u8.float() / 255.0 - torch.tensor([0.30, 0.50, 0.40], device=cuda)) / torch.tensor([0.20, 0.25, 0.30], device=cuda))
+        want = model(fclip.permute(0, 4, 1, 2, 3).contiguous())[0].clone()
+    assert torch.equal(a, a2)
+    assert not torch.allclose(a, b, atol=1e-4)
+    assert torch.allclose(b, want, atol=1e-5, rtol=0)
+
+
+def test_wrong_current_device_is_caught(cuda):
+    """ops launch on the CURRENT device/stream: a tensor that lives elsewhere is refused instead of being read through the
+    wrong context; the module forward switches the device itself."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from gava_clip_b200 import ops
+    model, kw, B = build_model("tiny", device=torch.device("cuda", 1))
+    video = fx.make_inputs("tiny")["video"].to("cuda:1")
+    with torch.no_grad():
+        out1 = model(video)[0].cpu()                   # current device is cuda:0: forward() guards
+    ref, _, _ = build_model("tiny", device=cuda)
+    with torch.no_grad():
+        out0 = ref(video.to(cuda))[0].cpu()
+    assert torch.allclose(out0, out1, atol=1e-5, rtol=0)
+    x = torch.zeros(8, 128, device="cuda:1")
+    with pytest.raises(RuntimeError):
+        ops.layernorm(x, None, None, torch.empty(8, 128, device="cuda:1", dtype=torch.bfloat16), rows=8, in_row_stride=128)
+
+
+def test_two_forwards_before_backward_are_refused(cuda):
+    """the activation tape is per clip shape: a second train-mode forward overwrites it, and the first graph's backward must
+    say so instead of returning gradients of the wrong tape."""
+    import torch.nn.functional as Fn
+    model, kw, B = build_model("tiny", device=cuda)
+    model.train()
+    video = fx.make_inputs("tiny")["video"].to(cuda)
+    l1 = Fn.cross_entropy(model(video)[0], torch.tensor([2, 0], device=cuda))
+    l2 = Fn.cross_entropy(model(video * 0.5)[0], torch.tensor([1, 1], device=cuda))
+    l2.backward()                                      # the newest tape: fine
+    with pytest.raises(RuntimeError, match="tape"):
+        l1.backward()
+
+
 def test_full_size_config2_properties(cuda):
     """BASELINE.json configs[1] at full size (ViT-B/16, 8 frames, batch 64): size-independent properties.
     (i) the two golden clips placed inside the 64-batch reproduce the reference logits; (ii) duplicated clips give
