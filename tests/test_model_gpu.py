@@ -271,8 +271,9 @@ def test_set_input_norm_again_takes_effect(cuda):
         fclip = ((u8.float() / 255.0 - torch.tensor([0.30, 0.50, 0.40], device=cuda)) / torch.tensor([0.20, 0.25, 0.30], device=cuda))
         want = model(fclip.permute(0, 4, 1, 2, 3).contiguous())[0].clone()
     assert torch.equal(a, a2)
-    assert not torch.allclose(a, b, atol=1e-4)
-    assert torch.allclose(b, want, atol=1e-5, rtol=0)
+    e_new, e_old = rel_err(b, want), rel_err(a, want)
+    print(f"\nafter set_input_norm: rel err vs the float path with the NEW constants {e_new:.2e}, with the old graph {e_old:.2e}")
+    assert e_new < 2e-3 and e_old > 10 * max(e_new, 1e-4)
 
 
 def test_wrong_current_device_is_caught(cuda):
