@@ -58,14 +58,14 @@ SIGNATURES = {
     "gava_cls_rows_fwd": [_p, _i32, _p, _p, _p, _i32, _i32, _i32, _p],
     "gava_temporal_attention_fwd": [_p, _p, _i32, _i32, _i32, _p],
     "gava_prompt_rows_fwd": [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p],
-    "gava_attention_fwd": [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p],
+    "gava_attention_fwd": [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p],
     "gava_head_fwd": [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _p],
     "gava_split_bf16_fwd": [_p, _i64, _p, _p, _i64, _i64, _i32, _p],
     "gava_split3_bf16_fwd": [_p, _i64, _p, _i64, _i32, _p],
     "gava_patch_gather_split_fwd": [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p],
     "gava_embed_assemble_fwd": [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p],
     "gava_quickgelu_f32_fwd": [_p, _i64, _p],
-    "gava_attention_f32_fwd": [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p],
+    "gava_attention_f32_fwd": [_p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p],
     "gava_causal_attention_f32_fwd": [_p, _p, _i32, _i32, _i32, _p],
     "gava_prompt_rows_f32_fwd": [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p],
     "gava_layernorm_bwd": [_p, _i64, _i32, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _f32, _p],

@@ -120,13 +120,13 @@ int gava_prompt_rows_fwd(const float* global_prompts, const float* local_prompts
 }
 
 int gava_attention_fwd(const void* qkv, const void* kv_aux, void* out, int32_t B, int32_t T, int32_t N0, int32_t G,
-                       int32_t H, int32_t n_q, void* stream) {
-  return attention(qkv, kv_aux, out, nullptr, B, T, N0, G, H, n_q, (cudaStream_t)stream);
+                       int32_t H, int32_t n_q, int32_t key_groups, void* stream) {
+  return attention(qkv, kv_aux, out, nullptr, B, T, N0, G, H, n_q, key_groups, (cudaStream_t)stream);
 }
 
 int gava_attention_train_fwd(const void* qkv, const void* kv_aux, void* out, float* lse, int32_t B, int32_t T, int32_t N0,
                              int32_t G, int32_t H, int32_t n_q, void* stream) {
-  return attention(qkv, kv_aux, out, lse, B, T, N0, G, H, n_q, (cudaStream_t)stream);
+  return attention(qkv, kv_aux, out, lse, B, T, N0, G, H, n_q, 3, (cudaStream_t)stream);
 }
 
 int gava_head_fwd(const float* frame_feat, const float* summary_tok, const float* text_hat,
@@ -158,8 +158,8 @@ int gava_embed_assemble_fwd(const float* tmp, float* x, const float* pos_embed, 
 int gava_quickgelu_f32_fwd(float* x, int64_t n, void* stream) { return quickgelu_f32(x, n, (cudaStream_t)stream); }
 
 int gava_attention_f32_fwd(const float* qkv, const float* kv_aux, float* out, int32_t B, int32_t T, int32_t N0,
-                           int32_t G, int32_t H, int32_t n_q, void* stream) {
-  return attention_f32(qkv, kv_aux, out, B, T, N0, G, H, n_q, (cudaStream_t)stream);
+                           int32_t G, int32_t H, int32_t n_q, int32_t key_groups, void* stream) {
+  return attention_f32(qkv, kv_aux, out, B, T, N0, G, H, n_q, key_groups, (cudaStream_t)stream);
 }
 
 int gava_causal_attention_f32_fwd(const float* qkv, float* out, int32_t n_seq, int32_t L, int32_t H, void* stream) {

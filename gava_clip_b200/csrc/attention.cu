@@ -23,6 +23,7 @@ struct AttnArgs {
   __nv_bfloat16* out;
   float* lse;   // optional [BT, H, N0] log2-domain log-sum-exp rows
   int T, N0, G, H, n_q, S, n_chunks, BT;
+  int groups;   // bit 0: local-prompt keys take part, bit 1: the summary-token key takes part
 };
 
 template <int CT>  // 16-key tiles per softmax chunk
@@ -235,7 +236,9 @@ __global__ void __launch_bounds__(256) attention_q1_kernel(const AttnArgs p) {
     d += __shfl_xor_sync(0xffffffffu, d, 1);
     d += __shfl_xor_sync(0xffffffffu, d, 2);
     d += __shfl_xor_sync(0xffffffffu, d, 4);
-    const float v = (row < p.S) ? d * scale_log2 : -INFINITY;
+    bool on = row < p.S;
+    if (on && row >= p.N0 + p.G) on = (row < p.N0 + p.G + p.T) ? (p.groups & 1) : (p.groups & 2);   // disabled prompt group
+    const float v = on ? d * scale_log2 : -INFINITY;
     if (ch == 0 && row < p.S) sc[row] = v;
     mx = fmaxf(mx, v);
   }
@@ -297,7 +300,7 @@ static int launch_attention(const AttnArgs& a, int frames, size_t smem_bytes, cu
 }
 
 int attention(const void* qkv, const void* kv_aux, void* out, float* lse, int B, int T, int N0, int G, int H, int n_q,
-              cudaStream_t stream) {
+              int key_groups, cudaStream_t stream) {
   if (!qkv || !kv_aux || !out || B <= 0 || T <= 0 || N0 <= 0 || G < 0 || H <= 0 || n_q <= 0 || n_q > N0) {
     set_error("attention: bad arguments");
     return GAVA_ERR_ARG;
@@ -312,17 +315,22 @@ int attention(const void* qkv, const void* kv_aux, void* out, float* lse, int B,
     a.kv_aux = reinterpret_cast<const __nv_bfloat16*>(kv_aux);
     a.out = reinterpret_cast<__nv_bfloat16*>(out);
     a.lse = lse;
-    a.T = T; a.N0 = N0; a.G = G; a.H = H; a.n_q = 1; a.BT = B * T; a.S = N0 + G + T + 1; a.n_chunks = 0;
+    a.T = T; a.N0 = N0; a.G = G; a.H = H; a.n_q = 1; a.BT = B * T; a.S = N0 + G + T + 1; a.n_chunks = 0; a.groups = key_groups;
     attention_q1_kernel<<<(unsigned)((B * T * H + 7) / 8), 256, 0, stream>>>(a);
     return check_launch("attention_q1");
   }
   static const bool use_tc = [] { const char* e = getenv("GAVA_ATTN_TC"); return !(e && e[0] == '0'); }();
-  if (use_tc && attention_tc_keys(T, N0, G) != 0 && n_q <= 384) return attention_tc(qkv, kv_aux, out, lse, B, T, N0, G, H, n_q, stream);
+  if (use_tc && attention_tc_keys(T, N0, G) != 0 && n_q <= 384) return attention_tc(qkv, kv_aux, out, lse, B, T, N0, G, H, n_q, key_groups, stream);
+  if ((key_groups & 3) != 3) {
+    set_error("attention: the mma.sync kernel (shapes outside the tcgen05 specialisation) needs all prompt groups (key_groups = 3)");
+    return GAVA_ERR_SHAPE;
+  }
   AttnArgs a;
   a.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
   a.kv_aux = reinterpret_cast<const __nv_bfloat16*>(kv_aux);
   a.out = reinterpret_cast<__nv_bfloat16*>(out);
   a.lse = lse;
+  a.groups = 3;
   a.T = T; a.N0 = N0; a.G = G; a.H = H; a.n_q = n_q; a.BT = B * T;
   a.S = N0 + G + T + 1;
   const int tiles16 = (a.S + 15) / 16;

@@ -69,6 +69,7 @@ struct AttnTcArgs {
   int live_box;    // rows per TMA box of the live K/V rows (divides kb_live, <= 256)
   int t_pad;       // T rounded up to 8 (local prompts are fetched in 8-row boxes)
   int num_items;   // BT * H
+  int groups;      // bit 0: local-prompt keys valid, bit 1: summary-token key valid
   int n_units;     // query tiles per item
   uint32_t kv_tx_bytes;
 };
@@ -98,7 +99,7 @@ __device__ __forceinline__ float chunk16_exp(const uint32_t (&v)[16], uint32_t (
 // single-pass sum overflowed.  Thread `hh` of the row's pair produces output dims [32 hh, 32 hh + 32) into the staging
 // row.  Scalar arguments only: a reference to the kernel's parameter struct would force a local-memory copy of it (and an
 // LDL for every p.x in the hot loops).
-struct ExactRowDims { int T, N0, G, H, BT, D; };
+struct ExactRowDims { int T, N0, G, H, BT, D, groups; };
 __device__ __noinline__ void attn_row_exact(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ kvaux,
                                             uint8_t* stage_row, float* __restrict__ lse, ExactRowDims dm, int f, int h,
                                             int qrow, int hh) {
@@ -116,6 +117,7 @@ __device__ __noinline__ void attn_row_exact(const __nv_bfloat16* __restrict__ qk
   };
   const __nv_bfloat16* qp = qkv + ((long long)f * dm.N0 + qrow) * 3 * D + h * 64;
   auto score = [&](int i) {
+    if (i >= dm.N0 + dm.G && ((i < dm.N0 + dm.G + dm.T) ? !(dm.groups & 1) : !(dm.groups & 2))) return -INFINITY;   // disabled group
     const __nv_bfloat16* kp = key_ptr(i);
     float s = 0.f;
 #pragma unroll 1
@@ -181,7 +183,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   {   // the masking operands
     KeyMask km0;
-    km0.v0 = p.N0; km0.v1 = p.kb_live; km0.v2 = p.kb_live + 8 + p.T; km0.v3 = p.kb_live + 8 + p.t_pad;
+    km0.v0 = p.N0; km0.v1 = p.kb_live; km0.v2 = p.kb_live + 8 + ((p.groups & 1) ? p.T : 0);
+    km0.v3 = (p.groups & 2) ? p.kb_live + 8 + p.t_pad : -1;
     const __nv_bfloat16 one = __float2bfloat16_rn(1.0f), zero = __float2bfloat16_rn(0.0f), neg = __float2bfloat16_rn(-1e30f);
     for (int i = threadIdx.x; i < 128 * 16; i += ATC_THREADS)
       *reinterpret_cast<__nv_bfloat16*>(a_ext + nosw_offset(i >> 4, i & 15)) = (i & 15) == 0 ? one : zero;
@@ -341,7 +344,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     const uint32_t t_mine = t_slot + (uint32_t)(hh * HALF);
     const float c = 0.125f * 1.4426950408889634f;  // dh^-0.5 * log2(e)
     KeyMask km;
-    km.v0 = p.N0; km.v1 = p.kb_live; km.v2 = p.kb_live + 8 + p.T; km.v3 = p.kb_live + 8 + p.t_pad;
+    km.v0 = p.N0; km.v1 = p.kb_live; km.v2 = p.kb_live + 8 + ((p.groups & 1) ? p.T : 0);
+    km.v3 = (p.groups & 2) ? p.kb_live + 8 + p.t_pad : km.v2 - 1;      // here: the LAST valid smem key row (bounds the exp pass)
     // one slot per (group, half, row): holds the first-chunk maximum until the named barrier, the row sum afterwards
     float* my_max = xch + (s * 2 + hh) * 128 + row_in_tile;
     float* ot_max = xch + (s * 2 + (hh ^ 1)) * 128 + row_in_tile;
@@ -488,7 +492,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 #undef GAVA_PK
         } else {
           ExactRowDims dm;
-          dm.T = p.T; dm.N0 = p.N0; dm.G = p.G; dm.H = p.H; dm.BT = p.BT; dm.D = p.D;
+          dm.T = p.T; dm.N0 = p.N0; dm.G = p.G; dm.H = p.H; dm.BT = p.BT; dm.D = p.D; dm.groups = p.groups;
           attn_row_exact(p.qkv, p.kvaux, stage_row, p.lse, dm, f, h, qrow, hh);
         }
         fence_proxy_async();                        // generic-proxy smem writes -> visible to the TMA store
@@ -551,7 +555,7 @@ int attention_tc_keys(int T, int N0, int G) {
 }
 
 int attention_tc(const void* qkv, const void* kv_aux, void* out, float* lse, int B, int T, int N0, int G, int H, int n_q,
-                 cudaStream_t stream) {
+                 int key_groups, cudaStream_t stream) {
   const int keys = attention_tc_keys(T, N0, G);
   if (keys == 0 || n_q > 3 * 128) {
     set_error("attention_tc: shape outside the tcgen05 specialisation (G=%d T=%d N0=%d n_q=%d)", G, T, N0, n_q);
@@ -577,6 +581,7 @@ int attention_tc(const void* qkv, const void* kv_aux, void* out, float* lse, int
   a.T = T; a.N0 = N0; a.G = G; a.H = H; a.n_q = n_q; a.BT = BT; a.D = D;
   a.kb_live = kb_live; a.live_box = 8 * g; a.t_pad = t_pad;
   a.num_items = BT * H;
+  a.groups = key_groups;
   a.n_units = (n_q + 127) / 128;
   a.kv_tx_bytes = (uint32_t)(2 * 128 * keys);
   if (keys <= 224) return launch_attention_tc<224, 1, 4>(tq, tkv, taux, tout, a, stream);

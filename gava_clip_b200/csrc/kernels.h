@@ -57,11 +57,13 @@ int prompt_rows(const float* global_prompts, const float* local_prompts, const f
 
 // tcgen05/TMEM/TMA attention (attention_tc.cu); returns GAVA_ERR_SHAPE when the shape is outside its specialisation
 int attention_tc_keys(int T, int N0, int G);   // smem key rows needed; 0 = outside the specialisation
+// key_groups: bit 0 = the T local-prompt rows take part, bit 1 = the summary-token row takes part (the global prompts always
+// do); 3 = the full Vita-CLIP configuration.  Rows of a disabled group stay in kv_aux's layout but get zero probability.
 int attention_tc(const void* qkv, const void* kv_aux, void* out, float* lse, int B, int T, int N0, int G, int H, int n_q,
-                 cudaStream_t stream);
+                 int key_groups, cudaStream_t stream);
 
 int attention(const void* qkv, const void* kv_aux, void* out, float* lse, int B, int T, int N0, int G, int H, int n_q,
-              cudaStream_t stream);
+              int key_groups, cudaStream_t stream);
 
 int head(const float* frame_feat, const float* summary_tok, const float* text_hat, const int* class_offsets,
          float* video_features, float* summary_out, float* logits, int B, int T, int E, int D, int n_cls, float scale,
@@ -77,7 +79,7 @@ int embed_assemble(const float* tmp, float* x, const float* pos, const float* ti
                    cudaStream_t stream);
 int quickgelu_f32(float* x, long long n, cudaStream_t stream);
 int attention_f32(const float* qkv, const float* kv_aux, float* out, int B, int T, int N0, int G, int H, int n_q,
-                  cudaStream_t stream);
+                  int key_groups, cudaStream_t stream);
 int causal_attention_f32(const float* qkv, float* out, int n_seq, int L, int H, cudaStream_t stream);
 int prompt_rows_f32(const float* global_prompts, const float* local_prompts, const float* cls_proj_out,
                     const float* summary, const float* ln_w, const float* ln_b, float* out, int G, int B, int T, int D,

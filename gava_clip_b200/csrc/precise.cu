@@ -153,6 +153,7 @@ struct AttnF32Args {
   float* out;            // [rows, D]
   int T, N0, G, H, n_q, BT, S;
   int causal;            // 1: query q attends keys 0..q only (text transformer); needs kv_aux == NULL
+  int groups;            // bit 0: local-prompt keys take part, bit 1: the summary-token key takes part
 };
 
 __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32Args p) {
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32Args p)
       float acc = 0.f;
 #pragma unroll 16
       for (int d = 0; d < 64; ++d) acc = fmaf(sQ[warp * 64 + d], sK[j * 65 + d], acc);
+      if (p.kv_aux != nullptr && j >= p.N0 + p.G && !((j < p.N0 + p.G + p.T) ? (p.groups & 1) : (p.groups & 2))) acc = -INFINITY;
       sP[warp * S + j] = acc;
       mx = fmaxf(mx, acc);
     }
@@ -219,26 +221,27 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const AttnF32Args p)
 }
 
 static int attention_f32_impl(const float* qkv, const float* kv_aux, float* out, int B, int T, int N0, int G, int H,
-                              int n_q, int causal, cudaStream_t stream);
+                              int n_q, int causal, int groups, cudaStream_t stream);
 
 int attention_f32(const float* qkv, const float* kv_aux, float* out, int B, int T, int N0, int G, int H, int n_q,
-                  cudaStream_t stream) {
-  return attention_f32_impl(qkv, kv_aux, out, B, T, N0, G, H, n_q, 0, stream);
+                  int key_groups, cudaStream_t stream) {
+  return attention_f32_impl(qkv, kv_aux, out, B, T, N0, G, H, n_q, 0, key_groups, stream);
 }
 
 // causal self-attention over n_seq sequences of L tokens (CLIP text transformer, VitaCLIP_text_encoder.py:67-88)
 int causal_attention_f32(const float* qkv, float* out, int n_seq, int L, int H, cudaStream_t stream) {
-  return attention_f32_impl(qkv, nullptr, out, n_seq, 1, L, 0, H, L, 1, stream);
+  return attention_f32_impl(qkv, nullptr, out, n_seq, 1, L, 0, H, L, 1, 3, stream);
 }
 
 static int attention_f32_impl(const float* qkv, const float* kv_aux, float* out, int B, int T, int N0, int G, int H,
-                              int n_q, int causal, cudaStream_t stream) {
+                              int n_q, int causal, int groups, cudaStream_t stream) {
   if (!qkv || !out || B <= 0 || T <= 0 || N0 <= 0 || G < 0 || H <= 0 || n_q <= 0 || n_q > N0 || (causal && kv_aux)) {
     set_error("attention_f32: bad arguments");
     return GAVA_ERR_ARG;
   }
   AttnF32Args a;
   a.causal = causal;
+  a.groups = groups;
   a.qkv = qkv; a.kv_aux = kv_aux; a.out = out;
   a.T = T; a.N0 = N0; a.G = G; a.H = H; a.n_q = n_q; a.BT = B * T;
   a.S = kv_aux ? N0 + G + T + 1 : N0;       // kv_aux == NULL: plain self-attention over the N0 rows (summary attention)

@@ -181,7 +181,7 @@ class VitaCLIP(nn.Module):
         dev = ff.device
         n_out = offs.numel() - 1
         vf = torch.empty(B, ff.shape[1], device=dev, dtype=torch.float32)
-        so = torch.empty(B, st.shape[1], device=dev, dtype=torch.float32)
+        so = torch.empty(B, st.shape[1], device=dev, dtype=torch.float32) if st is not None else None   # no summary token
         logits = torch.empty(B, n_out, device=dev, dtype=torch.float32)
         if ff.shape[1] != t_hat.shape[1]:      # frame_feat rows are padded to the GEMM N tile
             pad = torch.zeros(t_hat.shape[0], ff.shape[1], device=dev, dtype=torch.float32)
@@ -221,7 +221,7 @@ class VitaCLIP(nn.Module):
         dev = ff.device
         E = self.visual.embed_dim
         vf = ff[:, :E].reshape(B, T, E).mean(dim=1)
-        summary = st.reshape(B, T, -1).mean(dim=1)
+        summary = st.reshape(B, T, -1).mean(dim=1) if st is not None else None
         v_hat = vf / vf.norm(dim=-1, keepdim=True)
         scale = self.logit_scale.exp()
         if self.use_text_prompt_learning:

@@ -196,14 +196,15 @@ def prompt_rows(global_prompts: Tensor, local_prompts: Tensor, cls_proj_out: Ten
 
 
 def attention(qkv: Tensor, kv_aux: Tensor, out: Tensor, *, B: int, T: int, N0: int, G: int, H: int,
-              n_q: Optional[int] = None) -> Tensor:
+              n_q: Optional[int] = None, key_groups: int = 3) -> Tensor:
+    """key_groups: bit 0 = local-prompt rows take part, bit 1 = the summary-token row takes part (3 = full Vita-CLIP)."""
     _req(qkv, torch.bfloat16, "attention qkv"); _req(kv_aux, torch.bfloat16, "attention kv_aux")
     _req(out, torch.bfloat16, "attention out")
     D = H * 64
     assert qkv.is_contiguous() and kv_aux.is_contiguous() and out.is_contiguous()
     assert qkv.shape == (B * T * N0, 3 * D) and kv_aux.shape == (G + 2 * B * T, 2 * D) and out.shape == (B * T * N0, D)
     rc = _lib.load().gava_attention_fwd(qkv.data_ptr(), kv_aux.data_ptr(), out.data_ptr(), B, T, N0, G, H,
-                                        N0 if n_q is None else n_q, _stream())
+                                        N0 if n_q is None else n_q, key_groups, _stream())
     _lib.check(rc, "gava_attention_fwd")
     return out
 
@@ -290,7 +291,7 @@ def quickgelu_f32(x: Tensor) -> Tensor:
 
 
 def attention_f32(qkv: Tensor, kv_aux: Optional[Tensor], out: Tensor, *, B: int, T: int, N0: int, G: int, H: int,
-                  n_q: Optional[int] = None) -> Tensor:
+                  n_q: Optional[int] = None, key_groups: int = 3) -> Tensor:
     _req(qkv, torch.float32, "attention_f32 qkv"); _req(out, torch.float32, "attention_f32 out")
     D = H * 64
     assert qkv.is_contiguous() and out.is_contiguous() and qkv.shape == (B * T * N0, 3 * D) and out.shape == (B * T * N0, D)
@@ -298,7 +299,7 @@ def attention_f32(qkv: Tensor, kv_aux: Optional[Tensor], out: Tensor, *, B: int,
         _req(kv_aux, torch.float32, "attention_f32 kv_aux")
         assert kv_aux.is_contiguous() and kv_aux.shape == (G + 2 * B * T, 2 * D)
     rc = _lib.load().gava_attention_f32_fwd(qkv.data_ptr(), _ptr(kv_aux), out.data_ptr(), B, T, N0, G, H,
-                                            N0 if n_q is None else n_q, _stream())
+                                            N0 if n_q is None else n_q, key_groups, _stream())
     _lib.check(rc, "gava_attention_f32_fwd")
     return out
 

@@ -225,19 +225,27 @@ class TowerEngine:
                 lambda a=a: bf(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0)))
             put(k + "qkv.b", [a.q_proj.bias, a.k_proj.bias, a.v_proj.bias],
                 lambda a=a: f32(torch.cat([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias], 0)))
-            for nm, lin in (("out", a.out_proj), ("fc1", blk.mlp.fc1), ("fc2", blk.mlp.fc2), ("cls", blk.cls_proj),
-                            ("sout", blk.summary_attn_layer.out_proj)):
+            lins = [("out", a.out_proj), ("fc1", blk.mlp.fc1), ("fc2", blk.mlp.fc2)]
+            norms = ["norm1", "norm2"]
+            if e.use_summary_token or e.use_local_prompts:          # utils.py:124-126
+                lins.append(("cls", blk.cls_proj))
+            if e.use_summary_token:                                  # utils.py:129-134
+                lins.append(("sout", blk.summary_attn_layer.out_proj))
+                norms.append("summary_ln")
+            for nm, lin in lins:
                 put(k + nm + ".w", [lin.weight], lambda lin=lin: bf(lin.weight))
                 put(k + nm + ".b", [lin.bias], lambda lin=lin: f32(lin.bias))
-            for n in ("norm1", "norm2", "summary_ln"):
+            for n in norms:
                 put(k + n + ".w", [getattr(blk, n).weight], lambda blk=blk, n=n: f32(getattr(blk, n).weight))
                 put(k + n + ".b", [getattr(blk, n).bias], lambda blk=blk, n=n: f32(getattr(blk, n).bias))
-            sa = blk.summary_attn_layer
-            put(k + "sqkv.w", [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight],
-                lambda sa=sa: bf(torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0)))
-            put(k + "sqkv.b", [sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias],
-                lambda sa=sa: f32(torch.cat([sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias], 0)))
-            put(k + "local", [blk.local_prompts], lambda blk=blk: f32(blk.local_prompts))
+            if e.use_summary_token:
+                sa = blk.summary_attn_layer
+                put(k + "sqkv.w", [sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight],
+                    lambda sa=sa: bf(torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0)))
+                put(k + "sqkv.b", [sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias],
+                    lambda sa=sa: f32(torch.cat([sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias], 0)))
+            if e.use_local_prompts:                                  # utils.py:137-139
+                put(k + "local", [blk.local_prompts], lambda blk=blk: f32(blk.local_prompts))
         for key in [key for key in P if key.startswith("time_embed@")]:
             del P[key]                                  # resized copies are rebuilt on demand
         if copies:           # fine-tuning refreshes ~100 small tensors per step: a handful of launches instead of one each
@@ -269,14 +277,17 @@ class TowerEngine:
         pair(pj, "proj.wT", Q)
         for i, blk in enumerate(e.blocks):
             k = f"b{i}."
-            a, sa = blk.attn, blk.summary_attn_layer
+            a = blk.attn
             pair(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0), k + "qkv.w", Q)
             pair(a.out_proj.weight, k + "out.w", Q)
             pair(blk.mlp.fc1.weight, k + "fc1.w", Q)
             pair(blk.mlp.fc2.weight, k + "fc2.w", Q)
-            pair(blk.cls_proj.weight, k + "cls.w", Q)
-            pair(torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0), k + "sqkv.w", Q)
-            pair(sa.out_proj.weight, k + "sout.w", Q)
+            if e.use_summary_token or e.use_local_prompts:
+                pair(blk.cls_proj.weight, k + "cls.w", Q)
+            if e.use_summary_token:
+                sa = blk.summary_attn_layer
+                pair(torch.cat([sa.q_proj.weight, sa.k_proj.weight, sa.v_proj.weight], 0), k + "sqkv.w", Q)
+                pair(sa.out_proj.weight, k + "sout.w", Q)
         self.packed_lo, self._precise_sig = Q, self.signature
         return Q
 
@@ -333,6 +344,14 @@ class TowerEngine:
             "kvaux": z(G + 2 * BT, 2 * D, dt=bf),
             "frame_feat": z(BT, self.packed["proj.wT"].shape[0], dt=f32),
         }
+        # inputs of the prompt-row kernel that a disabled prompt group does not produce (zeros: their K/V rows are masked
+        # out by the attention kernels' key_groups, they only have to be finite)
+        if not e.use_local_prompts:
+            W["zero_local"] = torch.zeros(1, T, D, device=dev, dtype=f32)
+        if not (e.use_summary_token or e.use_local_prompts):
+            W["cls_proj"].zero_()
+        if not e.use_summary_token:
+            W["summary"].zero_()
         self.ws[key] = W
         return W
 
@@ -377,7 +396,7 @@ class TowerEngine:
         self.launches_last_call = n_launch
         B, T, _, _ = _clip_dims(video)
         W = self.ws[(B, T)]
-        return W["frame_feat"], W["summary"]
+        return W["frame_feat"], (W["summary"] if self.enc.use_summary_token else None)
 
     # ------------------------------------------------------------------ schedule
     def encode_frames(self, video: Tensor) -> Tuple[Tensor, Tensor]:
@@ -406,6 +425,7 @@ class TowerEngine:
         ops.layernorm2(x, P["ln_pre.w"], P["ln_pre.b"], x, P["b0.norm1.w"], P["b0.norm1.b"], xn, rows=M)
 
         L = len(e.blocks)
+        kg = (1 if e.use_local_prompts else 0) | (2 if e.use_summary_token else 0)      # prompt groups among the keys
         main = torch.cuda.current_stream(self.device)
         side = self.side_stream if self.overlap_chain else None
         norm1_done = True       # True when xn already holds norm1(x) of the coming block (block 0: done by the ln_pre pass)
@@ -419,16 +439,18 @@ class TowerEngine:
                 ev_x.record(main)
                 side.wait_event(ev_x)
             with torch.cuda.stream(side if side is not None else main):
-                ops.layernorm(x, None, None, W["cls_bf2"], rows=BT, in_row_stride=N0 * D)
-                ops.gemm(W["cls_bf2"], P[k + "cls.w"], W["cls_proj"], mode=ops.EPI_BIAS_F32, bias=P[k + "cls.b"])
-                ops.layernorm(W["cls_proj"], P[k + "summary_ln.w"], P[k + "summary_ln.b"], W["sum_n"], rows=BT,
-                              in_row_stride=D)
-                ops.gemm(W["sum_n"], P[k + "sqkv.w"], W["sqkv"], mode=ops.EPI_BIAS_BF16, bias=P[k + "sqkv.b"])
-                ops.temporal_attention(W["sqkv"], W["smix"], B, T, H)
-                ops.gemm(W["smix"], P[k + "sout.w"], W["summary"], mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "sout.b"],
-                         resid=W["cls_proj"])
-                ops.prompt_rows(P["global_prompts"][i], P[k + "local"], W["cls_proj"], W["summary"], P[k + "norm1.w"],
-                                P[k + "norm1.b"], W["aux_n"], B, T, LN_EPS)
+                if e.use_summary_token or e.use_local_prompts:                               # utils.py:160-165
+                    ops.layernorm(x, None, None, W["cls_bf2"], rows=BT, in_row_stride=N0 * D)
+                    ops.gemm(W["cls_bf2"], P[k + "cls.w"], W["cls_proj"], mode=ops.EPI_BIAS_F32, bias=P[k + "cls.b"])
+                if e.use_summary_token:                                                      # utils.py:168-172
+                    ops.layernorm(W["cls_proj"], P[k + "summary_ln.w"], P[k + "summary_ln.b"], W["sum_n"], rows=BT,
+                                  in_row_stride=D)
+                    ops.gemm(W["sum_n"], P[k + "sqkv.w"], W["sqkv"], mode=ops.EPI_BIAS_BF16, bias=P[k + "sqkv.b"])
+                    ops.temporal_attention(W["sqkv"], W["smix"], B, T, H)
+                    ops.gemm(W["smix"], P[k + "sout.w"], W["summary"], mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "sout.b"],
+                             resid=W["cls_proj"])
+                ops.prompt_rows(P["global_prompts"][i], P[k + "local"] if e.use_local_prompts else W["zero_local"],
+                                W["cls_proj"], W["summary"], P[k + "norm1.w"], P[k + "norm1.b"], W["aux_n"], B, T, LN_EPS)
                 ops.gemm(W["aux_n"], P[k + "qkv.w"][D:], W["kvaux"], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:])
                 if side is not None:
                     ev_kv = torch.cuda.Event()
@@ -442,7 +464,7 @@ class TowerEngine:
                          max_ctas=self.qkv_ctas if side is not None else 0)
                 if side is not None:
                     main.wait_event(ev_kv)
-                ops.attention(qkv, W["kvaux"], xn, B=B, T=T, N0=N0, G=G, H=H)
+                ops.attention(qkv, W["kvaux"], xn, B=B, T=T, N0=N0, G=G, H=H, key_groups=kg)
                 if self.defer_resid:
                     dl = W["delta"]
                     ops.gemm(xn, P[k + "out.w"], dl, mode=ops.EPI_BIAS_BF16, bias=P[k + "out.b"])
@@ -468,7 +490,7 @@ class TowerEngine:
                          bias=P[k + "qkv.b"][:D])
                 if side is not None:
                     main.wait_event(ev_kv)
-                ops.attention(qkv, W["kvaux"], xn, B=B, T=T, N0=N0, G=G, H=H, n_q=1)
+                ops.attention(qkv, W["kvaux"], xn, B=B, T=T, N0=N0, G=G, H=H, n_q=1, key_groups=kg)
                 ops.gemm(xn_cls, P[k + "out.w"], W["x_cls"], mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "out.b"],
                          resid=x_cls_src)
                 ops.layernorm(W["x_cls"], P[k + "norm2.w"], P[k + "norm2.b"], W["cls_bf"], rows=BT, in_row_stride=D)
@@ -482,7 +504,7 @@ class TowerEngine:
         # ln_post(cls) @ proj per frame                                   vision_encoder.py:126-127
         ops.layernorm(W["x_cls"], P["ln_post.w"], P["ln_post.b"], W["cls_bf"], rows=BT, in_row_stride=D)
         ops.gemm(W["cls_bf"], P["proj.wT"], W["frame_feat"], mode=ops.EPI_BIAS_F32)
-        return W["frame_feat"], W["summary"]
+        return W["frame_feat"], (W["summary"] if e.use_summary_token else None)
 
 
     # ------------------------------------------------------------------ fp32-accuracy schedule
@@ -505,6 +527,12 @@ class TowerEngine:
              "smix": z(BT, D, dt=f32), "summary": z(BT, D, dt=f32), "aux_n": z(G + 2 * BT, D, dt=f32),
              "kvaux": z(G + 2 * BT, 2 * D, dt=f32), "x_cls": z(BT, D, dt=f32), "hc": z(BT, Dm, dt=f32),
              "frame_feat": z(BT, self.packed["proj.wT"].shape[0], dt=f32)}
+        if not e.use_local_prompts:
+            W["zero_local"] = torch.zeros(1, T, D, device=dev, dtype=f32)
+        if not (e.use_summary_token or e.use_local_prompts):
+            W["cls_proj"].zero_()
+        if not e.use_summary_token:
+            W["summary"].zero_()
         self.ws[key] = W
         return W
 
@@ -543,21 +571,24 @@ class TowerEngine:
         ops.layernorm(x, P["ln_pre.w"], P["ln_pre.b"], x, rows=M, in_row_stride=D)
 
         L = len(e.blocks)
+        kg = (1 if e.use_local_prompts else 0) | (2 if e.use_summary_token else 0)
         for i in range(L):
             k = f"b{i}."
             # temporal message (utils.py:160-188)
-            mm(x, BT, D, k + "cls.w", W["cls_proj"], bias=P[k + "cls.b"], in_row_stride=N0 * D)
-            ops.layernorm(W["cls_proj"], P[k + "summary_ln.w"], P[k + "summary_ln.b"], W["sum_n"], rows=BT, in_row_stride=D)
-            mm(W["sum_n"], BT, D, k + "sqkv.w", W["sqkv"], bias=P[k + "sqkv.b"])
-            ops.attention_f32(W["sqkv"], None, W["smix"], B=B, T=1, N0=T, G=0, H=H)
-            mm(W["smix"], BT, D, k + "sout.w", W["summary"], bias=P[k + "sout.b"], resid=W["cls_proj"])
-            ops.prompt_rows_f32(P["global_prompts"][i], P[k + "local"], W["cls_proj"], W["summary"], P[k + "norm1.w"],
-                                P[k + "norm1.b"], W["aux_n"], B, T, LN_EPS)
+            if e.use_summary_token or e.use_local_prompts:
+                mm(x, BT, D, k + "cls.w", W["cls_proj"], bias=P[k + "cls.b"], in_row_stride=N0 * D)
+            if e.use_summary_token:
+                ops.layernorm(W["cls_proj"], P[k + "summary_ln.w"], P[k + "summary_ln.b"], W["sum_n"], rows=BT, in_row_stride=D)
+                mm(W["sum_n"], BT, D, k + "sqkv.w", W["sqkv"], bias=P[k + "sqkv.b"])
+                ops.attention_f32(W["sqkv"], None, W["smix"], B=B, T=1, N0=T, G=0, H=H)
+                mm(W["smix"], BT, D, k + "sout.w", W["summary"], bias=P[k + "sout.b"], resid=W["cls_proj"])
+            ops.prompt_rows_f32(P["global_prompts"][i], P[k + "local"] if e.use_local_prompts else W["zero_local"],
+                                W["cls_proj"], W["summary"], P[k + "norm1.w"], P[k + "norm1.b"], W["aux_n"], B, T, LN_EPS)
             mm(W["aux_n"], G + 2 * BT, D, k + "qkv.w", W["kvaux"], bias=P[k + "qkv.b"][D:], w_rows=slice(D, 3 * D))
             # x = x + attn(norm1(x))
             ops.layernorm(x, P[k + "norm1.w"], P[k + "norm1.b"], t, rows=M, in_row_stride=D)
             mm(t, M, D, k + "qkv.w", qkv, bias=P[k + "qkv.b"])
-            ops.attention_f32(qkv, W["kvaux"], att, B=B, T=T, N0=N0, G=G, H=H)
+            ops.attention_f32(qkv, W["kvaux"], att, B=B, T=T, N0=N0, G=G, H=H, key_groups=kg)
             mm(att, M, D, k + "out.w", x, bias=P[k + "out.b"], resid=x)
             # x = x + fc2(QuickGELU(fc1(norm2(x))))
             ops.layernorm(x, P[k + "norm2.w"], P[k + "norm2.b"], t, rows=M, in_row_stride=D)
@@ -567,7 +598,7 @@ class TowerEngine:
 
         ops.layernorm(x, P["ln_post.w"], P["ln_post.b"], W["cls"], rows=BT, in_row_stride=N0 * D)
         mm(W["cls"], BT, D, "proj.wT", W["frame_feat"])
-        return W["frame_feat"], W["summary"]
+        return W["frame_feat"], (W["summary"] if e.use_summary_token else None)
 
 
 class CLIPVisionEncoder(nn.Module):
@@ -629,9 +660,10 @@ class CLIPVisionEncoder(nn.Module):
 
     # -- engine plumbing ---------------------------------------------------------------------------
     def engine(self, device: torch.device) -> TowerEngine:
-        if not (self.use_global_prompts and self.use_summary_token and self.use_local_prompts):
-            # the reference itself only runs with all three enabled (the other branch crashes)
-            raise NotImplementedError("the sm_100a tower implements the summary+local+global prompt configuration")
+        if not self.use_global_prompts:
+            # the reference encoder itself crashes without global prompts (VitaCLIP_vision_encoder.py:123-124 assigns the
+            # layer's (x, summary) tuple to x): there is no behaviour to reproduce
+            raise NotImplementedError("use_global_prompts=False: the reference encoder has no working forward for it")
         if self.feature_dim // self.num_heads != 64:
             raise NotImplementedError("attention kernel is specialised for head_dim 64")
         if self._engine is None or self._engine.device != device:
@@ -667,6 +699,9 @@ class CLIPVisionEncoder(nn.Module):
         eng = self.engine(x.device)
         B, T, _, _ = _clip_dims(x)
         if self._wants_grad():
+            if not (self.use_summary_token and self.use_local_prompts):
+                raise NotImplementedError("the fine-tune step (tape + backward kernels) covers the summary+local+global prompt "
+                                          "configuration of the shipped recipes; inference runs every combination")
             if self.precision == "fp32":
                 raise NotImplementedError("the fine-tune step runs in the bf16 path (set precision='bf16')")
             from .train_engine import TowerFunction
@@ -684,5 +719,5 @@ class CLIPVisionEncoder(nn.Module):
         E = self.embed_dim
         # temporal means (vision_encoder.py:128-130); the fused head kernel does the same inside VitaCLIP.forward
         cls_x = ff[:, :E].reshape(B, T, E).mean(dim=1)
-        summary = st.reshape(B, T, -1).mean(dim=1)
+        summary = st.reshape(B, T, -1).mean(dim=1) if st is not None else None      # vision_encoder.py:129-130
         return cls_x, summary

@@ -136,10 +136,13 @@ int gava_prompt_rows_fwd(const float* global_prompts, const float* local_prompts
  *   qkv    : bf16 [B*T*N0, 3*D]  = [q | k | v] (q NOT pre-scaled; 1/sqrt(dh) is applied inside)
  *   kv_aux : bf16 [G + 2*B*T, 2*D] = [k | v]
  *   out    : bf16 [B*T*N0, D]; only rows f*N0 + i, i < n_q are written
- * dh = D / H must be 64.  Replaces Attention.forward core, VitaCLIP_vision_encoder_utils.py:71-77, for the
- * token set built at :171-188 (dead query rows :194-197 are never computed). */
+ * dh = D / H must be 64.  key_groups selects the prompt groups that take part: bit 0 = the T local rows
+ * (use_local_prompts), bit 1 = the summary row (use_summary_token); the G global rows always do; 3 = the full Vita-CLIP
+ * configuration.  Rows of a disabled group keep their place in kv_aux (contents ignored, must be finite).
+ * Replaces Attention.forward core, VitaCLIP_vision_encoder_utils.py:71-77, for the token set built at :160-188 (dead
+ * query rows :194-197 are never computed). */
 int gava_attention_fwd(const void* qkv, const void* kv_aux, void* out, int32_t B, int32_t T, int32_t N0, int32_t G,
-                       int32_t H, int32_t n_q, void* stream);
+                       int32_t H, int32_t n_q, int32_t key_groups, void* stream);
 
 /* Logit head.  frame_feat: f32 [B*T, E] (ln_post(cls) @ proj per frame); summary_tok: f32 [B*T, D] or NULL.
  *   video_features[b] = mean_t frame_feat[b*T + t]                               (f32 [B, E], un-normalised)
@@ -181,9 +184,9 @@ int gava_quickgelu_f32_fwd(float* x, int64_t n, void* stream);
 
 /* gava_attention_fwd in f32 on the CUDA cores: qkv f32 [B*T*N0, 3D], kv_aux f32 [G+2BT, 2D], out f32 [B*T*N0, D].
  * kv_aux == NULL: plain self-attention over the N0 rows of each of the B*T groups (used for the summary-token
- * attention with B*T = videos, N0 = frames). */
+ * attention with B*T = videos, N0 = frames).  key_groups as in gava_attention_fwd. */
 int gava_attention_f32_fwd(const float* qkv, const float* kv_aux, float* out, int32_t B, int32_t T, int32_t N0,
-                           int32_t G, int32_t H, int32_t n_q, void* stream);
+                           int32_t G, int32_t H, int32_t n_q, int32_t key_groups, void* stream);
 
 /* Causal multi-head self-attention core of the CLIP text transformer in f32: qkv f32 [n_seq*L, 3D] (packed in_proj
  * output), out f32 [n_seq*L, D]; query t attends tokens 0..t of its sequence; dh = 64.

@@ -29,6 +29,19 @@ CASES: Dict[str, Tuple[dict, int]] = {
     "tiny": (dict(input_size=(64, 64), num_frames=3, feature_dim=128, num_heads=2, num_layers=2, embed_dim=128,
                   text_transformer_width=128, text_transformer_heads=2, text_transformer_layers=2,
                   num_classes=3, text_prompt_classes_path="updrs_3cls_classes.txt", **_PROMPT_FLAGS), 2),
+    # prompt-flag combinations the reference layer handles independently (utils.py:160-197; global prompts are mandatory)
+    "tiny_global_only": (dict(input_size=(64, 64), num_frames=3, feature_dim=128, num_heads=2, num_layers=2, embed_dim=128,
+                              text_transformer_width=128, text_transformer_heads=2, text_transformer_layers=2, num_classes=3,
+                              text_prompt_classes_path="updrs_3cls_classes.txt",
+                              **{**_PROMPT_FLAGS, "use_summary_token": False, "use_local_prompts": False}), 2),
+    "tiny_no_local": (dict(input_size=(64, 64), num_frames=3, feature_dim=128, num_heads=2, num_layers=2, embed_dim=128,
+                           text_transformer_width=128, text_transformer_heads=2, text_transformer_layers=2, num_classes=3,
+                           text_prompt_classes_path="updrs_3cls_classes.txt",
+                           **{**_PROMPT_FLAGS, "use_local_prompts": False}), 2),
+    "tiny_no_summary": (dict(input_size=(64, 64), num_frames=3, feature_dim=128, num_heads=2, num_layers=2, embed_dim=128,
+                             text_transformer_width=128, text_transformer_heads=2, text_transformer_layers=2, num_classes=3,
+                             text_prompt_classes_path="updrs_3cls_classes.txt",
+                             **{**_PROMPT_FLAGS, "use_summary_token": False}), 2),
     "b16_t8": (dict(num_frames=8, num_classes=3, text_prompt_classes_path="updrs_3cls_classes.txt", **_PROMPT_FLAGS), 2),
     # config-2 shapes at batch 8 (two full 128-row GEMM tiles of cls rows, > 1 wave of attention items per SM)
     "b16_t8_b8": (dict(num_frames=8, num_classes=3, text_prompt_classes_path="updrs_3cls_classes.txt", **_PROMPT_FLAGS), 8),

@@ -82,12 +82,13 @@ def run_case(ref_model, name: str, tokens: dict) -> None:
 
     def tap_block(m, i, o):          # hooks must return None (a non-None return replaces the output)
         taps["layer_cls"].append(o[0][:, 0].clone())
-        taps["layer_summary"].append(o[1].clone())
+        if o[1] is not None:
+            taps["layer_summary"].append(o[1].clone())
 
     feats = {}
 
     def tap_visual(m, i, o):
-        feats.update(video_features=o[0].clone(), summary=o[1].clone())
+        feats.update(video_features=o[0].clone(), summary=o[1].clone() if o[1] is not None else None)
 
     for blk in model.visual.blocks:
         hooks.append(blk.register_forward_hook(tap_block))
@@ -108,6 +109,7 @@ def run_case(ref_model, name: str, tokens: dict) -> None:
         # per-layer taps only for the two small cases (keeps the fixtures small)
         "layer_cls": torch.stack(taps["layer_cls"][:n_layers]) if name in ("tiny", "b16_t8") else None,
         "layer_summary": torch.stack(taps["layer_summary"][:n_layers]) if name in ("tiny", "b16_t8") else None,
+        "prompt_flags": {k: kw.get(k, False) for k in ("use_summary_token", "use_local_prompts", "use_global_prompts")},
         "desc_wise": desc,
         "state_dict_shapes": {k: list(v.shape) for k, v in model.state_dict().items()},
         "requires_grad": sorted(n for n, p in model.named_parameters() if p.requires_grad),

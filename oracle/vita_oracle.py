@@ -127,8 +127,9 @@ def encoder_layer(
 def vision_encoder(
     sd: SD, video: Tensor, *, num_frames: int, num_heads: int, num_layers: int,
     num_global_prompts: int = 8, prefix: str = "visual.", taps: Optional[dict] = None,
-) -> Tuple[Tensor, Tensor]:
-    """CLIPVisionEncoder.forward -- VitaCLIP_vision_encoder.py:102-132.
+    use_summary: bool = True, use_local: bool = True,
+) -> Tuple[Tensor, Optional[Tensor]]:
+    """CLIPVisionEncoder.forward -- VitaCLIP_vision_encoder.py:102-132 (use_global_prompts=True: its other branch crashes).
 
     video: (B, 3, T, H, W) fp32.  Returns (cls_x (B,E), summary (B,D)).
     `taps`, if given, receives per-layer cls rows and summary tokens (debug/parity aids).
@@ -151,16 +152,18 @@ def vision_encoder(
     for i in range(num_layers):                                                           # :116-121
         gp = sd[prefix + "global_prompts"][i].expand(B * T, -1, -1)
         x = torch.cat([x[:, :1], gp, x[:, 1:]], dim=1)
-        x, summary = encoder_layer(sd, f"{prefix}blocks.{i}.", x, num_frames, num_heads)
+        x, summary = encoder_layer(sd, f"{prefix}blocks.{i}.", x, num_frames, num_heads, use_summary, use_local)
         x = torch.cat([x[:, :1], x[:, G + 1:]], dim=1)
         if taps is not None:
             taps.setdefault("layer_cls", []).append(x[:, 0].clone())
-            taps.setdefault("layer_summary", []).append(summary.clone())
+            if summary is not None:
+                taps.setdefault("layer_summary", []).append(summary.clone())
             taps.setdefault("layer_patch_mean", []).append(x[:, 1:].mean(dim=(1,)).clone())
     cls_x = layer_norm(x[:, 0], sd[prefix + "ln_post.weight"], sd[prefix + "ln_post.bias"])  # :126
     cls_x = cls_x @ sd[prefix + "proj"]                                                   # :127
     cls_x = cls_x.view(B, T, -1).mean(dim=1)                                              # :128
-    summary = summary.mean(dim=1)                                                         # :129-130
+    if summary is not None:
+        summary = summary.mean(dim=1)                                                     # :129-130
     return cls_x, summary
 
 
@@ -326,12 +329,13 @@ def vita_forward(
     sd: SD, video: Tensor, tokenized: Sequence[Tensor], *, num_frames: int, num_heads: int,
     num_layers: int, text_heads: int = 8, text_layers: int = 12, n_ctx: int = 8,
     num_global_prompts: int = 8, kapt: bool = False, cntn_embeds=None, taps: Optional[dict] = None,
+    use_summary: bool = True, use_local: bool = True,
 ) -> Dict[str, Tensor]:
     """VitaCLIP.forward(x) with text prompt learning -- VitaCLIP_model.py:241-309."""
     with torch.no_grad():
         feat, summary = vision_encoder(
             sd, video, num_frames=num_frames, num_heads=num_heads, num_layers=num_layers,
-            num_global_prompts=num_global_prompts, taps=taps)
+            num_global_prompts=num_global_prompts, taps=taps, use_summary=use_summary, use_local=use_local)
         prompts = assemble_prompts(sd, tokenized, n_ctx, kapt=kapt, cntn_embeds=cntn_embeds)
         tfs = [text_encoder(sd, p, t, heads=text_heads, layers=text_layers) for p, t in zip(prompts, tokenized)]
         logits, text_features = logit_head(feat, tfs, sd["logit_scale"], sd.get("logit_bias"))
