@@ -449,11 +449,23 @@ def measure_finetune(D: Dist, cfg: dict, steps: int, warmup: int, detailed: bool
                   "serial_value": clips_total / (ms_serial * 1e-3), "serial_ms_per_step": ms_serial / steps}
     # ---- per-kernel CUDA-event breakdown of 3 steps (rank 0, single GPU: the eager all-reduce calls are not kernels of ours)
     if rank == 0 and world == 1:
-        with KernelTimer(TRAIN_KERNELS) as kt:
-            for _ in range(3):
-                tuner.step(clip, labels, memory, mem_labels)
-            torch.cuda.synchronize()
-            per = kt.drain()
+        # eager launches for this part: the timed steps above replay the tower's / text side's CUDA graphs
+        eng, tt = model.visual._engine, getattr(model._text_tower, "_trainer", None)
+        saved = (eng.use_graph, tt.use_graph if tt is not None else None)
+        eng.use_graph = False
+        if tt is not None:
+            tt.use_graph = False
+        try:
+            tuner.step(clip, labels, memory, mem_labels)
+            with KernelTimer(TRAIN_KERNELS) as kt:
+                for _ in range(3):
+                    tuner.step(clip, labels, memory, mem_labels)
+                torch.cuda.synchronize()
+                per = kt.drain()
+        finally:
+            eng.use_graph = saved[0]
+            if tt is not None:
+                tt.use_graph = saved[1]
         for d in per.values():
             d["ms"] /= 3; d["launches"] //= 3; d["flops"] /= 3
         out["per_kernel"] = per

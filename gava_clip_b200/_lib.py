@@ -101,8 +101,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError if the symbol is missing -> loud
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, C.c_int)
-    if lib.gava_version() != 3:
-        raise RuntimeError(f"libgava_sm100 ABI version {lib.gava_version()} != 3")
+    if lib.gava_version() != 4:
+        raise RuntimeError(f"libgava_sm100 ABI version {lib.gava_version()} != 4")
     _lib = lib
     return lib
 

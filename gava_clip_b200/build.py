@@ -18,7 +18,7 @@ LIBDIR = PKG / "lib"
 LIB = LIBDIR / "libgava_sm100.so"
 STAMP = LIBDIR / ".build_stamp"
 SOURCES = ["api.cu", "gemm_tcgen05.cu", "rowwise.cu", "attention.cu", "attention_tc.cu", "precise.cu", "backward.cu",
-           "attention_bwd.cu", "input_stage.cu"]
+           "attention_bwd.cu", "input_stage.cu", "seq_attention_mma.cu"]
 HEADERS = ["common.cuh", "kernels.h", "mma_sync.cuh", "rowwise.cuh", "attention_tc.cuh", "../../include/gava_sm100.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

@@ -13,6 +13,7 @@
 // VitaCLIP_model.py:230-235 (names containing summary / local / global / time_embed).
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace gava {
 
@@ -497,6 +498,9 @@ int temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int B,
 }
 
 int causal_attention_bwd(const float* qkv, const void* dout, void* dqkv, int n_seq, int L, int H, cudaStream_t stream) {
+  static const bool use_mma = [] { const char* e = getenv("GAVA_TEXT_ATTN_MMA"); return !(e && e[0] == '0'); }();
+  if (use_mma && qkv && dout && dqkv && n_seq > 0 && causal_attention_mma_supported(L, H))
+    return causal_attention_bwd_mma(qkv, dout, dqkv, n_seq, L, H, stream);
   return launch_seq_attention_bwd<true, true>(qkv, dout, dqkv, n_seq, L, H, stream, "causal_attention_bwd");
 }
 

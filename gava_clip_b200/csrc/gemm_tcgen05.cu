@@ -11,6 +11,7 @@
 //   cls_proj        training/VitaCLIP_vision_encoder_utils.py:164-165
 //   patch_embed     training/VitaCLIP_vision_encoder_utils.py:215-219
 //   final proj      training/VitaCLIP_vision_encoder.py:127
+#include <memory>
 #include "common.cuh"
 #include "kernels.h"
 #include "rowwise.cuh"
@@ -565,8 +566,43 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
+static int encode_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows);
+static int encode_tmap_bf16_3d(CUtensorMap* m, const void* ptr, long long planes, long long rows, long long cols, long long ld,
+                               long long ld_plane, int box_rows);
+
+// Encoded descriptors are a pure function of (address, shape, pitch, box): the eager fine-tune step issues ~700 GEMM /
+// attention launches over a few hundred distinct operands per step, so each host thread keeps a small direct-mapped cache
+// instead of calling the driver's encoder two or three times per launch.
+struct TmapKey {
+  const void* ptr;
+  long long rows, cols, ld, plane;   // plane: planes << 40 | ld_plane for the 3-D form, -1 for 2-D
+  int box_rows;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && plane == o.plane && box_rows == o.box_rows;
+  }
+};
+struct TmapSlot { TmapKey key; CUtensorMap map; bool valid; };
+constexpr int kTmapSlots = 1024;
+static TmapSlot* tmap_slot(const TmapKey& k) {
+  static thread_local std::unique_ptr<TmapSlot[]> slots;     // heap, not TLS: 1024 x 176 bytes per calling thread
+  if (!slots) slots.reset(new TmapSlot[kTmapSlots]());
+  uint64_t h = reinterpret_cast<uintptr_t>(k.ptr) * 0x9E3779B97F4A7C15ull;
+  h ^= (uint64_t)k.rows * 0xC2B2AE3D27D4EB4Full + (uint64_t)k.cols * 0x165667B19E3779F9ull + (uint64_t)k.ld * 31 +
+       (uint64_t)k.plane * 131 + (uint64_t)k.box_rows;
+  return &slots[(h >> 40) & (kTmapSlots - 1)];
+}
+
 // 2-D bf16 row-major [rows, cols] with row pitch ld (elements); box = [box_rows, 64 cols], 128B swizzle
 int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  const TmapKey key{ptr, rows, cols, ld, -1, box_rows};
+  TmapSlot* slot = tmap_slot(key);
+  if (slot->valid && slot->key == key) { *m = slot->map; return GAVA_OK; }
+  const int rc = encode_tmap_bf16(m, ptr, rows, cols, ld, box_rows);
+  if (rc == GAVA_OK) { slot->key = key; slot->map = *m; slot->valid = true; }
+  return rc;
+}
+
+static int encode_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return GAVA_ERR_DRIVER; }
   if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || ((ld * 2) & 15)) {
@@ -588,6 +624,16 @@ int make_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, long long co
 // Used for TMA STORES of per-frame tiles: rows beyond `rows` are clipped instead of spilling into the next plane.
 int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, long long planes, long long rows, long long cols, long long ld,
                       long long ld_plane, int box_rows) {
+  const TmapKey key{ptr, rows, cols, ld, (planes << 40) | ld_plane, box_rows};
+  TmapSlot* slot = tmap_slot(key);
+  if (slot->valid && slot->key == key) { *m = slot->map; return GAVA_OK; }
+  const int rc = encode_tmap_bf16_3d(m, ptr, planes, rows, cols, ld, ld_plane, box_rows);
+  if (rc == GAVA_OK) { slot->key = key; slot->map = *m; slot->valid = true; }
+  return rc;
+}
+
+static int encode_tmap_bf16_3d(CUtensorMap* m, const void* ptr, long long planes, long long rows, long long cols, long long ld,
+                               long long ld_plane, int box_rows) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return GAVA_ERR_DRIVER; }
   if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || ((ld * 2) & 15) || ((ld_plane * 2) & 15)) {

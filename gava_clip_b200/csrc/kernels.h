@@ -81,6 +81,10 @@ int quickgelu_f32(float* x, long long n, cudaStream_t stream);
 int attention_f32(const float* qkv, const float* kv_aux, float* out, int B, int T, int N0, int G, int H, int n_q,
                   int key_groups, cudaStream_t stream);
 int causal_attention_f32(const float* qkv, float* out, int n_seq, int L, int H, cudaStream_t stream);
+// tensor-core forms for L <= 128 (seq_attention_mma.cu): fp32-accurate 3-term split-bf16 forward, bf16 backward
+bool causal_attention_mma_supported(int L, int H);
+int causal_attention_mma(const float* qkv, float* out, int n_seq, int L, int H, cudaStream_t stream);
+int causal_attention_bwd_mma(const float* qkv, const void* dout, void* dqkv, int n_seq, int L, int H, cudaStream_t stream);
 int prompt_rows_f32(const float* global_prompts, const float* local_prompts, const float* cls_proj_out,
                     const float* summary, const float* ln_w, const float* ln_b, float* out, int G, int B, int T, int D,
                     float eps, cudaStream_t stream);

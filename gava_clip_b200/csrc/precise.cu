@@ -7,6 +7,7 @@
 // instrument, not the throughput path) and the patch-embed assemble step.
 #include "common.cuh"
 #include "kernels.h"
+#include <stdlib.h>
 
 namespace gava {
 
@@ -230,6 +231,9 @@ int attention_f32(const float* qkv, const float* kv_aux, float* out, int B, int 
 
 // causal self-attention over n_seq sequences of L tokens (CLIP text transformer, VitaCLIP_text_encoder.py:67-88)
 int causal_attention_f32(const float* qkv, float* out, int n_seq, int L, int H, cudaStream_t stream) {
+  static const bool use_mma = [] { const char* e = getenv("GAVA_TEXT_ATTN_MMA"); return !(e && e[0] == '0'); }();
+  if (use_mma && qkv && out && n_seq > 0 && causal_attention_mma_supported(L, H))
+    return causal_attention_mma(qkv, out, n_seq, L, H, stream);
   return attention_f32_impl(qkv, nullptr, out, n_seq, 1, L, 0, H, L, 1, 3, stream);
 }
 

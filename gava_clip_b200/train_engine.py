@@ -98,6 +98,7 @@ class TowerTrainer(TowerEngine):
                 ops.transpose_bf16(src.detach(), P[name])   # bf16 [N,K] -> [K,N]
             else:
                 P[name] = src.detach().t().to(self.device, torch.bfloat16).contiguous()
+                self._t_moves = getattr(self, "_t_moves", 0) + 1
             vers[name] = key
 
         D = e.feature_dim
@@ -105,6 +106,7 @@ class TowerTrainer(TowerEngine):
             pw = torch.zeros(D, _ceil_to(e.embed_dim, 128), device=self.device, dtype=torch.bfloat16)
             pw[:, : e.embed_dim] = e.proj.detach().to(self.device, torch.bfloat16)
             P["proj.w"] = pw
+            self._t_moves = getattr(self, "_t_moves", 0) + 1
             vers["proj.w"] = (e.proj.data_ptr(), e.proj._version)
         for i in range(len(e.blocks)):
             k = f"b{i}."
@@ -150,25 +152,80 @@ class TowerTrainer(TowerEngine):
             # ---- last layer, cls rows only (vision_encoder.py:126: nothing else reaches the output)
             "xc_mid": z(BT, D, dt=f32), "xc_out": z(BT, D, dt=f32), "a1c": z(BT, Dm, dt=bf), "hc": z(BT, Dm, dt=bf),
             "dxc": z(BT, D, dt=f32), "dxc_bf": z(BT, D, dt=bf), "g4c": z(BT, Dm, dt=bf), "gDc": z(BT, D, dt=bf),
+            "dxc2": z(BT, D, dt=f32), "dxc2_bf": z(BT, D, dt=bf), "d_sum_ext": z(BT, D, dt=f32),
         }
+        W["gx0"] = W["g4"].view(-1)[: 2 * M * D].view(torch.float32).view(M, D)     # tail scratch: g4 is dead by then
         self.ws[key] = W
         return W
 
     # ------------------------------------------------------------------ forward with tape
     def forward_train(self, video: Tensor) -> Tuple[Tensor, Tensor]:
-        """Same schedule as TowerEngine.encode_frames (incl. the cls-rows-only last layer), activations kept for backward()."""
+        """Same schedule as TowerEngine.encode_frames (incl. the cls-rows-only last layer), activations kept for backward().
+
+        The ~190 launches are replayed from one CUDA graph per clip shape (the tape, the packed weights and the static clip
+        buffer keep their addresses; re-packing after an optimizer step copies in place): the eager fine-tune step spends
+        ~24 ms of host time issuing launches, which bounds small-batch recipes (70 frames x 4 clips per GPU)."""
         self.pack_train()
-        e, P = self.enc, self.packed
         B, T, _, _ = _clip_dims(video)
-        D, N0, G, H = e.feature_dim, int(e.num_patches), e.num_global_prompts, e.num_heads
-        BT, M = B * T, B * T * N0
         W = self.train_ws(B, T)
         # every forward stamps its tape: backward() refuses a tape that a later forward of the same shape overwrote
         self.tape_generation = getattr(self, "tape_generation", 0) + 1
         W["generation"] = self.tape_generation
+        L = len(self.enc.blocks)
+        if not self._train_graph_ok(T):
+            n0 = ops.launch_count()
+            self._forward_train_body(video, W)
+            self.launches_last_call = ops.launch_count() - n0
+            return W["frame_feat"], W["summary"][L - 1]
+        key = ("fwd", tuple(video.shape), video.dtype)
+        ent = self._train_graphs(W).get(key)
+        if ent is None:
+            static_in = torch.empty_like(video)
+            static_in.copy_(video)
+            self._forward_train_body(static_in, W)        # warm-up: kernel attributes, allocator
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):   # a DataLoader thread may be busy with CUDA calls
+                self._forward_train_body(static_in, W)
+            ent = (g, static_in, ops.launch_count() - n0)
+            self._train_graphs(W)[key] = ent
+        g, static_in, n_launch = ent
+        if video.data_ptr() != static_in.data_ptr():
+            static_in.copy_(video)
+        g.replay()
+        self.launches_last_call = n_launch
+        return W["frame_feat"], W["summary"][L - 1]
+
+    def train_input_buffer(self, shape, dtype=torch.float32) -> Optional[Tensor]:
+        """Static clip buffer of the captured training forward for this shape (None before the first step): a caller that
+        uploads straight into it skips the staging copy."""
+        B, T = shape[0], shape[2]
+        W = self.ws.get(("train", B, T))
+        ent = W.get("graphs", {}).get(("fwd", tuple(shape), dtype)) if W is not None else None
+        return ent[1] if ent is not None else None
+
+    # ---- CUDA-graph bookkeeping of the training step
+    def _train_graphs(self, W: Dict[str, object]) -> Dict[tuple, tuple]:
+        """Graphs of the training forward / backward segments of one tape (they die with it); dropped when a packed
+        operand moved (pack() / pack_train() re-allocated instead of copying in place)."""
+        stamp = (self.pack_moves, getattr(self, "_t_moves", 0))
+        if W.get("graph_stamp") != stamp:
+            W["graphs"], W["graph_stamp"] = {}, stamp
+        return W["graphs"]
+
+    def _train_graph_ok(self, T: int) -> bool:
+        # a resized time_embed copy is rebuilt (new address) whenever time_embed changes, i.e. after every optimizer step
+        return (self.use_graph and not torch.cuda.is_current_stream_capturing()
+                and self.packed["time_embed"].shape[0] == T)
+
+    def _forward_train_body(self, video: Tensor, W: Dict[str, object]) -> None:
+        e, P = self.enc, self.packed
+        B, T, _, _ = _clip_dims(video)
+        D, N0, G, H = e.feature_dim, int(e.num_patches), e.num_global_prompts, e.num_heads
+        BT, M = B * T, B * T * N0
         te = self.time_embed_for(T)
         xn, h = W["xn"], W["h"]
-        n0 = ops.launch_count()
 
         if video.dtype == torch.uint8:
             ops.patch_gather_u8(video, W["patches"], None, e.input_norm[0], e.input_norm[1], e.patch_embed.patch_size)
@@ -226,8 +283,6 @@ class TowerTrainer(TowerEngine):
 
         ops.layernorm(W["xc_out"], P["ln_post.w"], P["ln_post.b"], W["cls_bf"], rows=BT, in_row_stride=D)
         ops.gemm(W["cls_bf"], P["proj.wT"], W["frame_feat"], mode=ops.EPI_BIAS_F32)
-        self.launches_last_call = ops.launch_count() - n0
-        return W["frame_feat"], W["summary"][L - 1]
 
     # ------------------------------------------------------------------ backward
     def backward(self, B: int, T: int, d_frame_feat: Optional[Tensor], d_summary: Optional[Tensor],
@@ -245,100 +300,157 @@ class TowerTrainer(TowerEngine):
             raise RuntimeError("backward: the activation tape was overwritten by a later train-mode forward of the same clip "
                                "shape (two forwards before one backward are not supported: the tape is per shape)")
         self._alloc_grads()
-        D, N0, G, H = e.feature_dim, int(e.num_patches), e.num_global_prompts, e.num_heads
-        BT, M = B * T, B * T * N0
-        R = G + 2 * BT
         L = len(e.blocks)
         W = self.train_ws(B, T)
-        g = self.grads
-        dx, dxb, gD = W["dx"], W["dxb"], W["gD"]
-        dx_cls = dx.view(BT, N0 * D)[:, :D]
+        BT = B * T
         hook = getattr(self, "grad_ready_hook", None)   # finetune.FineTuner: per-layer gradient all-reduce overlap
         pending: List = []
         n0 = ops.launch_count()
 
-        # bf16 copy of dx for the dgrad GEMMs: written by the LayerNorm-backward kernels as a by-product; only the BT cls
-        # rows change outside those kernels (ln_post / cls_proj contributions) and are re-cast by a BT-row launch
-        cast_cls = lambda: ops.layernorm(dx, None, None, dxb, rows=BT, in_row_stride=N0 * D, out_row_stride=N0 * D)
-        # ---- frame_feat = ln_post(x_cls) @ proj   (vision_encoder.py:126-127)
-        dx.zero_()
-        if d_frame_feat is not None:
-            Ep = W["dff"].shape[1]
+        # ---- dynamic inputs -> static buffers (outside the replayed segments)
+        have_ff, have_ext = d_frame_feat is not None, d_summary is not None
+        if have_ff:
             dff = W["dff"]
-            if d_frame_feat.shape[1] != Ep:
+            if d_frame_feat.shape[1] != dff.shape[1]:
                 dff.zero_()
                 dff[:, : d_frame_feat.shape[1]].copy_(d_frame_feat)
             else:
                 dff.copy_(d_frame_feat)
-            ops.layernorm(dff, None, None, W["dff_bf"], rows=BT, in_row_stride=Ep)            # f32 -> bf16 cast
-            ops.gemm(W["dff_bf"], P["proj.w"], W["dcls_n"], mode=ops.EPI_BIAS_BF16)
-            ops.layernorm_bwd(W["dcls_n"], W["xc_out"], P["ln_post.w"], W["dxc"], rows=BT, D=D, dx_bf16=W["dxc_bf"])
+        if have_ext:
+            W["d_sum_ext"].copy_(d_summary.reshape(BT, -1))
+
+        # ---- segments: [head + last layer], one per remaining layer, [tail]; without an all-reduce hook they fuse into one
+        use_graph = self._train_graph_ok(T)
+        graphs = self._train_graphs(W) if use_graph else None
+
+        def run_segment(name: str, body) -> None:
+            """A segment consumes the gradient stream in place (dx += ...), so it must execute exactly once per step: the
+            first step runs it eagerly (kernel attributes, allocator), the second captures it (nothing executes during a
+            capture) and replays, every later step only replays."""
+            if graphs is None:
+                body()
+                return
+            key = ("bwd", name, have_ff, have_ext)
+            ent = graphs.get(key)
+            if ent is None:
+                graphs[key] = "seen"
+                body()
+                return
+            if ent == "seen":
+                g = torch.cuda.CUDAGraph()
+                m0 = ops.launch_count()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):   # autograd runs this on its own thread
+                    body()
+                ent = (g, ops.launch_count() - m0)
+                graphs[key] = ent
+                n_warm[0] += ent[1]
+            ent[0].replay()
+            n_replayed[0] += ent[1]
+
+        n_warm, n_replayed = [0], [0]
+        if hook is None:
+            def whole():
+                self._bwd_head(W, B, T, have_ff)
+                for i in reversed(range(L)):
+                    self._bwd_layer(W, B, T, i, have_ext)
+                self._bwd_tail(W, B, T)
+            run_segment("all", whole)
         else:
-            W["dxc"].zero_(); W["dxc_bf"].zero_()
-        ext = None
-        if d_summary is not None:
-            ext = d_summary.contiguous().float()
-
-        for i in reversed(range(L)):
-            k, kb = f"b{i}.", f"blocks.{i}."
-            cp, sm = W["cls_proj"][i], W["summary"][i]
-            if i == L - 1:
-                # ---- last layer: MLP / out-proj / attention-query gradients exist for the BT cls rows only
-                ops.gemm(W["dxc_bf"], P[k + "fc2.wT"], W["g4c"], mode=ops.EPI_DGELU_BF16, aux=W["a1c"])
-                ops.gemm(W["g4c"], P[k + "fc1.wT"], W["gDc"], mode=ops.EPI_BIAS_BF16)
-                ops.layernorm_bwd(W["gDc"], W["xc_mid"], P[k + "norm2.w"], W["dxc"], rows=BT, D=D, add1=W["dxc"],
-                                  dx_bf16=W["dxc_bf"])
-                dx_cls.copy_(W["dxc"])                                               # residual path into the stream's cls rows
-                ops.gemm(W["dxc_bf"], P[k + "out.wT"], gD.view(BT, N0 * D)[:, :D], mode=ops.EPI_BIAS_BF16)   # dO, cls rows of gD
-                W["dqkv"].view(BT * N0, 3, D)[:, 0].zero_()                          # dq of the rows without a query
-                ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G,
-                                  H=H, lse=W["lse"][i], n_q=1, scratch=W["dkv_slots"])
-            else:
-                # ---- MLP: dx += dLN2( (dx W2 * g'(a1)) W1 )
-                ops.gemm(dxb, P[k + "fc2.wT"], W["g4"], mode=ops.EPI_DGELU_BF16, aux=W["a1"][i])
-                ops.gemm(W["g4"], P[k + "fc1.wT"], gD, mode=ops.EPI_BIAS_BF16)
-                ops.layernorm_bwd(gD, W["x_mid"][i], P[k + "norm2.w"], dx, rows=M, D=D, add1=dx, dx_bf16=dxb)
-                # ---- attention: dO = dx Wo; (dq, dk, dv, d kv_aux); dx += dLN1(dqkv Wqkv)
-                ops.gemm(dxb, P[k + "out.wT"], gD, mode=ops.EPI_BIAS_BF16)
-                ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G,
-                                  H=H, lse=W["lse"][i], scratch=W["dkv_slots"])
-            ops.gemm(W["dqkv"], P[k + "qkv.wT"], gD, mode=ops.EPI_BIAS_BF16)
-            ops.layernorm_bwd(gD, W["x_in"][i], P[k + "norm1.w"], dx, rows=M, D=D, add1=dx, dx_bf16=dxb)
-            # ---- K/V-only prompt rows: d kv_aux -> normalised rows -> global / local / summary / cls_proj gradients
-            ops.layernorm(W["dkvaux"].view(2 * R, D), None, None, W["dkvaux_bf"].view(2 * R, D), rows=2 * R, in_row_stride=D)
-            ops.gemm(W["dkvaux_bf"], P[k + "qkv.wT"][:, D:], W["daux_n"], mode=ops.EPI_BIAS_BF16)
-            ops.prompt_rows_bwd(W["daux_n"], P["global_prompts"][i], P[k + "local"], cp, sm, P[k + "norm1.w"],
-                                g["global_prompts"][i], W["d_lcp"], W["d_sum"], ext if i == L - 1 else None, B, T, LN_EPS)
-            ops.group_sum(W["d_lcp"], g[kb + "local_prompts"], outer=B, J=T, inner=1)
-            # ---- summary = cls_proj + out_proj(temporal_attention(qkv(summary_ln(cls_proj))))   (utils.py:168-170)
-            ops.layernorm(W["d_sum"], None, None, W["d_sum_bf"], rows=BT, in_row_stride=D)     # cast
-            ops.gemm(W["d_sum_bf"], P[k + "sout.wT"], W["dsmix"], mode=ops.EPI_BIAS_BF16)
-            self._wgrad(W, W["d_sum"], W["smix"][i], g[kb + "summary_attn_layer.out_proj.weight"])
-            ops.group_sum(W["d_sum"], g[kb + "summary_attn_layer.out_proj.bias"], outer=BT, J=1, inner=1)
-            ops.temporal_attention_bwd(W["sqkv"][i], W["dsmix"], W["dsqkv"], B, T, H)
-            ops.gemm(W["dsqkv"], P[k + "sqkv.wT"], W["dsn"], mode=ops.EPI_BIAS_BF16)
-            self._wgrad(W, W["dsqkv"], W["sum_n"][i], g[kb + "sqkv.weight"])
-            ops.group_sum(W["dsqkv"], g[kb + "sqkv.bias"], outer=BT, J=1, inner=1)
-            g[kb + "summary_ln.weight"].zero_(); g[kb + "summary_ln.bias"].zero_()
-            ops.layernorm_bwd(W["dsn"], cp, P[k + "summary_ln.w"], W["d_cp"], rows=BT, D=D, add1=W["d_lcp"],
-                              add2=W["d_sum"], dx_bf16=W["d_cp_bf"], dw=g[kb + "summary_ln.weight"],
-                              db=g[kb + "summary_ln.bias"])
-            # ---- cls_proj (frozen): dx[cls rows] += d_cp Wc
-            ops.gemm(W["d_cp_bf"], P[k + "cls.wT"], dx_cls, mode=ops.EPI_BIAS_RESID_F32, resid=dx_cls)
-            cast_cls()
-            if hook is not None:
+            for i in reversed(range(L)):
+                def seg(i=i):
+                    if i == L - 1:
+                        self._bwd_head(W, B, T, have_ff)
+                    self._bwd_layer(W, B, T, i, have_ext)
+                run_segment(f"layer{i}", seg)
                 pending.append(hook(self.layer_slices[i]))   # this layer's gradients are final: start their all-reduce now
-
-        # ---- ln_pre and the embedding sum: d time_embed[t] = sum over videos and tokens   (vision_encoder.py:108-113)
-        ops.layernorm_bwd(dx, W["x0_pre"], P["ln_pre.w"], dx, rows=M, D=D)
-        ops.group_sum(dx, g["time_embed"], outer=B, J=T, inner=N0)
-        if hook is not None:
+            run_segment("tail", lambda: self._bwd_tail(W, B, T))
             pending.append(hook(self.head_slice))
             for h in pending:           # stream-level wait: autograd adds these buffers into the parameters' .grad next
                 if h is not None:
                     h.wait()
-        self.bwd_launches_last_call = ops.launch_count() - n0
-        return g
+        # kernels executed by this call: eager launches (minus the ones only recorded during a capture) + replayed ones
+        self.bwd_launches_last_call = ops.launch_count() - n0 - n_warm[0] + n_replayed[0]
+        return self.grads
+
+    def _bwd_head(self, W: Dict[str, object], B: int, T: int, have_ff: bool) -> None:
+        """frame_feat = ln_post(x_cls) @ proj   (vision_encoder.py:126-127): d(frame_feat) in W["dff"] -> W["dxc"]."""
+        e, P = self.enc, self.packed
+        D, BT = e.feature_dim, B * T
+        W["dx"].zero_()
+        if have_ff:
+            Ep = W["dff"].shape[1]
+            ops.layernorm(W["dff"], None, None, W["dff_bf"], rows=BT, in_row_stride=Ep)            # f32 -> bf16 cast
+            ops.gemm(W["dff_bf"], P["proj.w"], W["dcls_n"], mode=ops.EPI_BIAS_BF16)
+            ops.layernorm_bwd(W["dcls_n"], W["xc_out"], P["ln_post.w"], W["dxc"], rows=BT, D=D, dx_bf16=W["dxc_bf"])
+        else:
+            W["dxc"].zero_(); W["dxc_bf"].zero_()
+
+    def _bwd_layer(self, W: Dict[str, object], B: int, T: int, i: int, have_ext: bool) -> None:
+        e, P, g = self.enc, self.packed, self.grads
+        D, N0, G, H = e.feature_dim, int(e.num_patches), e.num_global_prompts, e.num_heads
+        BT, M = B * T, B * T * N0
+        R = G + 2 * BT
+        L = len(e.blocks)
+        dx, dxb, gD = W["dx"], W["dxb"], W["gD"]
+        dx_cls = dx.view(BT, N0 * D)[:, :D]
+        ext = W["d_sum_ext"] if have_ext else None
+        k, kb = f"b{i}.", f"blocks.{i}."
+        cp, sm = W["cls_proj"][i], W["summary"][i]
+        if i == L - 1:
+            # ---- last layer: MLP / out-proj / attention-query gradients exist for the BT cls rows only
+            ops.gemm(W["dxc_bf"], P[k + "fc2.wT"], W["g4c"], mode=ops.EPI_DGELU_BF16, aux=W["a1c"])
+            ops.gemm(W["g4c"], P[k + "fc1.wT"], W["gDc"], mode=ops.EPI_BIAS_BF16)
+            # dxc itself stays untouched (the segment may be replayed): the sum lands in the stream's cls rows
+            ops.layernorm_bwd(W["gDc"], W["xc_mid"], P[k + "norm2.w"], W["dxc2"], rows=BT, D=D, add1=W["dxc"],
+                              dx_bf16=W["dxc2_bf"])
+            dx_cls.copy_(W["dxc2"])                                              # residual path into the stream's cls rows
+            ops.gemm(W["dxc2_bf"], P[k + "out.wT"], gD.view(BT, N0 * D)[:, :D], mode=ops.EPI_BIAS_BF16)   # dO, cls rows of gD
+            W["dqkv"].view(BT * N0, 3, D)[:, 0].zero_()                          # dq of the rows without a query
+            ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G,
+                              H=H, lse=W["lse"][i], n_q=1, scratch=W["dkv_slots"])
+        else:
+            # ---- MLP: dx += dLN2( (dx W2 * g'(a1)) W1 )
+            ops.gemm(dxb, P[k + "fc2.wT"], W["g4"], mode=ops.EPI_DGELU_BF16, aux=W["a1"][i])
+            ops.gemm(W["g4"], P[k + "fc1.wT"], gD, mode=ops.EPI_BIAS_BF16)
+            ops.layernorm_bwd(gD, W["x_mid"][i], P[k + "norm2.w"], dx, rows=M, D=D, add1=dx, dx_bf16=dxb)
+            # ---- attention: dO = dx Wo; (dq, dk, dv, d kv_aux); dx += dLN1(dqkv Wqkv)
+            ops.gemm(dxb, P[k + "out.wT"], gD, mode=ops.EPI_BIAS_BF16)
+            ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G,
+                              H=H, lse=W["lse"][i], scratch=W["dkv_slots"])
+        ops.gemm(W["dqkv"], P[k + "qkv.wT"], gD, mode=ops.EPI_BIAS_BF16)
+        ops.layernorm_bwd(gD, W["x_in"][i], P[k + "norm1.w"], dx, rows=M, D=D, add1=dx, dx_bf16=dxb)
+        # ---- K/V-only prompt rows: d kv_aux -> normalised rows -> global / local / summary / cls_proj gradients
+        ops.layernorm(W["dkvaux"].view(2 * R, D), None, None, W["dkvaux_bf"].view(2 * R, D), rows=2 * R, in_row_stride=D)
+        ops.gemm(W["dkvaux_bf"], P[k + "qkv.wT"][:, D:], W["daux_n"], mode=ops.EPI_BIAS_BF16)
+        ops.prompt_rows_bwd(W["daux_n"], P["global_prompts"][i], P[k + "local"], cp, sm, P[k + "norm1.w"],
+                            g["global_prompts"][i], W["d_lcp"], W["d_sum"], ext if i == L - 1 else None, B, T, LN_EPS)
+        ops.group_sum(W["d_lcp"], g[kb + "local_prompts"], outer=B, J=T, inner=1)
+        # ---- summary = cls_proj + out_proj(temporal_attention(qkv(summary_ln(cls_proj))))   (utils.py:168-170)
+        ops.layernorm(W["d_sum"], None, None, W["d_sum_bf"], rows=BT, in_row_stride=D)     # cast
+        ops.gemm(W["d_sum_bf"], P[k + "sout.wT"], W["dsmix"], mode=ops.EPI_BIAS_BF16)
+        self._wgrad(W, W["d_sum"], W["smix"][i], g[kb + "summary_attn_layer.out_proj.weight"])
+        ops.group_sum(W["d_sum"], g[kb + "summary_attn_layer.out_proj.bias"], outer=BT, J=1, inner=1)
+        ops.temporal_attention_bwd(W["sqkv"][i], W["dsmix"], W["dsqkv"], B, T, H)
+        ops.gemm(W["dsqkv"], P[k + "sqkv.wT"], W["dsn"], mode=ops.EPI_BIAS_BF16)
+        self._wgrad(W, W["dsqkv"], W["sum_n"][i], g[kb + "sqkv.weight"])
+        ops.group_sum(W["dsqkv"], g[kb + "sqkv.bias"], outer=BT, J=1, inner=1)
+        g[kb + "summary_ln.weight"].zero_(); g[kb + "summary_ln.bias"].zero_()
+        ops.layernorm_bwd(W["dsn"], cp, P[k + "summary_ln.w"], W["d_cp"], rows=BT, D=D, add1=W["d_lcp"],
+                          add2=W["d_sum"], dx_bf16=W["d_cp_bf"], dw=g[kb + "summary_ln.weight"],
+                          db=g[kb + "summary_ln.bias"])
+        # ---- cls_proj (frozen): dx[cls rows] += d_cp Wc; then refresh the bf16 copy of dx's cls rows (the LayerNorm-
+        # backward kernels keep the other rows of dxb current as a by-product)
+        ops.gemm(W["d_cp_bf"], P[k + "cls.wT"], dx_cls, mode=ops.EPI_BIAS_RESID_F32, resid=dx_cls)
+        ops.layernorm(dx, None, None, dxb, rows=BT, in_row_stride=N0 * D, out_row_stride=N0 * D)
+
+    def _bwd_tail(self, W: Dict[str, object], B: int, T: int) -> None:
+        """ln_pre and the embedding sum: d time_embed[t] = sum over videos and tokens   (vision_encoder.py:108-113)."""
+        e, P, g = self.enc, self.packed, self.grads
+        D, N0 = e.feature_dim, int(e.num_patches)
+        M = B * T * N0
+        # out of place (W["gx0"]): a replayed segment must not consume its own input
+        ops.layernorm_bwd(W["dx"], W["x0_pre"], P["ln_pre.w"], W["gx0"], rows=M, D=D)
+        ops.group_sum(W["gx0"], g["time_embed"], outer=B, J=T, inner=N0)
 
     def _wgrad(self, W: Dict[str, object], dy: Tensor, x: Tensor, out: Tensor) -> None:
         """out[N, K] (f32) = dy[rows, N]^T x[rows, K] on the tensor cores: both operands transposed to [*, rows_pad]."""

@@ -150,6 +150,7 @@ class TowerEngine:
         self.defer_resid = os.environ.get("GAVA_DEFER_RESID", "1") != "0"
         self.side_stream = torch.cuda.Stream(device) if device.type == "cuda" else None
         self.launches_last_call = 0      # sm_100a kernels launched (or replayed) by the last run()
+        self.pack_moves = 0              # times pack() re-allocated (instead of refreshing in place) a packed operand
         # parity instrument (tests): a dict here receives, per layer, clones of the cls rows of the residual stream and of the
         # summary tokens -- the tensors the reference's per-block forward hooks see (VitaCLIP_vision_encoder.py:116-121).
         # Only honoured by eager runs (a replayed graph cannot clone per layer).
@@ -254,6 +255,7 @@ class TowerEngine:
         self.signature = sig
         if moved:
             self.graphs.clear()  # captured graphs hold pointers into the old packed tensors
+            self.pack_moves += 1  # TowerTrainer's graphs (kept with the tapes) compare this stamp
 
     def pack_precise(self) -> Dict[str, Tensor]:
         """hi/lo bf16 pairs of every GEMM weight for the fp32-accuracy path (w = hi + lo up to 2^-17)."""

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define GAVA_ABI_VERSION 3
+#define GAVA_ABI_VERSION 4
 
 /* epilogue modes of gava_gemm_bf16_fwd */
 enum gava_epilogue_mode {

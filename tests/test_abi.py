@@ -21,7 +21,7 @@ def test_header_symbols_exported_and_bound():
         assert hasattr(lib, s), f"{s} declared in include/gava_sm100.h but not exported"
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature in gava_clip_b200/_lib.py"
     assert sorted(_lib.SIGNATURES) == syms
-    assert lib.gava_version() == 3
+    assert lib.gava_version() == 4
 
 
 def test_epilogue_struct_layout():

@@ -229,8 +229,10 @@ def test_adamw_matches_torch(cuda):
     assert _rel(p, ref.detach()) < 1e-5
 
 
-@pytest.mark.parametrize("n_seq,L,H", [(15, 77, 8), (3, 20, 2)])
+@pytest.mark.parametrize("n_seq,L,H", [(15, 77, 8), (3, 20, 2), (2, 128, 1), (4, 16, 2), (2, 1, 1), (1, 97, 3)])
 def test_causal_attention_bwd(cuda, n_seq, L, H):
+    """Tensor-core causal attention of the text transformer (seq_attention_mma.cu): the 3-term split-bf16 forward keeps
+    fp32 accuracy (1e-4 of an fp32 PyTorch evaluation), the bf16 backward the 2e-2 budget of the tower's attention backward."""
     from gava_clip_b200 import ops
     g = _gen(n_seq + L + H)
     D = H * 64
@@ -242,9 +244,12 @@ def test_causal_attention_bwd(cuda, n_seq, L, H):
     s = (torch.einsum("bqhc,bkhc->bhqk", q / 8.0, k) + mask).softmax(-1)
     ref_out = torch.einsum("bhqk,bkhc->bqhc", s, v).reshape(n_seq * L, D)
     ref_out.backward(dout.float())
-    out = torch.empty(n_seq * L, D, device=cuda)
+    out = torch.full((n_seq * L, D), float("nan"), device=cuda)
     ops.causal_attention_f32(qkv, out, n_seq=n_seq, L=L, H=H)
-    assert _rel(out, ref_out.detach()) < 1e-4
-    dqkv = torch.empty(n_seq * L, 3 * D, device=cuda, dtype=torch.bfloat16)
+    e_fwd = _rel(out, ref_out.detach())
+    dqkv = torch.full((n_seq * L, 3 * D), float("nan"), device=cuda, dtype=torch.bfloat16)
     ops.causal_attention_bwd(qkv, dout, dqkv, n_seq=n_seq, L=L, H=H)
-    assert _rel(dqkv.float(), qr.grad) < 1e-2
+    e_bwd = _rel(dqkv.float(), qr.grad)
+    print(f"\n[causal attention {n_seq}x{L}x{H}] forward rel err {e_fwd:.2e}, backward rel err {e_bwd:.2e}")
+    assert e_fwd < 1e-4
+    assert e_bwd < 2e-2

@@ -419,11 +419,19 @@ def test_finetune_gradients_match_oracle(cuda, name):
     # fixed order, attention_bwd's slot path); only leaf reductions that use f32 atomics (bias / LayerNorm-weight /
     # time_embed / local_prompts sums) vary in the last bits.  k_proj.* of the summary attention are cancellation-dominated.
     g1 = {n: params[n].grad.clone() for n in vis}
-    Fn.cross_entropy(model(video.to(cuda))[0], labels.to(cuda)).backward()
-    for n in vis:
-        if "k_proj" in n:
-            continue
-        assert rel_l2(params[n].grad, 2 * g1[n]) < 1e-4, n
+    # Pass 1 above ran the tower's forward / backward eagerly, pass 2 captures them into CUDA graphs and replays, pass 3 only
+    # replays (train_engine.TowerTrainer): all three must produce the same gradient.
+    eng = model.visual._engine
+    for k_pass in (2, 3):
+        Fn.cross_entropy(model(video.to(cuda))[0], labels.to(cuda)).backward()
+        for n in vis:
+            if "k_proj" in n:
+                continue
+            assert rel_l2(params[n].grad, k_pass * g1[n]) < 1e-4, (k_pass, n)
+    tape = eng.ws[("train", B, kw["num_frames"])]
+    kinds = {k[0] for k, v in tape["graphs"].items() if isinstance(v, tuple)}
+    assert kinds == {"fwd", "bwd"}, f"training graphs not captured: {tape['graphs'].keys()}"
+    assert eng.launches_last_call > 0 and eng.bwd_launches_last_call > 0
 
 
 def test_text_side_finetune_with_frozen_tower(cuda):
