@@ -247,7 +247,8 @@ class KernelTimer:
                 r = _f(*a, **k)
                 e1.record()
                 fl = 2.0 * a[0].shape[0] * a[0].shape[1] * a[1].shape[0] if _n == "gemm" else 0.0
-                self.records.append((_n, e0, e1, fl))
+                tag = f"M{a[0].shape[0]}_N{a[1].shape[0]}_K{a[0].shape[1]}_mode{k.get('mode')}" if _n == "gemm" else None
+                self.records.append((_n, e0, e1, fl, tag))
                 return r
             setattr(self.ops, n, g)
         return self
@@ -258,11 +259,16 @@ class KernelTimer:
 
     def drain(self) -> dict:
         """per-kernel {ms, launches, flops} of the records so far (call after a synchronize); clears the records"""
-        per = {}
-        for n, e0, e1, fl in self.records:
+        per, shapes = {}, {}
+        for n, e0, e1, fl, tag in self.records:
             d = per.setdefault(n, {"ms": 0.0, "launches": 0, "flops": 0.0})
-            d["ms"] += e0.elapsed_time(e1); d["launches"] += 1; d["flops"] += fl
+            ms = e0.elapsed_time(e1)
+            d["ms"] += ms; d["launches"] += 1; d["flops"] += fl
+            if tag is not None:
+                t = shapes.setdefault(tag, {"ms": 0.0, "launches": 0, "flops": 0.0})
+                t["ms"] += ms; t["launches"] += 1; t["flops"] += fl
         self.records = []
+        self.gemm_shapes = shapes          # per (M, N, K, epilogue mode) of the same records
         return per
 
 
@@ -290,6 +296,7 @@ def gemm_roofline(model, clip, peaks, ms_graph_step: float, eager_steps: int = 5
                     model(clip)
                     torch.cuda.synchronize()
                     steps.append(kt.drain())
+                gemm_shapes = kt.gemm_shapes
     finally:
         eng.use_graph = saved
     shares, eager_tf, flops = [], [], steps[0]["gemm"]["flops"]
@@ -317,7 +324,11 @@ def gemm_roofline(model, clip, peaks, ms_graph_step: float, eager_steps: int = 5
             "gemm_share_of_step": {"median": share, "min": min(shares), "max": max(shares)},
             "eager_event_tflops": {"median": med, "min": min(eager_tf), "max": max(eager_tf),
                                    "spread": (max(eager_tf) - min(eager_tf)) / med, "stable_within_3pct": (max(eager_tf) - min(eager_tf)) / med < 0.03},
-            "kernel_share_of_step": {n: round(d["ms"] / tot_last, 4) for n, d in last.items()}}
+            "kernel_share_of_step": {n: round(d["ms"] / tot_last, 4) for n, d in last.items()},
+            # the large GEMM shapes of the last eager step: average launch (us, CUDA events) and TFLOP/s
+            "gemm_shapes_eager": {t: {"launches": d["launches"], "avg_us": round(1e3 * d["ms"] / d["launches"], 1),
+                                      "tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 1)}
+                                  for t, d in sorted(gemm_shapes.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
 
 
 # ------------------------------------------------------------------------------------------- fine-tune step (config 5)

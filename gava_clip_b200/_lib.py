@@ -17,6 +17,8 @@ EPI_BIAS_RESID_F32 = 2
 EPI_BIAS_F32 = 3
 EPI_PATCH_F32 = 4
 EPI_DGELU_BF16 = 5
+EPI_LNFOLD_BF16 = 7
+EPI_BIAS_RESID_STATS_F32 = 8
 
 
 class GemmEpilogue(C.Structure):
@@ -38,6 +40,14 @@ class GemmEpilogue(C.Structure):
         ("ld_aux", C.c_int64),
         ("aux_out", C.c_void_p),
         ("max_ctas", C.c_int32),
+        ("copy_out", C.c_void_p),
+        ("ld_copy", C.c_int64),
+        ("stats_out", C.c_void_p),
+        ("stats_in", C.c_void_p),
+        ("ld_stats", C.c_int64),
+        ("colsum", C.c_void_p),
+        ("n_slots", C.c_int32),
+        ("eps", C.c_float),
     ]
 
 
@@ -50,6 +60,7 @@ SIGNATURES = {
     "gava_init": [],
     "gava_workspace_bytes": [_i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32],
     "gava_gemm_bf16_fwd": [_p, _i64, _p, _i64, _i64, _i64, _i64, C.POINTER(GemmEpilogue), _p],
+    "gava_gemm_stats_slots": [_i64, _i64],
     "gava_layernorm_fwd": [_p, _i64, _p, _p, _p, _i64, _i32, _i64, _i32, _f32, _p],
     "gava_layernorm2_fwd": [_p, _i64, _p, _p, _p, _i64, _p, _p, _p, _i64, _i64, _i32, _f32, _p],
     "gava_layernorm_resid_fwd": [_p, _i64, _p, _i64, _p, _p, _p, _i64, _i32, _i64, _i32, _f32, _p],

@@ -4,6 +4,7 @@
 #include "kernels.h"
 
 #include <stdarg.h>
+#include <stddef.h>
 
 namespace gava {
 
@@ -53,6 +54,7 @@ int64_t gava_workspace_bytes(int32_t B, int32_t T, int32_t N0, int32_t D, int32_
   int64_t infer = 0;
   infer += BT * (N0 - 1) * Kpad * 2;            // patches
   infer += M * D * 4 + M * D * 2 * 2;           // x, xn, delta
+  infer += M * D * 2 + M * (D / 64) * 2 * 4;    // xb, xstats (LayerNorm fold; at most D/64 column slices per row)
   infer += M * 3 * D * 2 + M * Dm * 2;          // qkv, h
   infer += BT * D * (2 + 2 + 4 + 4 + 2 + 2 + 4) + BT * 3 * D * 2;   // cls_bf, cls_bf2, cls_proj, x_cls, sum_n, smix, summary, sqkv
   infer += R * D * 2 + R * 2 * D * 2;           // aux_n, kvaux
@@ -69,10 +71,17 @@ int64_t gava_workspace_bytes(int32_t B, int32_t T, int32_t N0, int32_t D, int32_
   return infer + tape + scratch;
 }
 
+static_assert(sizeof(gava_gemm_epilogue) == 168 && offsetof(gava_gemm_epilogue, max_ctas) == 104 &&
+                  offsetof(gava_gemm_epilogue, copy_out) == 112 && offsetof(gava_gemm_epilogue, stats_in) == 136 &&
+                  offsetof(gava_gemm_epilogue, colsum) == 152 && offsetof(gava_gemm_epilogue, eps) == 164,
+              "gava_gemm_epilogue layout is part of the ABI (ctypes mirror: _lib.GemmEpilogue)");
+
 int gava_gemm_bf16_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
                        const gava_gemm_epilogue* epi, void* stream) {
   return gemm_bf16(A, lda, W, ldw, M, N, K, epi, (cudaStream_t)stream);
 }
+
+int32_t gava_gemm_stats_slots(int64_t M, int64_t N) { return gemm_stats_slots(M, N); }
 
 int gava_layernorm_fwd(const float* x, int64_t in_row_stride, const float* weight, const float* bias, void* out,
                        int64_t out_row_stride, int32_t out_bf16, int64_t rows, int32_t D, float eps, void* stream) {

@@ -56,6 +56,17 @@ struct GemmArgs {
   const __nv_bfloat16* aux;  // EPI_DGELU_BF16: fc1 pre-activations bf16 [M, ld_aux]
   __nv_bfloat16* aux_out;    // EPI_BIAS_GELU_BF16 (optional): also store the pre-activations acc + bias here, pitch ld_aux
   long long ld_aux;
+  // LayerNorm folding.  Producer (EPI_BIAS_RESID_STATS_F32): also bf16(out) -> copy_out and per-row partial
+  // (sum, sum of squares) of each epilogue warp's column slice -> stats_out [M, n_slots, 2].
+  __nv_bfloat16* copy_out;
+  long long ld_copy;
+  float* stats_out;
+  // Consumer (EPI_LNFOLD_BF16): A is the raw bf16 copy, W carries the norm's weight; out = rstd_r (acc - mean_r colsum[n]) + bias[n]
+  const float* stats_in;     // [rows, n_slots, 2], row pitch ld_stats floats
+  long long ld_stats;
+  const float* colsum;       // [N]
+  int n_slots;
+  float eps;
 };
 
 // ---- epilogue: TMEM -> registers (one row per thread) -> swizzled smem staging -> transposed, coalesced global access.
@@ -71,19 +82,49 @@ __device__ __forceinline__ uint32_t dgelu_mul2(uint32_t dy2, uint32_t a2) {
                      __bfloat162float(d.y) * quick_gelu_grad(__bfloat162float(a.y)));
 }
 
+// Row statistics carried through one warp's share of a tile: fold = (rstd, -mean * rstd) of this thread's row and the
+// staged colsum slice (consumer); rs / rq = running sum / sum of squares of the 8 rows this lane touches in the transposed
+// store loop (producer).
+struct FoldRow { float rstd, nmr; const float* colsum_s; };
+
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage, int row0, int col0,
                                                const uint32_t (&v)[32], const float4 (&resid)[8], const float* bias_s,
-                                               int lane) {
-  if constexpr (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16 || MODE == EPI_DGELU_BF16) {
+                                               int lane, const FoldRow& fold, float (&rs)[8], float (&rq)[8]) {
+  if constexpr (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16 || MODE == EPI_DGELU_BF16 || MODE == EPI_LNFOLD_BF16) {
     float acc[32];
     {  // bias of this chunk from shared memory (staged per tile before the accumulator wait; broadcast LDS.128)
       const float4* b4 = reinterpret_cast<const float4*>(bias_s);
+      if constexpr (MODE == EPI_LNFOLD_BF16) {
+        // LayerNorm applied after the contraction: rstd (acc - mean colsum) + bias'.  With row-centred weights
+        // (colsum == NULL: sum_k W'[n,k] = 0) the mean drops out inside the contraction and one FMA per element is left.
+        if (fold.colsum_s != nullptr) {
+          const float4* c4 = reinterpret_cast<const float4*>(fold.colsum_s);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b = b4[j];
-        acc[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x; acc[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-        acc[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z; acc[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = b4[j], c = c4[j];
+            acc[4 * j + 0] = fmaf(fold.rstd, __uint_as_float(v[4 * j + 0]), fmaf(fold.nmr, c.x, b.x));
+            acc[4 * j + 1] = fmaf(fold.rstd, __uint_as_float(v[4 * j + 1]), fmaf(fold.nmr, c.y, b.y));
+            acc[4 * j + 2] = fmaf(fold.rstd, __uint_as_float(v[4 * j + 2]), fmaf(fold.nmr, c.z, b.z));
+            acc[4 * j + 3] = fmaf(fold.rstd, __uint_as_float(v[4 * j + 3]), fmaf(fold.nmr, c.w, b.w));
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 b = b4[j];
+            acc[4 * j + 0] = fmaf(fold.rstd, __uint_as_float(v[4 * j + 0]), b.x);
+            acc[4 * j + 1] = fmaf(fold.rstd, __uint_as_float(v[4 * j + 1]), b.y);
+            acc[4 * j + 2] = fmaf(fold.rstd, __uint_as_float(v[4 * j + 2]), b.z);
+            acc[4 * j + 3] = fmaf(fold.rstd, __uint_as_float(v[4 * j + 3]), b.w);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 b = b4[j];
+          acc[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + b.x; acc[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+          acc[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z; acc[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+        }
       }
     }
     // stage as bf16 (row pitch 64 B = 4 chunks of 16 B, chunk' = chunk ^ ((row >> 1) & 3)), then store transposed
@@ -138,9 +179,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
       float4 a = *reinterpret_cast<const float4*>(stage + r * 128 + ((c ^ (r & 7)) << 4));
       a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
       if (grow < p.M) {
-        if constexpr (MODE == EPI_BIAS_RESID_F32) {
+        if constexpr (MODE == EPI_BIAS_RESID_F32 || MODE == EPI_BIAS_RESID_STATS_F32) {
           a.x += resid[i].x; a.y += resid[i].y; a.z += resid[i].z; a.w += resid[i].w;
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)grow * p.ldo + col) = a;
+          if constexpr (MODE == EPI_BIAS_RESID_STATS_F32) {
+            // the next LayerNorm's operand (raw bf16 copy) and its row statistics, from the values still in registers
+            *reinterpret_cast<uint2*>(p.copy_out + (long long)grow * p.ld_copy + col) =
+                make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+            rs[i] += (a.x + a.y) + (a.z + a.w);
+            rq[i] = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, rq[i]))));
+          }
         } else if constexpr (MODE == EPI_BIAS_F32) {
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)grow * p.ldo + col) = a;
         } else {  // EPI_PATCH_F32: + pos_embed[1+n] + time_embed[t], scatter to the frame's token slot
@@ -164,11 +212,34 @@ template <int MODE, int NCH>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage, float* bias_s, uint64_t* tmem_full_bar,
                                               uint32_t full_phase, uint32_t t_addr, int row0, int col_base, int lane,
                                               long long& dbg_wait) {
-  if constexpr (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16 || MODE == EPI_DGELU_BF16) {
+  FoldRow fold;
+  fold.rstd = 1.f; fold.nmr = 0.f; fold.colsum_s = nullptr;
+  float rs[8], rq[8];
+  if constexpr (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16 || MODE == EPI_DGELU_BF16 || MODE == EPI_LNFOLD_BF16) {
     static_assert(NCH * 32 <= 128, "one float4 per lane covers the warp's columns");
     if (lane < NCH * 8) {
       const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + col_base) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
       reinterpret_cast<float4*>(bias_s)[lane] = b;   // the 4 lane-quarter warps of a column half write identical values
+    }
+    if constexpr (MODE == EPI_LNFOLD_BF16) {
+      // colsum slice into the unused upper half of this warp's staging buffer (bf16 staging needs 2 KB of the 4 KB);
+      // this thread's row statistics from the producer's partials -- all before the accumulator wait
+      if (p.colsum != nullptr) {
+        float* cs = reinterpret_cast<float*>(stage + 2048);
+        if (lane < NCH * 8) reinterpret_cast<float4*>(cs)[lane] = __ldg(reinterpret_cast<const float4*>(p.colsum + col_base) + lane);
+        fold.colsum_s = cs;
+      }
+      const int grow = row0 + lane;
+      if (grow < p.M) {
+        const float2* st = reinterpret_cast<const float2*>(p.stats_in + (long long)grow * p.ld_stats);
+        float sm = 0.f, sq = 0.f;
+        for (int j = 0; j < p.n_slots; ++j) { const float2 t = __ldg(st + j); sm += t.x; sq += t.y; }
+        const float inv_k = 1.0f / (float)p.K;
+        const float mean = sm * inv_k;
+        const float var = fmaxf(fmaf(-mean, mean, sq * inv_k), 0.f);
+        fold.rstd = rsqrtf(var + p.eps);
+        fold.nmr = -mean * fold.rstd;
+      }
     }
     __syncwarp();
 #if GAVA_GEMM_DEBUG == 4
@@ -189,10 +260,16 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage,
       uint32_t (&nxt)[32] = (cc & 1) ? va : vb;
       if (cc + 1 < NCH) tmem_ld_32x32(t_addr + (uint32_t)((cc + 1) * 32), nxt);
 #if GAVA_GEMM_DEBUG != 1
-      epilogue_chunk<MODE>(p, stage, row0, col_base + cc * 32, cur, resid, bias_s + cc * 32, lane);
+      FoldRow fc = fold;
+      if constexpr (MODE == EPI_LNFOLD_BF16) fc.colsum_s = fold.colsum_s ? fold.colsum_s + cc * 32 : nullptr;
+      epilogue_chunk<MODE>(p, stage, row0, col_base + cc * 32, cur, resid, bias_s + cc * 32, lane, fc, rs, rq);
 #endif
     }
   } else {
+    if constexpr (MODE == EPI_BIAS_RESID_STATS_F32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
+    }
 #if GAVA_GEMM_DEBUG == 4
     const long long t0 = clock64();
 #endif
@@ -205,7 +282,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage,
     for (int cc = 0; cc < NCH; ++cc) {
       const int col0 = col_base + cc * 32;
       float4 resid[8];
-      if constexpr (MODE == EPI_BIAS_RESID_F32) {  // coalesced residual loads, in flight while TMEM is read
+      if constexpr (MODE == EPI_BIAS_RESID_F32 || MODE == EPI_BIAS_RESID_STATS_F32) {  // coalesced residual loads, in flight while TMEM is read
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int grow = row0 + 4 * i + (lane >> 3);
@@ -229,8 +306,23 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage,
 #if GAVA_GEMM_DEBUG == 6   // experiment: residual loads but no stores
       if (v[0] == 0x7fc12345u && resid[0].x == 1.2345f) reinterpret_cast<uint32_t*>(p.out)[0] = v[3];
 #elif GAVA_GEMM_DEBUG != 1
-      epilogue_chunk<MODE>(p, stage, row0, col0, v, resid, nullptr, lane);
+      epilogue_chunk<MODE>(p, stage, row0, col0, v, resid, nullptr, lane, fold, rs, rq);
 #endif
+    }
+    if constexpr (MODE == EPI_BIAS_RESID_STATS_F32) {
+      // the 8 lanes that share a row in the transposed store loop combine their partials; slot = this warp's column slice
+      const int slot = col_base / (NCH * 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int o = 1; o <= 4; o <<= 1) {
+          rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], o);
+          rq[i] += __shfl_xor_sync(0xffffffffu, rq[i], o);
+        }
+        const int grow = row0 + 4 * i + (lane >> 3);
+        if ((lane & 7) == 0 && grow < p.M)
+          *reinterpret_cast<float2*>(p.stats_out + ((long long)grow * p.n_slots + slot) * 2) = make_float2(rs[i], rq[i]);
+      }
     }
   }
 }
@@ -712,6 +804,8 @@ static int dispatch_mode2(int mode, const CUtensorMap& ta, const CUtensorMap& tb
     case EPI_BIAS_F32: return launch_gemm2<EPI_BIAS_F32>(ta, tb, a, s);
     case EPI_PATCH_F32: return launch_gemm2<EPI_PATCH_F32>(ta, tb, a, s);
     case EPI_DGELU_BF16: return launch_gemm2<EPI_DGELU_BF16>(ta, tb, a, s);
+    case EPI_LNFOLD_BF16: return launch_gemm2<EPI_LNFOLD_BF16>(ta, tb, a, s, max_ctas);
+    case EPI_BIAS_RESID_STATS_F32: return launch_gemm2<EPI_BIAS_RESID_STATS_F32>(ta, tb, a, s);
   }
   set_error("gemm: unknown epilogue mode %d", mode);
   return GAVA_ERR_ARG;
@@ -726,9 +820,24 @@ static int dispatch_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tb,
     case EPI_BIAS_F32: return launch_gemm<BN, EPI_BIAS_F32>(ta, tb, a, s);
     case EPI_PATCH_F32: return launch_gemm<BN, EPI_PATCH_F32>(ta, tb, a, s);
     case EPI_DGELU_BF16: return launch_gemm<BN, EPI_DGELU_BF16>(ta, tb, a, s);
+    case EPI_LNFOLD_BF16: return launch_gemm<BN, EPI_LNFOLD_BF16>(ta, tb, a, s);
+    case EPI_BIAS_RESID_STATS_F32: return launch_gemm<BN, EPI_BIAS_RESID_STATS_F32>(ta, tb, a, s);
   }
   set_error("gemm: unknown epilogue mode %d", mode);
   return GAVA_ERR_ARG;
+}
+
+static long long gemm_small_m() {
+  static const long long v = [] { const char* e = getenv("GAVA_SMALL_M"); return e ? atoll(e) : 2048LL; }();
+  return v;
+}
+
+// Column slices per row of the statistics a EPI_BIAS_RESID_STATS_F32 launch of this shape writes: one per epilogue warp
+// column share (128 columns with the 256-wide tiles, 64 with the 128-wide ones the small-M shapes use).
+int gemm_stats_slots(long long M, long long N) {
+  if (M <= 0 || N <= 0 || (N % 128) != 0) return 0;
+  const bool wide = (N % 256 == 0) && M > gemm_small_m();
+  return (int)(N / (wide ? 128 : 64));
 }
 
 int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long long M, long long N, long long K,
@@ -738,7 +847,20 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
     set_error("gemm: unsupported shape M=%lld N=%lld K=%lld (need K%%64==0, N%%128==0)", M, N, K);
     return GAVA_ERR_SHAPE;
   }
-  if (epi->mode == EPI_BIAS_RESID_F32 && !epi->resid) { set_error("gemm: residual epilogue without resid"); return GAVA_ERR_ARG; }
+  if ((epi->mode == EPI_BIAS_RESID_F32 || epi->mode == EPI_BIAS_RESID_STATS_F32) && !epi->resid) {
+    set_error("gemm: residual epilogue without resid");
+    return GAVA_ERR_ARG;
+  }
+  if (epi->mode == EPI_BIAS_RESID_STATS_F32 &&
+      (!epi->copy_out || !epi->stats_out || (epi->ld_copy & 3) || epi->n_slots != gemm_stats_slots(M, N))) {
+    set_error("gemm: stats epilogue needs copy_out (pitch %% 4 == 0), stats_out and n_slots == gava_gemm_stats_slots(M, N)");
+    return GAVA_ERR_ARG;
+  }
+  if (epi->mode == EPI_LNFOLD_BF16 && (!epi->stats_in || epi->n_slots <= 0 || epi->ld_stats < 2LL * epi->n_slots ||
+                                       (epi->ld_stats & 1) || !(epi->eps > 0.f))) {
+    set_error("gemm: LayerNorm-fold epilogue needs stats_in (pitch >= 2 n_slots, even), n_slots > 0, eps > 0");
+    return GAVA_ERR_ARG;
+  }
   if (epi->mode == EPI_PATCH_F32 && (!epi->pos || !epi->time_embed || epi->group <= 0 || epi->T <= 0)) {
     set_error("gemm: patch epilogue needs pos/time_embed/group/T");
     return GAVA_ERR_ARG;
@@ -748,8 +870,7 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
   static const bool use_pair = [] { const char* e = getenv("GAVA_GEMM_PAIR"); return !(e && e[0] == '0'); }();
   // CTA-pair kernel for every N % 256 == 0 shape; the handful-of-tiles GEMMs of the temporal-message chain (M = B*T rows)
   // are latency-bound and spread over more SMs with the single-CTA 128x128 tiles (GAVA_SMALL_M: row threshold)
-  static const long long small_m = [] { const char* e = getenv("GAVA_SMALL_M"); return e ? atoll(e) : 2048LL; }();
-  const bool small = M <= small_m;
+  const bool small = M <= gemm_small_m();
   const bool pair = use_pair && bn == 256 && !small;
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16(&ta, A, M, K, lda, BM);
@@ -763,7 +884,11 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
   a.out = epi->out; a.ldo = epi->ldo;
   a.group = epi->group; a.group_stride = epi->group_stride; a.row_offset = epi->row_offset;
   a.pos = epi->pos; a.time_embed = epi->time_embed; a.T = epi->T;
-  a.aux = (epi->mode == EPI_DGELU_BF16 || epi->mode == EPI_BIAS_RESID_F32) ? reinterpret_cast<const __nv_bfloat16*>(epi->aux) : nullptr;
+  a.aux = (epi->mode == EPI_DGELU_BF16 || epi->mode == EPI_BIAS_RESID_F32 || epi->mode == EPI_BIAS_RESID_STATS_F32)
+              ? reinterpret_cast<const __nv_bfloat16*>(epi->aux) : nullptr;
+  a.copy_out = reinterpret_cast<__nv_bfloat16*>(epi->copy_out); a.ld_copy = epi->ld_copy;
+  a.stats_out = epi->stats_out; a.stats_in = epi->stats_in; a.ld_stats = epi->ld_stats;
+  a.colsum = epi->colsum; a.n_slots = epi->n_slots; a.eps = epi->eps;
   a.ld_aux = epi->ld_aux;
   a.aux_out = epi->mode == EPI_BIAS_GELU_BF16 ? reinterpret_cast<__nv_bfloat16*>(epi->aux_out) : nullptr;
   if (pair) return dispatch_mode2(epi->mode, ta, tb, a, stream, epi->max_ctas);

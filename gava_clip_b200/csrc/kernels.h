@@ -14,6 +14,8 @@ enum : int {
   EPI_BIAS_F32 = GAVA_EPI_BIAS_F32,
   EPI_PATCH_F32 = GAVA_EPI_PATCH_F32,
   EPI_DGELU_BF16 = GAVA_EPI_DGELU_BF16,
+  EPI_LNFOLD_BF16 = GAVA_EPI_LNFOLD_BF16,
+  EPI_BIAS_RESID_STATS_F32 = GAVA_EPI_BIAS_RESID_STATS_F32,
 };
 
 int num_sms();         // of the CURRENT device
@@ -27,6 +29,7 @@ int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, long long planes, long lo
 
 int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long long M, long long N, long long K,
               const gava_gemm_epilogue* epi, cudaStream_t stream);
+int gemm_stats_slots(long long M, long long N);
 
 int layernorm(const float* x, long long in_row_stride, const float* w, const float* b, void* out,
               long long out_row_stride, int out_bf16, long long rows, int D, float eps, cudaStream_t stream);

@@ -12,8 +12,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32,
-                   EPI_DGELU_BF16, EPI_PATCH_F32, GemmEpilogue)
+from ._lib import (EPI_BIAS_BF16, EPI_BIAS_F32, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_BIAS_RESID_STATS_F32,
+                   EPI_DGELU_BF16, EPI_LNFOLD_BF16, EPI_PATCH_F32, GemmEpilogue)
 
 Tensor = torch.Tensor
 
@@ -51,14 +51,20 @@ def _ptr(t: Optional[Tensor]) -> Optional[int]:
 def gemm(a: Tensor, w: Tensor, out: Tensor, *, mode: int, bias: Optional[Tensor] = None,
          resid: Optional[Tensor] = None, pos: Optional[Tensor] = None, time_embed: Optional[Tensor] = None,
          group: int = 0, group_stride: int = 0, row_offset: int = 0, T: int = 0, aux: Optional[Tensor] = None,
-         aux_out: Optional[Tensor] = None, max_ctas: int = 0) -> Tensor:
-    """out = epilogue(a @ w.T).  a: bf16 [M,K] (row stride free), w: bf16 [N,K], fp32 bias [N]."""
+         aux_out: Optional[Tensor] = None, max_ctas: int = 0, copy_out: Optional[Tensor] = None,
+         stats_out: Optional[Tensor] = None, stats_in: Optional[Tensor] = None, stats_row_step: int = 1,
+         colsum: Optional[Tensor] = None, eps: float = 1e-5) -> Tensor:
+    """out = epilogue(a @ w.T).  a: bf16 [M,K] (row stride free), w: bf16 [N,K], fp32 bias [N].
+
+    LayerNorm fold: mode EPI_BIAS_RESID_STATS_F32 (producer) also writes copy_out = bf16(out) and stats_out
+    [M, gemm_stats_slots(M, N), 2]; mode EPI_LNFOLD_BF16 (consumer) takes that copy as `a`, w = W * ln.weight, bias =
+    b + W @ ln.bias, colsum = w.float().sum(1) and stats_in (row r of `a` <-> stats row r * stats_row_step)."""
     _req(a, torch.bfloat16, "gemm a"); _req(w, torch.bfloat16, "gemm w")
     assert a.dim() == 2 and w.dim() == 2 and a.stride(1) == 1 and w.stride(1) == 1
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K, (a.shape, w.shape)
-    want = torch.bfloat16 if mode in (EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_DGELU_BF16) else torch.float32
+    want = torch.bfloat16 if mode in (EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_DGELU_BF16, EPI_LNFOLD_BF16) else torch.float32
     _req(out, want, "gemm out")
     assert out.dim() == 2 and out.stride(1) == 1 and out.shape[1] >= N
     if bias is not None:
@@ -69,7 +75,7 @@ def gemm(a: Tensor, w: Tensor, out: Tensor, *, mode: int, bias: Optional[Tensor]
     epi.out = out.data_ptr()
     epi.ldo = out.stride(0)
     epi.max_ctas = max_ctas
-    if mode == EPI_BIAS_RESID_F32:
+    if mode in (EPI_BIAS_RESID_F32, EPI_BIAS_RESID_STATS_F32):
         _req(resid, torch.float32, "gemm resid")
         assert resid.dim() == 2 and resid.stride(1) == 1 and resid.shape[0] >= M
         epi.resid = resid.data_ptr(); epi.ldr = resid.stride(0)
@@ -78,6 +84,23 @@ def gemm(a: Tensor, w: Tensor, out: Tensor, *, mode: int, bias: Optional[Tensor]
             _req(aux, torch.bfloat16, "gemm aux")
             assert aux.dim() == 2 and aux.stride(1) == 1 and aux.shape[0] >= M and aux.shape[1] >= N and aux.stride(0) % 4 == 0
             epi.aux = aux.data_ptr(); epi.ld_aux = aux.stride(0)
+        if mode == EPI_BIAS_RESID_STATS_F32:
+            _req(copy_out, torch.bfloat16, "gemm copy_out"); _req(stats_out, torch.float32, "gemm stats_out")
+            ns = gemm_stats_slots(M, N)
+            assert copy_out.dim() == 2 and copy_out.stride(1) == 1 and copy_out.shape[0] >= M and copy_out.shape[1] >= N
+            assert stats_out.is_contiguous() and stats_out.shape == (M, ns, 2), (stats_out.shape, (M, ns, 2))
+            epi.copy_out = copy_out.data_ptr(); epi.ld_copy = copy_out.stride(0)
+            epi.stats_out = stats_out.data_ptr(); epi.n_slots = ns
+    elif mode == EPI_LNFOLD_BF16:
+        _req(stats_in, torch.float32, "gemm stats_in")
+        assert stats_in.is_contiguous() and stats_in.dim() == 3 and stats_in.shape[2] == 2
+        assert stats_in.shape[0] >= (M - 1) * stats_row_step + 1
+        if colsum is not None:       # None: the rows of w are centred (sum_k w[n, k] == 0), the mean term vanishes
+            _req(colsum, torch.float32, "gemm colsum"); assert colsum.is_contiguous() and colsum.numel() == N
+        assert bias is not None and out.shape[0] >= M
+        epi.stats_in = stats_in.data_ptr(); epi.n_slots = stats_in.shape[1]
+        epi.ld_stats = 2 * stats_in.shape[1] * stats_row_step
+        epi.colsum = _ptr(colsum); epi.eps = eps
     elif mode == EPI_PATCH_F32:
         _req(pos, torch.float32, "gemm pos"); _req(time_embed, torch.float32, "gemm time_embed")
         assert pos.is_contiguous() and time_embed.is_contiguous()
@@ -315,6 +338,14 @@ def prompt_rows_f32(global_prompts: Tensor, local_prompts: Tensor, cls_proj_out:
                                               G, B, T, D, eps, _stream())
     _lib.check(rc, "gava_prompt_rows_f32_fwd")
     return out
+
+
+def gemm_stats_slots(M: int, N: int) -> int:
+    """column slices per row of the statistics an EPI_BIAS_RESID_STATS_F32 launch of shape (M, N) writes"""
+    n = int(_lib.load().gava_gemm_stats_slots(M, N))
+    if n <= 0:
+        raise ValueError(f"gemm_stats_slots: unsupported shape M={M} N={N}")
+    return n
 
 
 def gemm3(a_hi: Tensor, a_lo: Tensor, w_hi: Tensor, w_lo: Tensor, out: Tensor, *, bias: Optional[Tensor] = None,

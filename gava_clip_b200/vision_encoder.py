@@ -148,6 +148,9 @@ class TowerEngine:
         # which made that K=768 GEMM HBM-bound), norm2 normalises x + delta, and the fc2 epilogue -- hidden under a K=3072
         # mainloop -- adds delta together with the MLP output.  Same bytes overall, but none of them on a critical path.
         self.defer_resid = os.environ.get("GAVA_DEFER_RESID", "1") != "0"
+        # norm1 of blocks 1..L-1 folded around the (fc2 -> QKV) GEMM pair: fc2's epilogue emits bf16(x) + row statistics,
+        # the QKV GEMM contracts the raw copy with W diag(norm1.weight) and normalises in its epilogue (no norm1 pass)
+        self.fold_norm1 = os.environ.get("GAVA_FOLD_LN1", "1") != "0"
         self.side_stream = torch.cuda.Stream(device) if device.type == "cuda" else None
         self.launches_last_call = 0      # sm_100a kernels launched (or replayed) by the last run()
         self.pack_moves = 0              # times pack() re-allocated (instead of refreshing in place) a packed operand
@@ -247,6 +250,20 @@ class TowerEngine:
                     lambda sa=sa: f32(torch.cat([sa.q_proj.bias, sa.k_proj.bias, sa.v_proj.bias], 0)))
             if e.use_local_prompts:                                  # utils.py:137-139
                 put(k + "local", [blk.local_prompts], lambda blk=blk: f32(blk.local_prompts))
+            if i >= 1 and self.fold_norm1 and self.defer_resid:
+                # LN(x) W^T + b == rstd (x - mean) W'^T + (b + W beta), W' = W diag(gamma).  Centring the rows of W'
+                # (W'' = W' - rowmean(W')) makes W'' orthogonal to the all-ones vector, so (x - mean) W''^T == x W''^T:
+                # the mean drops out inside the contraction and the epilogue is one FMA per element (rstd, bias').
+                ws, bs = [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], [a.q_proj.bias, a.k_proj.bias, a.v_proj.bias]
+                n1 = blk.norm1
+
+                def folded_w(ws=ws, n1=n1):
+                    w = torch.cat(ws, 0).detach().to(dev, torch.float32) * n1.weight.detach().to(dev, torch.float32)[None, :]
+                    return bf(w - w.mean(dim=1, keepdim=True))
+                put(k + "qkv.wf", ws + [n1.weight], folded_w)
+                put(k + "qkv.bf", bs + ws + [n1.bias],
+                    lambda ws=ws, bs=bs, n1=n1: (torch.cat(bs, 0).detach().to(dev, torch.float32)
+                                                 + torch.cat(ws, 0).detach().to(dev, torch.float32) @ n1.bias.detach().to(dev, torch.float32)).contiguous())
         for key in [key for key in P if key.startswith("time_embed@")]:
             del P[key]                                  # resized copies are rebuilt on demand
         if copies:           # fine-tuning refreshes ~100 small tensors per step: a handful of launches instead of one each
@@ -346,6 +363,9 @@ class TowerEngine:
             "kvaux": z(G + 2 * BT, 2 * D, dt=bf),
             "frame_feat": z(BT, self.packed["proj.wT"].shape[0], dt=f32),
         }
+        if self.fold_norm1 and self.defer_resid:
+            W["xb"] = z(M, D, dt=bf)                                         # bf16 copy of the stream after each block
+            W["xstats"] = z(M, ops.gemm_stats_slots(M, D), 2, dt=f32)       # its per-row (sum, sum of squares) partials
         # inputs of the prompt-row kernel that a disabled prompt group does not produce (zeros: their K/V rows are masked
         # out by the attention kernels' key_groups, they only have to be finite)
         if not e.use_local_prompts:
@@ -431,8 +451,10 @@ class TowerEngine:
         main = torch.cuda.current_stream(self.device)
         side = self.side_stream if self.overlap_chain else None
         norm1_done = True       # True when xn already holds norm1(x) of the coming block (block 0: done by the ln_pre pass)
+        fold = self.fold_norm1 and self.defer_resid
         for i in range(L):
             k = f"b{i}."
+            folded_in = fold and i >= 1      # this block's input came with its bf16 copy + row statistics (previous fc2)
             # ---- temporal message: cls_proj -> summary attention -> K/V-only prompt rows   utils.py:160-188
             # Eight small launches that depend only on the cls rows of x; they run on a side stream (a parallel branch of
             # the CUDA graph) next to norm1 + the QKV GEMM of the live rows and join before the attention kernel.
@@ -458,12 +480,17 @@ class TowerEngine:
                     ev_kv = torch.cuda.Event()
                     ev_kv.record(side)
             # ---- x = x + attn(norm1(x)) on the live rows                                     utils.py:190-191
-            if not norm1_done:
+            if not norm1_done and not folded_in:
                 ops.layernorm(x, P[k + "norm1.w"], P[k + "norm1.b"], xn, rows=M, in_row_stride=D)
             norm1_done = False
             if i < L - 1:
-                ops.gemm(xn, P[k + "qkv.w"], qkv, mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"],
-                         max_ctas=self.qkv_ctas if side is not None else 0)
+                if folded_in:
+                    ops.gemm(W["xb"], P[k + "qkv.wf"], qkv, mode=ops.EPI_LNFOLD_BF16, bias=P[k + "qkv.bf"],
+                             stats_in=W["xstats"], eps=LN_EPS,
+                             max_ctas=self.qkv_ctas if side is not None else 0)
+                else:
+                    ops.gemm(xn, P[k + "qkv.w"], qkv, mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"],
+                             max_ctas=self.qkv_ctas if side is not None else 0)
                 if side is not None:
                     main.wait_event(ev_kv)
                 ops.attention(qkv, W["kvaux"], xn, B=B, T=T, N0=N0, G=G, H=H, key_groups=kg)
@@ -473,7 +500,11 @@ class TowerEngine:
                     # ---- x = (x + delta) + fc2(QuickGELU(fc1(norm2(x + delta))))              utils.py:191,199
                     ops.layernorm(x, P[k + "norm2.w"], P[k + "norm2.b"], xn, rows=M, in_row_stride=D, delta=dl)
                     ops.gemm(xn, P[k + "fc1.w"], h, mode=ops.EPI_BIAS_GELU_BF16, bias=P[k + "fc1.b"])
-                    ops.gemm(h, P[k + "fc2.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"], resid=x, aux=dl)
+                    if fold:
+                        ops.gemm(h, P[k + "fc2.w"], x, mode=ops.EPI_BIAS_RESID_STATS_F32, bias=P[k + "fc2.b"], resid=x, aux=dl,
+                                 copy_out=W["xb"], stats_out=W["xstats"])
+                    else:
+                        ops.gemm(h, P[k + "fc2.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"], resid=x, aux=dl)
                 else:
                     ops.gemm(xn, P[k + "out.w"], x, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "out.b"], resid=x)
                     # ---- x = x + fc2(QuickGELU(fc1(norm2(x))))                                    utils.py:199
@@ -486,10 +517,18 @@ class TowerEngine:
                 # out-proj / MLP for one row per frame.  Row-independent ops => bit-for-meaning identical results.
                 xn_cls = xn.view(BT, N0 * D)[:, :D]                      # row f*N0 of a [M, D] buffer, pitch N0*D
                 x_cls_src = x.view(BT, N0 * D)[:, :D]
-                ops.gemm(xn, P[k + "qkv.w"][D:], qkv[:, D:], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:],
-                         max_ctas=self.qkv_ctas if side is not None else 0)
-                ops.gemm(xn_cls, P[k + "qkv.w"][:D], qkv.view(BT, N0 * 3 * D)[:, :D], mode=ops.EPI_BIAS_BF16,
-                         bias=P[k + "qkv.b"][:D])
+                if folded_in:
+                    ops.gemm(W["xb"], P[k + "qkv.wf"][D:], qkv[:, D:], mode=ops.EPI_LNFOLD_BF16, bias=P[k + "qkv.bf"][D:],
+                             stats_in=W["xstats"], eps=LN_EPS,
+                             max_ctas=self.qkv_ctas if side is not None else 0)
+                    ops.gemm(W["xb"].view(BT, N0 * D)[:, :D], P[k + "qkv.wf"][:D], qkv.view(BT, N0 * 3 * D)[:, :D],
+                             mode=ops.EPI_LNFOLD_BF16, bias=P[k + "qkv.bf"][:D], stats_in=W["xstats"], stats_row_step=N0,
+                             eps=LN_EPS)
+                else:
+                    ops.gemm(xn, P[k + "qkv.w"][D:], qkv[:, D:], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:],
+                             max_ctas=self.qkv_ctas if side is not None else 0)
+                    ops.gemm(xn_cls, P[k + "qkv.w"][:D], qkv.view(BT, N0 * 3 * D)[:, :D], mode=ops.EPI_BIAS_BF16,
+                             bias=P[k + "qkv.b"][:D])
                 if side is not None:
                     main.wait_event(ev_kv)
                 ops.attention(qkv, W["kvaux"], xn, B=B, T=T, N0=N0, G=G, H=H, n_q=1, key_groups=kg)

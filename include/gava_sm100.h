@@ -32,9 +32,16 @@ enum gava_epilogue_mode {
   GAVA_EPI_BIAS_F32 = 3,       /* out(f32)  = acc + bias                                  (cls_proj, proj) */
   GAVA_EPI_PATCH_F32 = 4,      /* out(f32)[(r/group)*group_stride + r%group + row_offset]
                                     = acc + bias + pos[1 + r%group] + time_embed[(r/group)%T] (patch embed) */
-  GAVA_EPI_DGELU_BF16 = 5      /* out(bf16) = acc * QuickGELU'(aux[r, c])   (dgrad through mlp.act; aux = fc1 pre-activations) */
+  GAVA_EPI_DGELU_BF16 = 5,     /* out(bf16) = acc * QuickGELU'(aux[r, c])   (dgrad through mlp.act; aux = fc1 pre-activations) */
   /* (mode 6, a LayerNorm tail behind the fc2 GEMM, existed in ABI version 2; it measured 5 % slower end to end than the
      separate LayerNorm launch and was removed in version 3) */
+  /* LayerNorm folded around a GEMM pair (ABI version 4): the PRODUCER of a residual-stream tensor also emits its bf16
+     copy and per-row partial statistics, the CONSUMER contracts that raw copy with W' = W diag(ln.weight) and applies
+     the normalisation after the contraction:  LN(x) W^T + b  ==  rstd (x W'^T - mean colsum(W')) + (b + W ln.bias).
+     Removes the separate norm1 pass over the stream (VitaCLIP_vision_encoder_utils.py:190, `self.norm1(x)`). */
+  GAVA_EPI_LNFOLD_BF16 = 7,           /* out(bf16) = rstd[r] * (acc - mean[r] * colsum[c]) + bias[c]   (consumer; colsum
+                                         NULL = 0 for row-centred W')  */
+  GAVA_EPI_BIAS_RESID_STATS_F32 = 8   /* mode 2, plus copy_out(bf16) = out and stats_out[r, slot] = (sum, sum sq) (producer) */
 };
 
 typedef struct gava_gemm_epilogue {
@@ -53,7 +60,19 @@ typedef struct gava_gemm_epilogue {
   const void* aux;         /* DGELU: bf16 [M, ld_aux] pre-activations; RESID (optional): bf16 [M, ld_aux] second addend */
   int64_t ld_aux;
   void* aux_out;           /* GELU (optional): also store the pre-activations acc + bias as bf16 [M, ld_aux] */
-  int32_t max_ctas;        /* 0 = all SMs; otherwise cap the persistent grid (BIAS_BF16 mode) so a concurrent stream keeps SMs */
+  int32_t max_ctas;        /* 0 = all SMs; otherwise cap the persistent grid (BIAS_BF16 / LNFOLD modes) so a concurrent stream keeps SMs */
+  /* LayerNorm fold, producer (RESID_STATS): */
+  void* copy_out;          /* bf16 [M, ld_copy]: the output again, rounded to bf16 (the consumer GEMM's A operand) */
+  int64_t ld_copy;
+  float* stats_out;        /* f32 [M, n_slots, 2]: (sum, sum of squares) over each column slice of a row;
+                              n_slots must equal gava_gemm_stats_slots(M, N) */
+  /* LayerNorm fold, consumer (LNFOLD): */
+  const float* stats_in;   /* f32 [rows, n_slots, 2] written by the producer, row r of A at stats_in + r * ld_stats */
+  int64_t ld_stats;        /* floats between consecutive A rows (2 * n_slots, times the row step of a strided A view) */
+  const float* colsum;     /* f32 [N]: sum_k W'[n, k] of the bf16 operand actually passed as W; NULL when the rows of W' are
+                              centred (W' = W diag(g) - rowmean): the mean term then vanishes inside the contraction */
+  int32_t n_slots;
+  float eps;               /* LayerNorm epsilon (consumer) */
 } gava_gemm_epilogue;
 
 int gava_version(void);
@@ -75,6 +94,9 @@ int64_t gava_workspace_bytes(int32_t B, int32_t T, int32_t N0, int32_t D, int32_
  * `cls_x @ self.proj` at VitaCLIP_vision_encoder.py:127. */
 int gava_gemm_bf16_fwd(const void* A, int64_t lda, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
                        const gava_gemm_epilogue* epi, void* stream);
+
+/* Column slices per row a GAVA_EPI_BIAS_RESID_STATS_F32 launch of shape (M, N) writes to stats_out (0: unsupported). */
+int32_t gava_gemm_stats_slots(int64_t M, int64_t N);
 
 /* LayerNorm over the last dim (fp32 statistics, eps inside the sqrt), row r read from
  * x + r * in_row_stride (elements, f32), written to out + r * out_row_stride as bf16 (out_bf16 != 0) or f32.

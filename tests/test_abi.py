@@ -26,9 +26,11 @@ def test_header_symbols_exported_and_bound():
 
 def test_epilogue_struct_layout():
     from gava_clip_b200._lib import GemmEpilogue
-    # int32 mode (+4 pad), 2 ptr, i64, ptr, i64, 4 x i32, 2 ptr, ptr, i64, ptr  -> 104 bytes on LP64
-    assert ctypes.sizeof(GemmEpilogue) == 112 and GemmEpilogue.aux.offset == 80 and GemmEpilogue.aux_out.offset == 96
-    assert GemmEpilogue.max_ctas.offset == 104
+    # int32 mode (+4 pad), 2 ptr, i64, ptr, i64, 4 x i32, 2 ptr, ptr, i64, ptr, i32 (+4 pad), then the LayerNorm-fold block:
+    # ptr, i64, 2 ptr, i64, ptr, i32, f32 -> 168 bytes on LP64 (api.cu static_asserts the same offsets on the C side)
+    assert ctypes.sizeof(GemmEpilogue) == 168 and GemmEpilogue.aux.offset == 80 and GemmEpilogue.aux_out.offset == 96
+    assert GemmEpilogue.max_ctas.offset == 104 and GemmEpilogue.copy_out.offset == 112 and GemmEpilogue.stats_in.offset == 136
+    assert GemmEpilogue.colsum.offset == 152 and GemmEpilogue.n_slots.offset == 160 and GemmEpilogue.eps.offset == 164
     assert GemmEpilogue.out.offset == 32 and GemmEpilogue.group.offset == 48 and GemmEpilogue.pos.offset == 64
 
 

@@ -434,3 +434,52 @@ def test_layernorm2_two_stage(cuda):
     ops.layernorm2(x, w1, b1, x, w2, b2, out2, rows=M)          # in place for the f32 output, as the engine uses it
     assert _rel(x, ref1) < 1e-5
     assert _rel(out2.float(), ref2) < 1e-2
+
+
+@pytest.mark.parametrize("M,D,Kp,N2,step", [(300, 128, 256, 384, 1), (4096 + 77, 768, 3072, 2304, 1), (2560, 1024, 512, 1024, 1),
+                                            (197 * 16, 768, 768, 768, 197)])
+def test_gemm_layernorm_fold_pair(cuda, M, D, Kp, N2, step):
+    """LayerNorm folded around a GEMM pair (GAVA_EPI_BIAS_RESID_STATS_F32 -> GAVA_EPI_LNFOLD_BF16): the producer's x, its
+    bf16 copy and row statistics, then  LN(x) W^T + b  from the raw copy -- against an fp32 PyTorch LayerNorm + linear on the
+    same x.  step > 1: the consumer reads every step-th row (the cls rows of the last block)."""
+    from gava_clip_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + D)
+    h = torch.randn(M, Kp, device=cuda, generator=g).bfloat16()
+    w2 = (torch.randn(D, Kp, device=cuda, generator=g) * Kp ** -0.5).bfloat16()
+    b2 = torch.randn(D, device=cuda, generator=g)
+    x = torch.randn(M, D, device=cuda, generator=g) * 2.0 + 0.3
+    x[:, 5] += 20.0                                    # an outlier channel, as in trained ViTs
+    delta = torch.randn(M, D, device=cuda, generator=g).bfloat16()
+    x_ref = x + delta.float() + h.float() @ w2.float().t() + b2
+    ns = ops.gemm_stats_slots(M, D)
+    xb = torch.empty(M, D, device=cuda, dtype=torch.bfloat16)
+    stats = torch.full((M, ns, 2), float("nan"), device=cuda)
+    ops.gemm(h, w2, x, mode=ops.EPI_BIAS_RESID_STATS_F32, bias=b2, resid=x, aux=delta, copy_out=xb, stats_out=stats)
+    assert _rel(x, x_ref) < 2e-5
+    assert torch.equal(xb, x.bfloat16())
+    assert _rel(stats[:, :, 0].sum(1), x.sum(1)) < 1e-5 and _rel(stats[:, :, 1].sum(1), (x * x).sum(1)) < 1e-5
+    # consumer
+    gamma = torch.rand(D, device=cuda, generator=g) + 0.5
+    beta = torch.randn(D, device=cuda, generator=g) * 0.2
+    w = torch.randn(N2, D, device=cuda, generator=g) * D ** -0.5
+    b = torch.randn(N2, device=cuda, generator=g)
+    wf = (w * gamma[None, :]).bfloat16()
+    colsum = wf.float().sum(1).contiguous()
+    bf = (b + w @ beta).contiguous()
+    rows = torch.arange(0, M, step, device=cuda)
+    a = xb.view(M // step, step * D)[:, :D] if step > 1 else xb
+    out = torch.empty(rows.numel(), N2, device=cuda, dtype=torch.bfloat16)
+    ops.gemm(a, wf, out, mode=ops.EPI_LNFOLD_BF16, bias=bf, colsum=colsum, stats_in=stats, stats_row_step=step, eps=1e-5)
+    ref = F.layer_norm(x[rows], (D,), gamma, beta, 1e-5) @ w.t() + b
+    # the un-folded kernel path for comparison: bf16(LN(x)) @ bf16(w)^T
+    plain = F.layer_norm(x[rows], (D,), gamma, beta, 1e-5).bfloat16().float() @ w.bfloat16().float().t() + b
+    e_fold, e_plain = _rel(out.float(), ref), _rel(plain.bfloat16().float(), ref)
+    # the engine's variant: row-centred weights, no colsum (the mean of x drops out inside the contraction)
+    wc = w * gamma[None, :]
+    wc = (wc - wc.mean(dim=1, keepdim=True)).bfloat16()
+    out_c = torch.empty_like(out)
+    ops.gemm(a, wc, out_c, mode=ops.EPI_LNFOLD_BF16, bias=bf, stats_in=stats, stats_row_step=step, eps=1e-5)
+    e_cent = _rel(out_c.float(), ref)
+    print(f"\n[fold {M}x{D}->{N2}, slots {ns}] folded rel err {e_fold:.2e}, row-centred weights {e_cent:.2e}; "
+          f"un-folded bf16 path {e_plain:.2e}")
+    assert e_fold < 1e-2 and e_cent < 1e-2
