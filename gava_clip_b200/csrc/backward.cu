@@ -494,6 +494,9 @@ static int launch_seq_attention_bwd(const void* qkv, const void* dout, void* dqk
 }
 
 int temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int B, int T, int H, cudaStream_t stream) {
+  static const bool use_mma = [] { const char* e = getenv("GAVA_TEXT_ATTN_MMA"); return !(e && e[0] == '0'); }();
+  if (use_mma && qkv && dout && dqkv && B > 0 && H > 0 && T > 16 && causal_attention_mma_supported(T, H))
+    return temporal_attention_bwd_mma(qkv, dout, dqkv, B, T, H, stream);
   return launch_seq_attention_bwd<false, false>(qkv, dout, dqkv, B, T, H, stream, "temporal_attention_bwd");
 }
 

@@ -88,6 +88,9 @@ int causal_attention_f32(const float* qkv, float* out, int n_seq, int L, int H, 
 bool causal_attention_mma_supported(int L, int H);
 int causal_attention_mma(const float* qkv, float* out, int n_seq, int L, int H, cudaStream_t stream);
 int causal_attention_bwd_mma(const float* qkv, const void* dout, void* dqkv, int n_seq, int L, int H, cudaStream_t stream);
+// the same kernels without a mask on bf16 q|k|v: the summary-token attention for clips of more than 16 frames
+int temporal_attention_mma(const void* qkv, void* out, int B, int T, int H, cudaStream_t stream);
+int temporal_attention_bwd_mma(const void* qkv, const void* dout, void* dqkv, int B, int T, int H, cudaStream_t stream);
 int prompt_rows_f32(const float* global_prompts, const float* local_prompts, const float* cls_proj_out,
                     const float* summary, const float* ln_w, const float* ln_b, float* out, int G, int B, int T, int D,
                     float eps, cudaStream_t stream);

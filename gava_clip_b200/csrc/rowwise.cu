@@ -397,6 +397,10 @@ __global__ void __launch_bounds__(128) temporal_attention_kernel(const __nv_bflo
 int temporal_attention(const void* qkv, void* out, int B, int T, int H, cudaStream_t stream) {
   if (!qkv || !out || B <= 0 || T <= 0 || H <= 0) { set_error("temporal_attention: bad arguments"); return GAVA_ERR_ARG; }
   if (T > TA_MAX_T) { set_error("temporal_attention: T=%d > %d unsupported", T, TA_MAX_T); return GAVA_ERR_SHAPE; }
+  // more than one 16-row tile of frames (the 70-frame recipe): tensor-core form (seq_attention_mma.cu); a handful of
+  // frames stays on this scalar kernel (one partially filled MMA tile would not be faster)
+  static const bool use_mma = [] { const char* e = getenv("GAVA_TEXT_ATTN_MMA"); return !(e && e[0] == '0'); }();
+  if (use_mma && T > 16) return temporal_attention_mma(qkv, out, B, T, H, stream);
   temporal_attention_kernel<<<dim3(H, B), 128, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(qkv),
                                                             reinterpret_cast<__nv_bfloat16*>(out), T, H);
   return check_launch("temporal_attention");

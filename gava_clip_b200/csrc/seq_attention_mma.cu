@@ -1,5 +1,8 @@
-// Causal multi-head self-attention of the CLIP text transformer (77 tokens, head_dim 64) on the tensor cores, forward and
-// backward -- nn.MultiheadAttention's core with the causal mask, training/VitaCLIP_text_encoder.py:83-88,146-152.
+// Short-sequence multi-head self-attention (<= 128 tokens, head_dim 64) on the tensor cores, forward and backward:
+//   * the causal attention of the CLIP text transformer (77 tokens) -- nn.MultiheadAttention's core with the causal mask,
+//     training/VitaCLIP_text_encoder.py:83-88,146-152 (f32 activations);
+//   * the summary-token attention over the T frames of a clip, training/VitaCLIP_vision_encoder_utils.py:168-170, for
+//     clips longer than one 16-row tile (the shipped 70-frame recipe; bf16 activations, no mask).
 //
 // One CTA per (sequence, head); the sequence's q, k, v rows (f32 in HBM: the text side keeps fp32 activations) are staged
 // once in swizzled shared memory as bf16 and every contraction is mma.sync m16n8k16 (bf16 operands, f32 accumulate).
@@ -38,15 +41,24 @@ __device__ __forceinline__ void split8_bf16(const float4& a, const float4& b, ui
   lo = pack8_bf16(ra, rb);
 }
 
-// ============================================================================================== forward (fp32-accurate)
+// key `kc` takes part in the softmax of query row `r`: the causal mask, or (self-attention over the whole sequence) only
+// the padding keys beyond T are excluded
+template <bool CAUSAL>
+__device__ __forceinline__ bool key_on(int kc, int r, int T) { return CAUSAL ? kc <= r : kc < T; }
+
+// ============================================================================================== forward
+// PRECISE: f32 in / out, 3-term split-bf16 products (text transformer); otherwise bf16 in / out, plain bf16 products (the
+// tower's summary-token attention over the T frames of a clip, utils.py:168-170, for clips longer than one 16-row tile).
+template <bool PRECISE, bool CAUSAL>
 __global__ void __launch_bounds__(SAM_THREADS, 1)
-causal_attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T, int H, int t_pad) {
+seq_attention_mma_kernel(const void* __restrict__ qkv_, void* __restrict__ out_, int T, int H, int t_pad) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int h = blockIdx.x, b = blockIdx.y;
   const int D = H * 64;
   const uint32_t plane = (uint32_t)t_pad * 128u;
-  const uint32_t sQh = smem_u32(smem), sQl = sQh + plane, sKh = sQl + plane, sKl = sKh + plane, sVh = sKl + plane,
-                 sVl = sVh + plane;
+  constexpr uint32_t PS = PRECISE ? 2u : 1u;       // planes per operand: hi (+ lo)
+  const uint32_t sQh = smem_u32(smem), sQl = sQh + plane, sKh = sQh + PS * plane, sKl = sKh + plane,
+                 sVh = sQh + 2u * PS * plane, sVl = sVh + plane;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tg = lane & 3, mi = lane >> 3;
   const long long ld = 3LL * D;
@@ -56,55 +68,65 @@ causal_attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ o
     const int row = j >> 3, ch = j & 7;
     uint4 hi = make_uint4(0, 0, 0, 0), lo = hi;
     if (row < T) {
-      const float* src = qkv + ((long long)b * T + row) * ld + which * D + h * 64 + ch * 8;
-      split8_bf16(*reinterpret_cast<const float4*>(src), *reinterpret_cast<const float4*>(src + 4), hi, lo);
+      const long long e = ((long long)b * T + row) * ld + which * D + h * 64 + ch * 8;
+      if constexpr (PRECISE) {
+        const float* src = reinterpret_cast<const float*>(qkv_) + e;
+        split8_bf16(*reinterpret_cast<const float4*>(src), *reinterpret_cast<const float4*>(src + 4), hi, lo);
+      } else {
+        hi = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(qkv_) + e);
+      }
     }
-    const uint32_t off = kv_off(row, ch) + (uint32_t)(2 * which) * plane;
+    const uint32_t off = kv_off(row, ch) + (uint32_t)which * PS * plane;
     *reinterpret_cast<uint4*>(smem + off) = hi;
-    *reinterpret_cast<uint4*>(smem + off + plane) = lo;
+    if constexpr (PRECISE) *reinterpret_cast<uint4*>(smem + off + plane) = lo;
   }
   __syncthreads();
 
   const float scale_log2 = 0.125f * 1.4426950408889634f;
   const int n_t = t_pad >> 4;
   for (int mt = n_t - 1 - warp; mt >= 0; mt -= SAM_WARPS) {      // longest rows first
-    uint32_t qh[4][4], ql[4][4];
+    uint32_t qh[4][4], ql[PRECISE ? 4 : 1][4];
     {
       const int row = mt * 16 + (lane & 15);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         ldmatrix_x4(sQh + kv_off(row, 2 * ks + (lane >> 4)), qh[ks][0], qh[ks][1], qh[ks][2], qh[ks][3]);
-        ldmatrix_x4(sQl + kv_off(row, 2 * ks + (lane >> 4)), ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3]);
+        if constexpr (PRECISE) ldmatrix_x4(sQl + kv_off(row, 2 * ks + (lane >> 4)), ql[ks][0], ql[ks][1], ql[ks][2], ql[ks][3]);
       }
     }
     const int r0 = mt * 16 + g, r1 = r0 + 8;
+    const int kt_end = CAUSAL ? mt : n_t - 1;        // last key tile this query tile attends to
     float s[SAM_MAX_TILES][2][4];
     float m0 = -1e30f, m1 = -1e30f;
 #pragma unroll
     for (int kt = 0; kt < SAM_MAX_TILES; ++kt) {
-      if (kt <= mt) {
+      if (kt <= kt_end) {
 #pragma unroll
         for (int n = 0; n < 2; ++n) { s[kt][n][0] = s[kt][n][1] = s[kt][n][2] = s[kt][n][3] = 0.f; }
         const int key = kt * 16 + (mi >> 1) * 8 + (lane & 7);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           uint32_t b0, b1, b2, b3;
-          ldmatrix_x4(sKl + kv_off(key, 2 * ks + (mi & 1)), b0, b1, b2, b3);      // small terms first
-          mma_bf16_16816(s[kt][0], qh[ks], b0, b1);
-          mma_bf16_16816(s[kt][1], qh[ks], b2, b3);
+          if constexpr (PRECISE) {
+            ldmatrix_x4(sKl + kv_off(key, 2 * ks + (mi & 1)), b0, b1, b2, b3);      // small terms first
+            mma_bf16_16816(s[kt][0], qh[ks], b0, b1);
+            mma_bf16_16816(s[kt][1], qh[ks], b2, b3);
+          }
           ldmatrix_x4(sKh + kv_off(key, 2 * ks + (mi & 1)), b0, b1, b2, b3);
-          mma_bf16_16816(s[kt][0], ql[ks], b0, b1);
-          mma_bf16_16816(s[kt][1], ql[ks], b2, b3);
+          if constexpr (PRECISE) {
+            mma_bf16_16816(s[kt][0], ql[ks], b0, b1);
+            mma_bf16_16816(s[kt][1], ql[ks], b2, b3);
+          }
           mma_bf16_16816(s[kt][0], qh[ks], b0, b1);
           mma_bf16_16816(s[kt][1], qh[ks], b2, b3);
         }
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
           const int kc = kt * 16 + 8 * n + 2 * tg;
-          s[kt][n][0] = (kc <= r0) ? s[kt][n][0] * scale_log2 : -1e30f;
-          s[kt][n][1] = (kc + 1 <= r0) ? s[kt][n][1] * scale_log2 : -1e30f;
-          s[kt][n][2] = (kc <= r1) ? s[kt][n][2] * scale_log2 : -1e30f;
-          s[kt][n][3] = (kc + 1 <= r1) ? s[kt][n][3] * scale_log2 : -1e30f;
+          s[kt][n][0] = key_on<CAUSAL>(kc, r0, T) ? s[kt][n][0] * scale_log2 : -1e30f;
+          s[kt][n][1] = key_on<CAUSAL>(kc + 1, r0, T) ? s[kt][n][1] * scale_log2 : -1e30f;
+          s[kt][n][2] = key_on<CAUSAL>(kc, r1, T) ? s[kt][n][2] * scale_log2 : -1e30f;
+          s[kt][n][3] = key_on<CAUSAL>(kc + 1, r1, T) ? s[kt][n][3] * scale_log2 : -1e30f;
           m0 = fmaxf(m0, fmaxf(s[kt][n][0], s[kt][n][1]));
           m1 = fmaxf(m1, fmaxf(s[kt][n][2], s[kt][n][3]));
         }
@@ -118,7 +140,7 @@ causal_attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ o
     for (int n = 0; n < 8; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f; }
 #pragma unroll
     for (int kt = 0; kt < SAM_MAX_TILES; ++kt) {
-      if (kt <= mt) {
+      if (kt <= kt_end) {
         uint32_t ph[4], pl[4];
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
@@ -127,19 +149,25 @@ causal_attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ o
           l0 += p0 + p1; l1 += p2 + p3;
           ph[2 * n] = pack_bf16x2(p0, p1);
           ph[2 * n + 1] = pack_bf16x2(p2, p3);
-          pl[2 * n] = pack_bf16x2(p0 - bf16_round(p0), p1 - bf16_round(p1));
-          pl[2 * n + 1] = pack_bf16x2(p2 - bf16_round(p2), p3 - bf16_round(p3));
+          if constexpr (PRECISE) {
+            pl[2 * n] = pack_bf16x2(p0 - bf16_round(p0), p1 - bf16_round(p1));
+            pl[2 * n + 1] = pack_bf16x2(p2 - bf16_round(p2), p3 - bf16_round(p3));
+          }
         }
         const int krow = kt * 16 + (mi & 1) * 8 + (lane & 7);
 #pragma unroll
         for (int nd2 = 0; nd2 < 4; ++nd2) {
           uint32_t b0, b1, b2, b3;
-          ldmatrix_x4_trans(sVl + kv_off(krow, 2 * nd2 + (mi >> 1)), b0, b1, b2, b3);
-          mma_bf16_16816(o[2 * nd2], ph, b0, b1);
-          mma_bf16_16816(o[2 * nd2 + 1], ph, b2, b3);
+          if constexpr (PRECISE) {
+            ldmatrix_x4_trans(sVl + kv_off(krow, 2 * nd2 + (mi >> 1)), b0, b1, b2, b3);
+            mma_bf16_16816(o[2 * nd2], ph, b0, b1);
+            mma_bf16_16816(o[2 * nd2 + 1], ph, b2, b3);
+          }
           ldmatrix_x4_trans(sVh + kv_off(krow, 2 * nd2 + (mi >> 1)), b0, b1, b2, b3);
-          mma_bf16_16816(o[2 * nd2], pl, b0, b1);
-          mma_bf16_16816(o[2 * nd2 + 1], pl, b2, b3);
+          if constexpr (PRECISE) {
+            mma_bf16_16816(o[2 * nd2], pl, b0, b1);
+            mma_bf16_16816(o[2 * nd2 + 1], pl, b2, b3);
+          }
           mma_bf16_16816(o[2 * nd2], ph, b0, b1);
           mma_bf16_16816(o[2 * nd2 + 1], ph, b2, b3);
         }
@@ -148,20 +176,27 @@ causal_attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ o
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-    float* o0 = out + ((long long)b * T + r0) * D + h * 64 + 2 * tg;
-    float* o1 = o0 + 8LL * D;
+    const long long e0 = ((long long)b * T + r0) * D + h * 64 + 2 * tg, e1 = e0 + 8LL * D;
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      if (r0 < T) *reinterpret_cast<float2*>(o0 + 8 * n) = make_float2(o[n][0] * i0, o[n][1] * i0);
-      if (r1 < T) *reinterpret_cast<float2*>(o1 + 8 * n) = make_float2(o[n][2] * i1, o[n][3] * i1);
+      if constexpr (PRECISE) {
+        float* out = reinterpret_cast<float*>(out_);
+        if (r0 < T) *reinterpret_cast<float2*>(out + e0 + 8 * n) = make_float2(o[n][0] * i0, o[n][1] * i0);
+        if (r1 < T) *reinterpret_cast<float2*>(out + e1 + 8 * n) = make_float2(o[n][2] * i1, o[n][3] * i1);
+      } else {
+        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_);
+        if (r0 < T) *reinterpret_cast<uint32_t*>(out + e0 + 8 * n) = pack_bf16x2(o[n][0] * i0, o[n][1] * i0);
+        if (r1 < T) *reinterpret_cast<uint32_t*>(out + e1 + 8 * n) = pack_bf16x2(o[n][2] * i1, o[n][3] * i1);
+      }
     }
   }
 }
 
 // ============================================================================================== backward
+template <bool IN_F32, bool CAUSAL>
 __global__ void __launch_bounds__(SAM_THREADS, 1)
-causal_attention_bwd_mma_kernel(const float* __restrict__ qkv, const __nv_bfloat16* __restrict__ dout,
-                                __nv_bfloat16* __restrict__ dqkv, int T, int H, int t_pad) {
+seq_attention_bwd_mma_kernel(const void* __restrict__ qkv_, const __nv_bfloat16* __restrict__ dout,
+                             __nv_bfloat16* __restrict__ dqkv, int T, int H, int t_pad) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int h = blockIdx.x, b = blockIdx.y;
   const int D = H * 64;
@@ -179,8 +214,13 @@ causal_attention_bwd_mma_kernel(const float* __restrict__ qkv, const __nv_bfloat
     uint4 v = make_uint4(0, 0, 0, 0);
     if (row < T) {
       if (which < 3) {
-        const float* src = qkv + ((long long)b * T + row) * ld + which * D + h * 64 + ch * 8;
-        v = pack8_bf16(*reinterpret_cast<const float4*>(src), *reinterpret_cast<const float4*>(src + 4));
+        const long long e = ((long long)b * T + row) * ld + which * D + h * 64 + ch * 8;
+        if constexpr (IN_F32) {
+          const float* src = reinterpret_cast<const float*>(qkv_) + e;
+          v = pack8_bf16(*reinterpret_cast<const float4*>(src), *reinterpret_cast<const float4*>(src + 4));
+        } else {
+          v = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(qkv_) + e);
+        }
       } else {
         v = *reinterpret_cast<const uint4*>(dout + ((long long)b * T + row) * D + h * 64 + ch * 8);
       }
@@ -205,11 +245,12 @@ causal_attention_bwd_mma_kernel(const float* __restrict__ qkv, const __nv_bfloat
       }
     }
     const int r0 = mt * 16 + g, r1 = r0 + 8;
+    const int kt_end = CAUSAL ? mt : n_t - 1;
     float s[SAM_MAX_TILES][2][4];
     float m0 = -1e30f, m1 = -1e30f;
 #pragma unroll
     for (int kt = 0; kt < SAM_MAX_TILES; ++kt) {
-      if (kt <= mt) {
+      if (kt <= kt_end) {
 #pragma unroll
         for (int n = 0; n < 2; ++n) { s[kt][n][0] = s[kt][n][1] = s[kt][n][2] = s[kt][n][3] = 0.f; }
         const int key = kt * 16 + (mi >> 1) * 8 + (lane & 7);
@@ -223,10 +264,10 @@ causal_attention_bwd_mma_kernel(const float* __restrict__ qkv, const __nv_bfloat
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
           const int kc = kt * 16 + 8 * n + 2 * tg;
-          s[kt][n][0] = (kc <= r0) ? s[kt][n][0] * scale_log2 : -1e30f;
-          s[kt][n][1] = (kc + 1 <= r0) ? s[kt][n][1] * scale_log2 : -1e30f;
-          s[kt][n][2] = (kc <= r1) ? s[kt][n][2] * scale_log2 : -1e30f;
-          s[kt][n][3] = (kc + 1 <= r1) ? s[kt][n][3] * scale_log2 : -1e30f;
+          s[kt][n][0] = key_on<CAUSAL>(kc, r0, T) ? s[kt][n][0] * scale_log2 : -1e30f;
+          s[kt][n][1] = key_on<CAUSAL>(kc + 1, r0, T) ? s[kt][n][1] * scale_log2 : -1e30f;
+          s[kt][n][2] = key_on<CAUSAL>(kc, r1, T) ? s[kt][n][2] * scale_log2 : -1e30f;
+          s[kt][n][3] = key_on<CAUSAL>(kc + 1, r1, T) ? s[kt][n][3] * scale_log2 : -1e30f;
           m0 = fmaxf(m0, fmaxf(s[kt][n][0], s[kt][n][1]));
           m1 = fmaxf(m1, fmaxf(s[kt][n][2], s[kt][n][3]));
         }
@@ -237,7 +278,7 @@ causal_attention_bwd_mma_kernel(const float* __restrict__ qkv, const __nv_bfloat
     float l0 = 0.f, l1 = 0.f, d0 = 0.f, d1 = 0.f;
 #pragma unroll
     for (int kt = 0; kt < SAM_MAX_TILES; ++kt) {
-      if (kt <= mt) {
+      if (kt <= kt_end) {
         float dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         const int key = kt * 16 + (mi >> 1) * 8 + (lane & 7);
 #pragma unroll
@@ -269,8 +310,8 @@ causal_attention_bwd_mma_kernel(const float* __restrict__ qkv, const __nv_bfloat
   }
   __syncthreads();
 
-  // ---- work units, costliest first: even u = key tile u/2 (dK, dV over query tiles >= it), odd u = query tile
-  // n_t-1-u/2 (dQ over key tiles <= it)
+  // ---- work units, costliest first: even u = key tile u/2 (dK, dV over the query tiles that see it), odd u = query tile
+  // n_t-1-u/2 (dQ over the key tiles it sees)
   for (int u = warp; u < 2 * n_t; u += SAM_WARPS) {
     if (u & 1) {
       const int mt = n_t - 1 - (u >> 1);
@@ -289,7 +330,8 @@ causal_attention_bwd_mma_kernel(const float* __restrict__ qkv, const __nv_bfloat
       float dq[8][4];
 #pragma unroll
       for (int n = 0; n < 8; ++n) { dq[n][0] = dq[n][1] = dq[n][2] = dq[n][3] = 0.f; }
-      for (int kt = 0; kt <= mt; ++kt) {
+      const int kt_end = CAUSAL ? mt : n_t - 1;
+      for (int kt = 0; kt <= kt_end; ++kt) {
         float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         float dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         const int key = kt * 16 + (mi >> 1) * 8 + (lane & 7);
@@ -309,10 +351,10 @@ causal_attention_bwd_mma_kernel(const float* __restrict__ qkv, const __nv_bfloat
 #pragma unroll
           for (int n = 0; n < 2; ++n) {
             const int kc = kt * 16 + 8 * n + 2 * tg;
-            ds[n][0] = (kc <= r0) ? exp2f(s[n][0] * scale_log2 - lse0) * (dp[n][0] - dl0) : 0.f;
-            ds[n][1] = (kc + 1 <= r0) ? exp2f(s[n][1] * scale_log2 - lse0) * (dp[n][1] - dl0) : 0.f;
-            ds[n][2] = (kc <= r1) ? exp2f(s[n][2] * scale_log2 - lse1) * (dp[n][2] - dl1) : 0.f;
-            ds[n][3] = (kc + 1 <= r1) ? exp2f(s[n][3] * scale_log2 - lse1) * (dp[n][3] - dl1) : 0.f;
+            ds[n][0] = key_on<CAUSAL>(kc, r0, T) ? exp2f(s[n][0] * scale_log2 - lse0) * (dp[n][0] - dl0) : 0.f;
+            ds[n][1] = key_on<CAUSAL>(kc + 1, r0, T) ? exp2f(s[n][1] * scale_log2 - lse0) * (dp[n][1] - dl0) : 0.f;
+            ds[n][2] = key_on<CAUSAL>(kc, r1, T) ? exp2f(s[n][2] * scale_log2 - lse1) * (dp[n][2] - dl1) : 0.f;
+            ds[n][3] = key_on<CAUSAL>(kc + 1, r1, T) ? exp2f(s[n][3] * scale_log2 - lse1) * (dp[n][3] - dl1) : 0.f;
           }
           a[0] = pack_bf16x2(ds[0][0], ds[0][1]);
           a[1] = pack_bf16x2(ds[0][2], ds[0][3]);
@@ -350,7 +392,7 @@ causal_attention_bwd_mma_kernel(const float* __restrict__ qkv, const __nv_bfloat
       float dk[8][4], dv[8][4];
 #pragma unroll
       for (int n = 0; n < 8; ++n) { dk[n][0] = dk[n][1] = dk[n][2] = dk[n][3] = 0.f; dv[n][0] = dv[n][1] = dv[n][2] = dv[n][3] = 0.f; }
-      for (int qt = kt; qt < n_t; ++qt) {
+      for (int qt = CAUSAL ? kt : 0; qt < n_t; ++qt) {
         float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         float dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
         const int qrow = qt * 16 + (mi >> 1) * 8 + (lane & 7);
@@ -372,10 +414,10 @@ causal_attention_bwd_mma_kernel(const float* __restrict__ qkv, const __nv_bfloat
             const int qc = qt * 16 + 8 * n + 2 * tg;
             const float2 ls = *reinterpret_cast<const float2*>(&s_lse[qc]);
             const float2 dl = *reinterpret_cast<const float2*>(&s_delta[qc]);
-            pt[n][0] = (kr0 <= qc) ? exp2f(s[n][0] * scale_log2 - ls.x) : 0.f;
-            pt[n][1] = (kr0 <= qc + 1) ? exp2f(s[n][1] * scale_log2 - ls.y) : 0.f;
-            pt[n][2] = (kr1 <= qc) ? exp2f(s[n][2] * scale_log2 - ls.x) : 0.f;
-            pt[n][3] = (kr1 <= qc + 1) ? exp2f(s[n][3] * scale_log2 - ls.y) : 0.f;
+            pt[n][0] = key_on<CAUSAL>(kr0, qc, T) ? exp2f(s[n][0] * scale_log2 - ls.x) : 0.f;
+            pt[n][1] = key_on<CAUSAL>(kr0, qc + 1, T) ? exp2f(s[n][1] * scale_log2 - ls.y) : 0.f;
+            pt[n][2] = key_on<CAUSAL>(kr1, qc, T) ? exp2f(s[n][2] * scale_log2 - ls.x) : 0.f;
+            pt[n][3] = key_on<CAUSAL>(kr1, qc + 1, T) ? exp2f(s[n][3] * scale_log2 - ls.y) : 0.f;
             ds[n][0] = pt[n][0] * (dp[n][0] - dl.x); ds[n][1] = pt[n][1] * (dp[n][1] - dl.y);
             ds[n][2] = pt[n][2] * (dp[n][2] - dl.x); ds[n][3] = pt[n][3] * (dp[n][3] - dl.y);
           }
@@ -428,33 +470,51 @@ static int opt_in_smem(K kern, size_t bytes, size_t* granted_dev, const char* wh
 
 bool causal_attention_mma_supported(int L, int H) { return L > 0 && L <= SAM_MAX_T && H > 0; }
 
-int causal_attention_mma(const float* qkv, float* out, int n_seq, int L, int H, cudaStream_t stream) {
+template <bool PRECISE, bool CAUSAL>
+static int launch_seq_fwd(const void* qkv, void* out, int n_seq, int L, int H, cudaStream_t stream, const char* what) {
   if (!qkv || !out || n_seq <= 0 || !causal_attention_mma_supported(L, H)) {
-    set_error("causal_attention_mma: bad arguments (n_seq=%d L=%d H=%d; L <= %d)", n_seq, L, H, SAM_MAX_T);
+    set_error("%s: bad arguments (n_seq=%d L=%d H=%d; L <= %d)", what, n_seq, L, H, SAM_MAX_T);
     return GAVA_ERR_ARG;
   }
   const int t_pad = (L + 15) / 16 * 16;
-  const size_t smem = (size_t)6 * t_pad * 128;
+  const size_t smem = (size_t)(PRECISE ? 6 : 3) * t_pad * 128;
   static size_t granted[64] = {0};
-  int rc = opt_in_smem(causal_attention_mma_kernel, smem, granted, "causal_attention_mma");
+  int rc = opt_in_smem(seq_attention_mma_kernel<PRECISE, CAUSAL>, smem, granted, what);
   if (rc) return rc;
-  causal_attention_mma_kernel<<<dim3(H, n_seq), SAM_THREADS, smem, stream>>>(qkv, out, L, H, t_pad);
-  return check_launch("causal_attention_mma");
+  seq_attention_mma_kernel<PRECISE, CAUSAL><<<dim3(H, n_seq), SAM_THREADS, smem, stream>>>(qkv, out, L, H, t_pad);
+  return check_launch(what);
 }
 
-int causal_attention_bwd_mma(const float* qkv, const void* dout, void* dqkv, int n_seq, int L, int H, cudaStream_t stream) {
+template <bool IN_F32, bool CAUSAL>
+static int launch_seq_bwd(const void* qkv, const void* dout, void* dqkv, int n_seq, int L, int H, cudaStream_t stream,
+                          const char* what) {
   if (!qkv || !dout || !dqkv || n_seq <= 0 || !causal_attention_mma_supported(L, H)) {
-    set_error("causal_attention_bwd_mma: bad arguments (n_seq=%d L=%d H=%d; L <= %d)", n_seq, L, H, SAM_MAX_T);
+    set_error("%s: bad arguments (n_seq=%d L=%d H=%d; L <= %d)", what, n_seq, L, H, SAM_MAX_T);
     return GAVA_ERR_ARG;
   }
   const int t_pad = (L + 15) / 16 * 16;
   const size_t smem = (size_t)4 * t_pad * 128 + (size_t)2 * t_pad * sizeof(float);
   static size_t granted[64] = {0};
-  int rc = opt_in_smem(causal_attention_bwd_mma_kernel, smem, granted, "causal_attention_bwd_mma");
+  int rc = opt_in_smem(seq_attention_bwd_mma_kernel<IN_F32, CAUSAL>, smem, granted, what);
   if (rc) return rc;
-  causal_attention_bwd_mma_kernel<<<dim3(H, n_seq), SAM_THREADS, smem, stream>>>(
+  seq_attention_bwd_mma_kernel<IN_F32, CAUSAL><<<dim3(H, n_seq), SAM_THREADS, smem, stream>>>(
       qkv, reinterpret_cast<const __nv_bfloat16*>(dout), reinterpret_cast<__nv_bfloat16*>(dqkv), L, H, t_pad);
-  return check_launch("causal_attention_bwd_mma");
+  return check_launch(what);
+}
+
+// text transformer: f32 q|k|v, causal
+int causal_attention_mma(const float* qkv, float* out, int n_seq, int L, int H, cudaStream_t stream) {
+  return launch_seq_fwd<true, true>(qkv, out, n_seq, L, H, stream, "causal_attention_mma");
+}
+int causal_attention_bwd_mma(const float* qkv, const void* dout, void* dqkv, int n_seq, int L, int H, cudaStream_t stream) {
+  return launch_seq_bwd<true, true>(qkv, dout, dqkv, n_seq, L, H, stream, "causal_attention_bwd_mma");
+}
+// summary-token attention over the T frames of each clip: bf16 q|k|v, every frame sees every frame
+int temporal_attention_mma(const void* qkv, void* out, int B, int T, int H, cudaStream_t stream) {
+  return launch_seq_fwd<false, false>(qkv, out, B, T, H, stream, "temporal_attention_mma");
+}
+int temporal_attention_bwd_mma(const void* qkv, const void* dout, void* dqkv, int B, int T, int H, cudaStream_t stream) {
+  return launch_seq_bwd<false, false>(qkv, dout, dqkv, B, T, H, stream, "temporal_attention_bwd_mma");
 }
 
 }  // namespace gava

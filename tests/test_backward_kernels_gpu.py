@@ -126,7 +126,7 @@ def test_attention_bwd(cuda, B, T, N0, G, H):
     check(dq4, da4)
 
 
-@pytest.mark.parametrize("B,T,H", [(3, 8, 12), (2, 70, 2), (1, 3, 2)])
+@pytest.mark.parametrize("B,T,H", [(3, 8, 12), (2, 70, 2), (1, 3, 2), (2, 17, 3), (1, 128, 2)])
 def test_temporal_attention_bwd(cuda, B, T, H):
     from gava_clip_b200 import ops
     g = _gen(B + T + H)

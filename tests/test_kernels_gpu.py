@@ -156,7 +156,7 @@ def test_cls_rows(cuda):
     assert (x.view(BT, N0, D)[:, 1:] == 0).all()
 
 
-@pytest.mark.parametrize("T", [8, 16, 70])
+@pytest.mark.parametrize("T", [8, 16, 17, 70, 128])      # > 16 frames: the mma.sync kernel (seq_attention_mma.cu)
 def test_temporal_attention(cuda, T):
     from gava_clip_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(T)
