@@ -38,18 +38,20 @@ struct AttnBwdArgs {
   int n_q;   // query rows per frame that carry a gradient (N0, or 1 in the last layer: only the cls row reaches the output)
 };
 
+// Launch shapes: <4 warps, 2 CTAs per SM> (255 registers per thread, K/V A-fragments of a key-tile unit live in
+// registers) while two CTAs' shared memory fits an SM; items with more keys (the 70-frame recipe: 276 keys, ViT-L/14 at
+// 16 frames: 282) only fit once per SM and run <8 warps, 1 CTA> with the same register budget.  <8 warps, 2 CTAs> (<= 128
+// registers, key-tile units re-read their K/V fragments every trip) measured slower (1.08 vs 0.96 ms at config 2) and is
+// kept for experiments only (GAVA_AB_WARPS=8).
 #ifndef GAVA_AB_WARPS
 #define GAVA_AB_WARPS 4
 #endif
-constexpr int AB_WARPS = GAVA_AB_WARPS;     // 4: 255 registers/thread, K/V A-fragments live in registers; 8: <= 128 registers
-constexpr bool AB_RELOAD_KV = AB_WARPS > 4; //    (2 CTAs x 8 warps per SM), key-tile units re-read their K/V fragments per trip
-#ifndef GAVA_AB_UNROLL
-#define GAVA_AB_UNROLL (GAVA_AB_WARPS > 4 ? 1 : 2)
-#endif
-constexpr int AB_UNROLL = GAVA_AB_UNROLL;   // key / query tiles per loop trip: independent MMA chains to overlap
 
-template <bool HAVE_LSE>
-__global__ void __launch_bounds__(32 * AB_WARPS, AB_WARPS > 4 ? 2 : 2) attention_bwd_kernel(const AttnBwdArgs p) {
+template <bool HAVE_LSE, int WARPS, int MIN_CTAS>
+__global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) attention_bwd_kernel(const AttnBwdArgs p) {
+  constexpr int AB_WARPS = WARPS;
+  constexpr bool AB_RELOAD_KV = WARPS * MIN_CTAS > 8;   // <= 128 registers per thread: no room for resident K/V fragments
+  constexpr int AB_UNROLL = AB_RELOAD_KV ? 1 : 2;       // key / query tiles per loop trip: independent MMA chains to overlap
   extern __shared__ __align__(128) uint8_t smem[];
   const int h = blockIdx.x, f = blockIdx.y;
   const int D = p.H * 64;
@@ -391,6 +393,23 @@ __global__ void __launch_bounds__(1024) attention_bwd_reduce_kernel(const float*
   dkv_aux[(long long)arow * 2 * D + (c < 64 ? h * 64 + c : D + h * 64 + (c - 64))] = v;
 }
 
+template <int WARPS, int MIN_CTAS>
+static int launch_attention_bwd(const AttnBwdArgs& a, bool have_lse, size_t smem_bytes, cudaStream_t stream) {
+  static size_t attr_bytes_dev[64] = {0};
+  size_t& attr_bytes = attr_bytes_dev[device_slot()];
+  if (smem_bytes > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<true, WARPS, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_bwd_kernel<false, WARPS, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(attention_bwd): %s", cudaGetErrorString(e)); return (int)e; }
+    attr_bytes = smem_bytes;
+  }
+  const dim3 grid(a.H, a.BT);
+  if (have_lse) attention_bwd_kernel<true, WARPS, MIN_CTAS><<<grid, 32 * WARPS, smem_bytes, stream>>>(a);
+  else attention_bwd_kernel<false, WARPS, MIN_CTAS><<<grid, 32 * WARPS, smem_bytes, stream>>>(a);
+  return GAVA_OK;
+}
+
 int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, const float* lse, void* dqkv,
                   float* dkv_aux, float* scratch, int B, int T, int N0, int G, int H, int n_q, cudaStream_t stream) {
   if (!qkv || !kv_aux || !out || !dout || !dqkv || !dkv_aux || B <= 0 || T <= 0 || N0 <= 0 || G < 0 || H <= 0 || n_q <= 0 ||
@@ -414,21 +433,22 @@ int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const vo
   a.s_pad = (a.S + 15) / 16 * 16;
   const size_t smem_bytes = (size_t)(2 * a.q_pad + 2 * a.s_pad) * 128 + (size_t)a.q_pad * 8;
   if (smem_bytes > 226 * 1024) { set_error("attention_bwd: %d keys x %d queries exceed the shared-memory budget", a.S, N0); return GAVA_ERR_SHAPE; }
-  static size_t attr_bytes_dev[64] = {0};
-  size_t& attr_bytes = attr_bytes_dev[device_slot()];
-  if (smem_bytes > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(attention_bwd): %s", cudaGetErrorString(e)); return (int)e; }
-    attr_bytes = smem_bytes;
-  }
   const long long D = 64LL * H;
   if (scratch == nullptr) {   // atomics path: accumulate straight into dkv_aux
     cudaError_t e = cudaMemsetAsync(dkv_aux, 0, sizeof(float) * (size_t)(G + 2 * B * T) * 2 * D, stream);
     if (e != cudaSuccess) { set_error("attention_bwd memset: %s", cudaGetErrorString(e)); return (int)e; }
   }
-  if (lse) attention_bwd_kernel<true><<<dim3(H, B * T), 32 * AB_WARPS, smem_bytes, stream>>>(a);
-  else attention_bwd_kernel<false><<<dim3(H, B * T), 32 * AB_WARPS, smem_bytes, stream>>>(a);
+  // two CTAs per SM while their shared memory (+1 KB each of system reservation) fits 228 KB; else one CTA of 8 warps
+  const bool two_per_sm = 2 * (smem_bytes + 1024) <= 228 * 1024;
+  int lrc;
+#if GAVA_AB_WARPS > 4
+  lrc = two_per_sm ? launch_attention_bwd<8, 2>(a, lse != nullptr, smem_bytes, stream)
+                   : launch_attention_bwd<8, 1>(a, lse != nullptr, smem_bytes, stream);
+#else
+  lrc = two_per_sm ? launch_attention_bwd<4, 2>(a, lse != nullptr, smem_bytes, stream)
+                   : launch_attention_bwd<8, 1>(a, lse != nullptr, smem_bytes, stream);
+#endif
+  if (lrc) return lrc;
   int rc = check_launch("attention_bwd");
   if (rc || scratch == nullptr) return rc;
   if (G > 0) attention_bwd_reduce_kernel<<<dim3(G, H), dim3(128, 8), 0, stream>>>(scratch, dkv_aux, 0, G, T, B * T, H);

@@ -71,7 +71,7 @@ def _attn_ref(qkv, kv_aux, B, T, N0, G, H):
     return torch.cat(outs, 0)
 
 
-@pytest.mark.parametrize("B,T,N0,G,H", [(2, 8, 197, 8, 12), (1, 3, 17, 8, 2), (2, 4, 50, 8, 3), (1, 70, 197, 8, 2)])
+@pytest.mark.parametrize("B,T,N0,G,H", [(2, 8, 197, 8, 12), (1, 3, 17, 8, 2), (2, 4, 50, 8, 3), (1, 70, 197, 8, 2), (1, 16, 257, 8, 2)])
 def test_attention_bwd(cuda, B, T, N0, G, H):
     from gava_clip_b200 import ops
     g = _gen(B * 1000 + T * 10 + N0)
