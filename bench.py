@@ -473,6 +473,10 @@ def measure_finetune(D: Dist, cfg: dict, steps: int, warmup: int, detailed: bool
                     tuner.step(clip, labels, memory, mem_labels)
                 torch.cuda.synchronize()
                 per = kt.drain()
+                out["gemm_shapes"] = {t: {"launches_per_step": d["launches"] // 3, "avg_us": round(1e3 * d["ms"] / d["launches"], 1),
+                                          "ms_per_step": round(d["ms"] / 3, 3),
+                                          "tflops": round(d["flops"] / (d["ms"] * 1e-3) / 1e12, 1)}
+                                      for t, d in sorted(kt.gemm_shapes.items(), key=lambda kv: -kv[1]["ms"])[:14]}
         finally:
             eng.use_graph = saved[0]
             if tt is not None:
@@ -518,7 +522,8 @@ def run_finetune(args, cfg):
                             "how": "CUDA events around every kernel of 3 consecutive eager steps",
                             "launches_per_step": gm["launches"],
                             "kernel_ms_per_step": {n: round(d["ms"], 3) for n, d in sorted(per.items(), key=lambda kv: -kv[1]["ms"])},
-                            "kernel_share_of_step": {n: round(d["ms"] / total, 4) for n, d in per.items()}}
+                            "kernel_share_of_step": {n: round(d["ms"] / total, 4) for n, d in per.items()},
+                            "gemm_shapes_eager": ft.get("gemm_shapes")}
         # forward 1x + backward (dgrad only) ~1x of the forward's dense FLOPs, attention backward 2.5x its forward
         line["step_tensor_util"] = {"algorithmic_gflop_per_clip_fwd": f_clip / 1e9,
                                     "tflops_per_gpu_fwd_equiv_x2": 2 * ft["value"] / D.world * f_clip / 1e12}

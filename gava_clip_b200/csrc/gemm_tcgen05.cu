@@ -90,7 +90,8 @@ struct FoldRow { float rstd, nmr; const float* colsum_s; };
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage, int row0, int col0,
                                                const uint32_t (&v)[32], const float4 (&resid)[8], const float* bias_s,
-                                               int lane, const FoldRow& fold, float (&rs)[8], float (&rq)[8]) {
+                                               int lane, const FoldRow& fold, float (&rs)[8], float (&rq)[8],
+                                               const uint4 (&auxv)[4]) {
   if constexpr (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16 || MODE == EPI_DGELU_BF16 || MODE == EPI_LNFOLD_BF16) {
     float acc[32];
     {  // bias of this chunk from shared memory (staged per tile before the accumulator wait; broadcast LDS.128)
@@ -145,11 +146,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
       for (int i = 0; i < 4; ++i) {
         const int r = 8 * i + (lane >> 2);
         uint4 w = *reinterpret_cast<const uint4*>(stage + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
-        if (dgelu) {   // dgrad through QuickGELU: multiply by g'(a1), a1 read coalesced (row segments)
-          if (row0 + r < p.M) {
-            const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(p.aux + (long long)(row0 + r) * p.ld_aux + col0 + 8 * c));
-            w.x = dgelu_mul2(w.x, a1.x); w.y = dgelu_mul2(w.y, a1.y); w.z = dgelu_mul2(w.z, a1.z); w.w = dgelu_mul2(w.w, a1.w);
-          }
+        if (dgelu) {   // dgrad through QuickGELU: multiply by g'(a1); a1 was prefetched as coalesced row segments
+          const uint4 a1 = auxv[i];
+          w.x = dgelu_mul2(w.x, a1.x); w.y = dgelu_mul2(w.y, a1.y); w.z = dgelu_mul2(w.z, a1.z); w.w = dgelu_mul2(w.w, a1.w);
         }
         if (row0 + r < p.M) *reinterpret_cast<uint4*>(obase + (long long)(row0 + r) * ld) = w;
       }
@@ -242,6 +241,23 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage,
       }
     }
     __syncwarp();
+    // DGELU: the fc1 pre-activations this lane multiplies with after the smem transpose (rows 8 i + lane / 4, 8 columns
+    // at 8 (lane % 4)) for all the warp's chunks, fetched before the accumulator wait: the latency hides under the
+    // mainloop.  With the loads issued inside the store loop the K = 768 dgrad (fc2^T) ran at 546 TFLOP/s, epilogue-bound
+    // on four serial global-load latencies per chunk; one chunk of look-ahead gave 958.
+    uint4 aux_all[MODE == EPI_DGELU_BF16 ? NCH : 1][4];
+    auto aux_prefetch = [&](int cc, uint4 (&dst)[4]) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int grow = row0 + 8 * i + (lane >> 2);
+        dst[i] = (grow < p.M) ? __ldg(reinterpret_cast<const uint4*>(p.aux + (long long)grow * p.ld_aux + col_base + cc * 32 + 8 * (lane & 3)))
+                              : make_uint4(0, 0, 0, 0);
+      }
+    };
+    if constexpr (MODE == EPI_DGELU_BF16) {   // every chunk of the tile, all before the accumulator wait
+#pragma unroll
+      for (int cc = 0; cc < NCH; ++cc) aux_prefetch(cc, aux_all[cc]);
+    }
 #if GAVA_GEMM_DEBUG == 4
     const long long t0 = clock64();
 #endif
@@ -262,7 +278,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage,
 #if GAVA_GEMM_DEBUG != 1
       FoldRow fc = fold;
       if constexpr (MODE == EPI_LNFOLD_BF16) fc.colsum_s = fold.colsum_s ? fold.colsum_s + cc * 32 : nullptr;
-      epilogue_chunk<MODE>(p, stage, row0, col_base + cc * 32, cur, resid, bias_s + cc * 32, lane, fc, rs, rq);
+      epilogue_chunk<MODE>(p, stage, row0, col_base + cc * 32, cur, resid, bias_s + cc * 32, lane, fc, rs, rq,
+                           aux_all[MODE == EPI_DGELU_BF16 ? cc : 0]);
 #endif
     }
   } else {
@@ -306,7 +323,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage,
 #if GAVA_GEMM_DEBUG == 6   // experiment: residual loads but no stores
       if (v[0] == 0x7fc12345u && resid[0].x == 1.2345f) reinterpret_cast<uint32_t*>(p.out)[0] = v[3];
 #elif GAVA_GEMM_DEBUG != 1
-      epilogue_chunk<MODE>(p, stage, row0, col0, v, resid, nullptr, lane, fold, rs, rq);
+      const uint4 no_aux[4] = {};
+      epilogue_chunk<MODE>(p, stage, row0, col0, v, resid, nullptr, lane, fold, rs, rq, no_aux);
 #endif
     }
     if constexpr (MODE == EPI_BIAS_RESID_STATS_F32) {
