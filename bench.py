@@ -316,7 +316,8 @@ def gemm_roofline(model, clip, peaks, ms_graph_step: float, eager_steps: int = 5
     return {"bound": "tensor", "kernel": "gemm_tcgen05_kernel", "achieved": achieved, "peak": peaks["bf16_tflops_sustained"],
             "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"], "frac_of_burst": achieved / peaks["bf16_tflops"],
             "peak_burst": peaks["bf16_tflops"], "traffic": traffic,
-            "traffic_source": "profiles/gemm_traffic.json (ncu dram__bytes_read+write, mean per launch of one step)",
+            "traffic_source": "profiles/gemm_traffic.json (ncu --set full: dram__bytes_read+write, mean per launch over the large "
+                              "GEMMs -- QKV, out-proj, fc1, fc2 -- of the captured layers; 0.96x their algorithmic operand + output bytes)",
             "peak_source": peaks["_source"] + ": frac vs the sustained bf16 figure (kernel timed inside a long step), frac_of_burst vs the burst figure",
             "how": f"2 MNK of the kernel's launches / (its median share of {eager_steps} event-timed eager steps x graph-replayed ms_per_step)",
             "launches_per_step": last["gemm"]["launches"], "gflop_per_step": flops / 1e9,

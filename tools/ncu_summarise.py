@@ -52,9 +52,11 @@ def full(rep, out, traffic_json=None):
                 gemm.append((name, rd + wr, float(r[ix["gpu__time_duration.sum"]])))
     print(open(out).read())
     if traffic_json and gemm:
-        json.dump({"source": rep.split("/")[-1], "what": "dram__bytes_read.sum + dram__bytes_write.sum per launch of gemm2_tcgen05_kernel, "
-                   "averaged over the 8 launches of one transformer layer (4 small temporal-message GEMMs + QKV, out-proj, fc1, fc2)",
-                   "dram_bytes_per_launch": sum(g[1] for g in gemm) / len(gemm),
+        json.dump({"source": rep.split("/")[-1], "what": "dram__bytes_read.sum + dram__bytes_write.sum per launch of gemm2_tcgen05_kernel (the CTA-pair kernel: the "
+                   "large GEMMs QKV, out-proj, fc1, fc2 of a transformer layer): mean per epilogue kind, then over the kinds",
+                   # one figure per epilogue kind first (a capture window may hold two fc1 and one QKV), then their mean
+                   "dram_bytes_per_launch": (lambda by: sum(sum(v) / len(v) for v in by.values()) / len(by))(
+                       {n: [g[1] for g in gemm if g[0] == n] for n in {g[0] for g in gemm}}),
                    "per_launch": [{"kernel": g[0], "dram_bytes": g[1], "us": g[2]} for g in gemm]}, open(traffic_json, "w"), indent=1)
 
 
