@@ -5,7 +5,7 @@ import os
 import pytest
 import torch
 
-from tests.util import build_model, fx
+from tests.util import build_model, fx, rel_err
 
 
 def test_cpu_input_fails_loudly():
@@ -62,3 +62,49 @@ def test_flops_formula():
     assert abs(VIT_B16_T8.flops_per_clip() / 1e9 - 298.59) < 0.05
     assert abs(VIT_B16_T16.flops_per_clip() / 1e9 - 606.50) < 0.05
     assert abs(VIT_L14_T16.flops_per_clip() / 1e9 - 2749.72) < 0.05
+
+
+def test_norm1_fold_packing_is_the_layernorm_identity():
+    """Host half of the norm1 fold (TowerEngine.pack): with W'' = W diag(gamma) - rowmean and b' = b + W beta,
+    LN(x) W^T + b == rstd * (x W''^T) + b' for ANY x -- the mean of x drops out because the rows of W'' sum to zero.  Checked on
+    the packed tensors of the tiny model (bf16 rounding of W'' is the only difference from an fp32 LayerNorm + linear)."""
+    import torch.nn.functional as F
+    from gava_clip_b200.vision_encoder import TowerEngine, LN_EPS
+    model, kw, B = build_model("tiny")
+    eng = TowerEngine(model.visual, torch.device("cpu"))
+    assert eng.fold_norm1 and eng.defer_resid
+    eng.pack()
+    P = eng.packed
+    assert "b0.qkv.wf" not in P                       # block 0's norm1 comes out of the ln_pre pass
+    blk = model.visual.blocks[1]
+    wf, bf_ = P["b1.qkv.wf"], P["b1.qkv.bf"]
+    D = model.visual.feature_dim
+    assert wf.dtype == torch.bfloat16 and wf.shape == (3 * D, D) and bf_.shape == (3 * D,)
+    w = torch.cat([blk.attn.q_proj.weight, blk.attn.k_proj.weight, blk.attn.v_proj.weight], 0).detach()
+    b = torch.cat([blk.attn.q_proj.bias, blk.attn.k_proj.bias, blk.attn.v_proj.bias], 0).detach()
+    # rows of the packed operand sum to (almost) zero: |sum| is bf16 rounding noise, far below the row's 1-norm
+    assert float((wf.float().sum(1).abs() / wf.float().abs().sum(1)).max()) < 2e-3
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(64, D, generator=g) * 3.0 + 1.5                      # a mean the epilogue never sees
+    ref = F.layer_norm(x, (D,), blk.norm1.weight.detach(), blk.norm1.bias.detach(), LN_EPS) @ w.t() + b
+    mean, var = x.mean(1, keepdim=True), x.var(1, unbiased=False, keepdim=True)
+    rstd = torch.rsqrt(var + LN_EPS)
+    folded = rstd * (x @ wf.float().t()) + bf_
+    assert rel_err(folded, ref) < 4e-3                                    # bf16 rounding of W'' only
+    # the parameters change -> the folded operands are re-packed
+    with torch.no_grad():
+        blk.norm1.weight.mul_(1.5)
+    eng.pack()
+    ref2 = F.layer_norm(x, (D,), blk.norm1.weight.detach(), blk.norm1.bias.detach(), LN_EPS) @ w.t() + b
+    assert rel_err(rstd * (x @ eng.packed["b1.qkv.wf"].float().t()) + eng.packed["b1.qkv.bf"], ref2) < 4e-3
+
+
+def test_gemm_stats_slots_host_function():
+    """gava_gemm_stats_slots is pure host arithmetic (no GPU): one slot per epilogue-warp column share."""
+    from gava_clip_b200 import ops
+    assert ops.gemm_stats_slots(100864, 768) == 6          # 256-wide tiles: 128 columns per warp
+    assert ops.gemm_stats_slots(65792, 1024) == 8
+    assert ops.gemm_stats_slots(512, 768) == 12            # small-M shapes run 128-wide tiles: 64 columns per warp
+    assert ops.gemm_stats_slots(102, 128) == 2
+    with pytest.raises(ValueError):
+        ops.gemm_stats_slots(100, 100)
