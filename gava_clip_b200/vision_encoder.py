@@ -139,11 +139,14 @@ class TowerEngine:
         self.ws: Dict[Tuple[int, int], Dict[str, Tensor]] = {}
         self.graphs: Dict[tuple, Tuple[torch.cuda.CUDAGraph, Tensor, int]] = {}
         self.use_graph = os.environ.get("GAVA_CUDA_GRAPH", "1") != "0"
-        # side-stream branch for the temporal-message chain: measured neutral on B200 (3061 vs 3056 clips/s; the pair
-        # GEMM CTAs own a whole SM each, so the small kernels cannot co-run), hence off by default
-        self.overlap_chain = os.environ.get("GAVA_OVERLAP_CHAIN", "0") == "1"
-        # with the chain on a side stream, the QKV GEMM's persistent grid is capped so that the chain's CTAs find free SMs
-        self.qkv_ctas = int(os.environ.get("GAVA_QKV_CTAS", "0"))
+        # The temporal-message chain (eight latency-bound launches on 512 rows, ~65 us per layer back to back) runs as a
+        # side-stream branch of the graph next to the block's QKV GEMM.  The persistent GEMM CTAs own a whole SM each, so
+        # the small kernels only co-run if the GEMM leaves SMs free: its grid is capped at (SMs - 16) CTAs.  Measured on two
+        # boxes (profiles/r02_chain_overlap.txt): uncapped 0 %, 144: +0.7 %, 140: +0.7 %, 136: +1.6 %, 132: +2.0 %, 128: +1.7 %,
+        # 124: +1.4 %, <= 120: slower than serial.  GAVA_OVERLAP_CHAIN=0 restores the serial schedule.
+        self.overlap_chain = os.environ.get("GAVA_OVERLAP_CHAIN", "1") == "1"
+        n_sm = torch.cuda.get_device_properties(device).multi_processor_count if device.type == "cuda" else 148
+        self.qkv_ctas = int(os.environ.get("GAVA_QKV_CTAS", str((n_sm - 16) // 2 * 2)))
         # Deferred attention residual: out_proj writes its result as a bf16 delta (no fp32 read-modify-write of the stream,
         # which made that K=768 GEMM HBM-bound), norm2 normalises x + delta, and the fc2 epilogue -- hidden under a K=3072
         # mainloop -- adds delta together with the MLP output.  Same bytes overall, but none of them on a critical path.
