@@ -140,7 +140,7 @@ class TowerTrainer(TowerEngine):
             "sum_n": per_layer(BT, D, dt=bf), "sqkv": per_layer(BT, 3 * D, dt=bf), "smix": per_layer(BT, D, dt=bf),
             # ---- forward scratch
             "patches": z(BT * (N0 - 1), self.packed["patch.w"].shape[1], dt=bf), "xn": z(M, D, dt=bf), "h": z(M, Dm, dt=bf),
-            "cls_bf": z(BT, D, dt=bf), "aux_n": z(R, D, dt=bf), "frame_feat": z(BT, Ep, dt=f32),
+            "cls_bf": z(BT, D, dt=bf), "cls_bf2": z(BT, D, dt=bf), "aux_n": z(R, D, dt=bf), "frame_feat": z(BT, Ep, dt=f32),
             # ---- backward scratch
             "dx": z(M, D, dt=f32), "dxb": z(M, D, dt=bf), "g4": z(M, Dm, dt=bf), "gD": z(M, D, dt=bf),
             "dqkv": z(M, 3 * D, dt=bf), "dkvaux": z(R, 2 * D, dt=f32),
@@ -238,21 +238,33 @@ class TowerTrainer(TowerEngine):
         ops.layernorm2(x0, P["ln_pre.w"], P["ln_pre.b"], W["x_in"][0], P["b0.norm1.w"], P["b0.norm1.b"], xn, rows=M)
 
         L = len(e.blocks)
+        main = torch.cuda.current_stream(self.device)
+        side = self.side_stream if self.overlap_chain else None
+        cap = self.qkv_ctas if side is not None else 0
         for i in range(L):
             k = f"b{i}."
             xin = W["x_in"][i]
             xmid, xnext = (W["x_mid"][i], W["x_in"][i + 1]) if i < L - 1 else (None, None)
             cp, sm = W["cls_proj"][i], W["summary"][i]
-            # temporal message (utils.py:160-188)
-            ops.layernorm(xin, None, None, W["cls_bf"], rows=BT, in_row_stride=N0 * D)
-            ops.gemm(W["cls_bf"], P[k + "cls.w"], cp, mode=ops.EPI_BIAS_F32, bias=P[k + "cls.b"])
-            ops.layernorm(cp, P[k + "summary_ln.w"], P[k + "summary_ln.b"], W["sum_n"][i], rows=BT, in_row_stride=D)
-            ops.gemm(W["sum_n"][i], P[k + "sqkv.w"], W["sqkv"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "sqkv.b"])
-            ops.temporal_attention(W["sqkv"][i], W["smix"][i], B, T, H)
-            ops.gemm(W["smix"][i], P[k + "sout.w"], sm, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "sout.b"], resid=cp)
-            ops.prompt_rows(P["global_prompts"][i], P[k + "local"], cp, sm, P[k + "norm1.w"], P[k + "norm1.b"], W["aux_n"],
-                            B, T, LN_EPS)
-            ops.gemm(W["aux_n"], P[k + "qkv.w"][D:], W["kvaux"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:])
+            # temporal message (utils.py:160-188): a side-stream branch next to norm1 + the QKV GEMM (whose grid is capped
+            # so that these small launches find free SMs), joined before the attention kernel -- as in TowerEngine
+            if side is not None:
+                ev_x = torch.cuda.Event()
+                ev_x.record(main)
+                side.wait_event(ev_x)
+            with torch.cuda.stream(side if side is not None else main):
+                ops.layernorm(xin, None, None, W["cls_bf2"], rows=BT, in_row_stride=N0 * D)
+                ops.gemm(W["cls_bf2"], P[k + "cls.w"], cp, mode=ops.EPI_BIAS_F32, bias=P[k + "cls.b"])
+                ops.layernorm(cp, P[k + "summary_ln.w"], P[k + "summary_ln.b"], W["sum_n"][i], rows=BT, in_row_stride=D)
+                ops.gemm(W["sum_n"][i], P[k + "sqkv.w"], W["sqkv"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "sqkv.b"])
+                ops.temporal_attention(W["sqkv"][i], W["smix"][i], B, T, H)
+                ops.gemm(W["smix"][i], P[k + "sout.w"], sm, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "sout.b"], resid=cp)
+                ops.prompt_rows(P["global_prompts"][i], P[k + "local"], cp, sm, P[k + "norm1.w"], P[k + "norm1.b"], W["aux_n"],
+                                B, T, LN_EPS)
+                ops.gemm(W["aux_n"], P[k + "qkv.w"][D:], W["kvaux"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:])
+                if side is not None:
+                    ev_kv = torch.cuda.Event()
+                    ev_kv.record(side)
             # x = x + attn(norm1(x))   (utils.py:190-191); block 0's norm1 came out of the ln_pre pass
             if i > 0:
                 ops.layernorm(xin, P[k + "norm1.w"], P[k + "norm1.b"], xn, rows=M, in_row_stride=D)
@@ -261,9 +273,11 @@ class TowerTrainer(TowerEngine):
                 # schedule -- K/V are projected for all rows, Q / attention query / out-proj / MLP for the cls rows alone.
                 qkv = W["qkv"][i]
                 xn_cls = xn.view(BT, N0 * D)[:, :D]
-                ops.gemm(xn, P[k + "qkv.w"][D:], qkv[:, D:], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:])
+                ops.gemm(xn, P[k + "qkv.w"][D:], qkv[:, D:], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:], max_ctas=cap)
                 ops.gemm(xn_cls, P[k + "qkv.w"][:D], qkv.view(BT, N0 * 3 * D)[:, :D], mode=ops.EPI_BIAS_BF16,
                          bias=P[k + "qkv.b"][:D])
+                if side is not None:
+                    main.wait_event(ev_kv)
                 ops.attention_train(qkv, W["kvaux"][i], W["o"][i], W["lse"][i], B=B, T=T, N0=N0, G=G, H=H, n_q=1)
                 ops.gemm(W["o"][i].view(BT, N0 * D)[:, :D], P[k + "out.w"], W["xc_mid"], mode=ops.EPI_BIAS_RESID_F32,
                          bias=P[k + "out.b"], resid=xin.view(BT, N0 * D)[:, :D])
@@ -273,7 +287,9 @@ class TowerTrainer(TowerEngine):
                 ops.gemm(W["hc"], P[k + "fc2.w"], W["xc_out"], mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "fc2.b"],
                          resid=W["xc_mid"])
                 break
-            ops.gemm(xn, P[k + "qkv.w"], W["qkv"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"])
+            ops.gemm(xn, P[k + "qkv.w"], W["qkv"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"], max_ctas=cap)
+            if side is not None:
+                main.wait_event(ev_kv)
             ops.attention_train(W["qkv"][i], W["kvaux"][i], W["o"][i], W["lse"][i], B=B, T=T, N0=N0, G=G, H=H)
             ops.gemm(W["o"][i], P[k + "out.w"], xmid, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "out.b"], resid=xin)
             # x = x + fc2(QuickGELU(fc1(norm2(x))))   (utils.py:199); the pre-activations stay for the DGELU epilogue
@@ -417,27 +433,43 @@ class TowerTrainer(TowerEngine):
             ops.gemm(dxb, P[k + "out.wT"], gD, mode=ops.EPI_BIAS_BF16)
             ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G,
                               H=H, lse=W["lse"][i], scratch=W["dkv_slots"])
-        ops.gemm(W["dqkv"], P[k + "qkv.wT"], gD, mode=ops.EPI_BIAS_BF16)
+        # The K/V-only prompt rows' backward (~20 latency-bound launches on G + 2 BT rows, everything from d kv_aux down to
+        # d cls_proj and the layer's parameter gradients) depends only on the attention backward's d kv_aux and touches none
+        # of the stream's buffers: it runs on the side stream next to the qkv^T dgrad GEMM (grid capped, as in the forward)
+        # and the LayerNorm backward, and joins before its result is added into the cls rows of dx.
+        main = torch.cuda.current_stream(self.device)
+        side = self.side_stream if self.overlap_chain else None
+        if side is not None:
+            ev_a = torch.cuda.Event()
+            ev_a.record(main)
+            side.wait_event(ev_a)
+        ops.gemm(W["dqkv"], P[k + "qkv.wT"], gD, mode=ops.EPI_BIAS_BF16, max_ctas=self.qkv_ctas if side is not None else 0)
         ops.layernorm_bwd(gD, W["x_in"][i], P[k + "norm1.w"], dx, rows=M, D=D, add1=dx, dx_bf16=dxb)
-        # ---- K/V-only prompt rows: d kv_aux -> normalised rows -> global / local / summary / cls_proj gradients
-        ops.layernorm(W["dkvaux"].view(2 * R, D), None, None, W["dkvaux_bf"].view(2 * R, D), rows=2 * R, in_row_stride=D)
-        ops.gemm(W["dkvaux_bf"], P[k + "qkv.wT"][:, D:], W["daux_n"], mode=ops.EPI_BIAS_BF16)
-        ops.prompt_rows_bwd(W["daux_n"], P["global_prompts"][i], P[k + "local"], cp, sm, P[k + "norm1.w"],
-                            g["global_prompts"][i], W["d_lcp"], W["d_sum"], ext if i == L - 1 else None, B, T, LN_EPS)
-        ops.group_sum(W["d_lcp"], g[kb + "local_prompts"], outer=B, J=T, inner=1)
-        # ---- summary = cls_proj + out_proj(temporal_attention(qkv(summary_ln(cls_proj))))   (utils.py:168-170)
-        ops.layernorm(W["d_sum"], None, None, W["d_sum_bf"], rows=BT, in_row_stride=D)     # cast
-        ops.gemm(W["d_sum_bf"], P[k + "sout.wT"], W["dsmix"], mode=ops.EPI_BIAS_BF16)
-        self._wgrad(W, W["d_sum"], W["smix"][i], g[kb + "summary_attn_layer.out_proj.weight"])
-        ops.group_sum(W["d_sum"], g[kb + "summary_attn_layer.out_proj.bias"], outer=BT, J=1, inner=1)
-        ops.temporal_attention_bwd(W["sqkv"][i], W["dsmix"], W["dsqkv"], B, T, H)
-        ops.gemm(W["dsqkv"], P[k + "sqkv.wT"], W["dsn"], mode=ops.EPI_BIAS_BF16)
-        self._wgrad(W, W["dsqkv"], W["sum_n"][i], g[kb + "sqkv.weight"])
-        ops.group_sum(W["dsqkv"], g[kb + "sqkv.bias"], outer=BT, J=1, inner=1)
-        g[kb + "summary_ln.weight"].zero_(); g[kb + "summary_ln.bias"].zero_()
-        ops.layernorm_bwd(W["dsn"], cp, P[k + "summary_ln.w"], W["d_cp"], rows=BT, D=D, add1=W["d_lcp"],
-                          add2=W["d_sum"], dx_bf16=W["d_cp_bf"], dw=g[kb + "summary_ln.weight"],
-                          db=g[kb + "summary_ln.bias"])
+        with torch.cuda.stream(side if side is not None else main):
+            # ---- K/V-only prompt rows: d kv_aux -> normalised rows -> global / local / summary / cls_proj gradients
+            ops.layernorm(W["dkvaux"].view(2 * R, D), None, None, W["dkvaux_bf"].view(2 * R, D), rows=2 * R, in_row_stride=D)
+            ops.gemm(W["dkvaux_bf"], P[k + "qkv.wT"][:, D:], W["daux_n"], mode=ops.EPI_BIAS_BF16)
+            ops.prompt_rows_bwd(W["daux_n"], P["global_prompts"][i], P[k + "local"], cp, sm, P[k + "norm1.w"],
+                                g["global_prompts"][i], W["d_lcp"], W["d_sum"], ext if i == L - 1 else None, B, T, LN_EPS)
+            ops.group_sum(W["d_lcp"], g[kb + "local_prompts"], outer=B, J=T, inner=1)
+            # ---- summary = cls_proj + out_proj(temporal_attention(qkv(summary_ln(cls_proj))))   (utils.py:168-170)
+            ops.layernorm(W["d_sum"], None, None, W["d_sum_bf"], rows=BT, in_row_stride=D)     # cast
+            ops.gemm(W["d_sum_bf"], P[k + "sout.wT"], W["dsmix"], mode=ops.EPI_BIAS_BF16)
+            self._wgrad(W, W["d_sum"], W["smix"][i], g[kb + "summary_attn_layer.out_proj.weight"])
+            ops.group_sum(W["d_sum"], g[kb + "summary_attn_layer.out_proj.bias"], outer=BT, J=1, inner=1)
+            ops.temporal_attention_bwd(W["sqkv"][i], W["dsmix"], W["dsqkv"], B, T, H)
+            ops.gemm(W["dsqkv"], P[k + "sqkv.wT"], W["dsn"], mode=ops.EPI_BIAS_BF16)
+            self._wgrad(W, W["dsqkv"], W["sum_n"][i], g[kb + "sqkv.weight"])
+            ops.group_sum(W["dsqkv"], g[kb + "sqkv.bias"], outer=BT, J=1, inner=1)
+            g[kb + "summary_ln.weight"].zero_(); g[kb + "summary_ln.bias"].zero_()
+            ops.layernorm_bwd(W["dsn"], cp, P[k + "summary_ln.w"], W["d_cp"], rows=BT, D=D, add1=W["d_lcp"],
+                              add2=W["d_sum"], dx_bf16=W["d_cp_bf"], dw=g[kb + "summary_ln.weight"],
+                              db=g[kb + "summary_ln.bias"])
+            if side is not None:
+                ev_b = torch.cuda.Event()
+                ev_b.record(side)
+        if side is not None:
+            main.wait_event(ev_b)
         # ---- cls_proj (frozen): dx[cls rows] += d_cp Wc; then refresh the bf16 copy of dx's cls rows (the LayerNorm-
         # backward kernels keep the other rows of dxb current as a by-product)
         ops.gemm(W["d_cp_bf"], P[k + "cls.wT"], dx_cls, mode=ops.EPI_BIAS_RESID_F32, resid=dx_cls)
