@@ -34,6 +34,11 @@ class ClipStreamer:
             self._stage[k] = torch.empty(host.shape, device=self.device, dtype=host.dtype)   # fp32 (B,3,T,H,W) or uint8 (B,T,H,W,3)
             # the caching allocator may hand back a block whose last use on the compute stream is still in flight
             self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+            # the two staging slots live as long as the streamer: the tower replays a graph captured on the slot itself
+            # instead of copying it into its own static clip buffer first
+            visual = getattr(self.model, "visual", None)
+            if visual is not None and hasattr(visual, "engine"):
+                visual.engine(self.device).register_input(self._stage[k])
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._consumed[k])            # slot free again?
             self._stage[k].copy_(host, non_blocking=True)

@@ -157,6 +157,7 @@ class TowerEngine:
         self.side_stream = torch.cuda.Stream(device) if device.type == "cuda" else None
         self.launches_last_call = 0      # sm_100a kernels launched (or replayed) by the last run()
         self.pack_moves = 0              # times pack() re-allocated (instead of refreshing in place) a packed operand
+        self._registered_inputs: Dict[tuple, bool] = {}   # (data_ptr, shape, dtype) of caller-owned static clip buffers, oldest first
         # parity instrument (tests): a dict here receives, per layer, clones of the cls rows of the residual stream and of the
         # summary tokens -- the tensors the reference's per-block forward hooks see (VitaCLIP_vision_encoder.py:116-121).
         # Only honoured by eager runs (a replayed graph cannot clone per layer).
@@ -390,6 +391,18 @@ class TowerEngine:
             return ent[1]
         return torch.empty(*shape, device=self.device, dtype=dtype)
 
+    def register_input(self, buf: Tensor) -> None:
+        """Declare `buf` a long-lived device clip buffer (e.g. a streaming loop's staging slot): forwards on it replay a
+        graph captured on the buffer itself instead of copying it into the shape's static input first (616 MB of HBM
+        traffic per step at config 2).  At most a handful of buffers per shape (each holds its own captured graph)."""
+        ent = (buf.data_ptr(), tuple(buf.shape), buf.dtype)
+        self._registered_inputs.pop(ent, None)
+        self._registered_inputs[ent] = True
+        while len(self._registered_inputs) > 8:          # forget the oldest registrations (and the graphs captured on them)
+            oldest = next(iter(self._registered_inputs))
+            del self._registered_inputs[oldest]
+            self.graphs.pop(oldest[1] + (oldest[0],), None)
+
     def run(self, video: Tensor) -> Tuple[Tensor, Tensor]:
         """encode_frames, replayed from a CUDA graph per clip shape (launch-bound inner loop: ~190 launches)."""
         if self.enc.precision == "fp32":
@@ -402,10 +415,12 @@ class TowerEngine:
             out = self.encode_frames(video)
             self.launches_last_call = ops.launch_count() - n0
             return out
-        key = tuple(video.shape)
+        # a registered (long-lived) input buffer gets a graph of its own that reads it in place: no staging copy
+        reg = (video.data_ptr(), tuple(video.shape), video.dtype) in self._registered_inputs
+        key = tuple(video.shape) + ((video.data_ptr(),) if reg else ())
         ent = self.graphs.get(key)
         if ent is None:
-            static_in = video.clone()
+            static_in = video if reg else video.clone()
             self.encode_frames(static_in)                 # warm-up: kernel attributes, workspace, allocator
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()

@@ -163,6 +163,16 @@ def test_clip_streamer_matches_direct_calls(cuda):
     for a, b in zip(streamed, direct):
         assert torch.equal(a, b)
     assert st.h2d_bytes == sum(b.numel() * 4 for b in batches)
+    # the two staging slots are registered inputs: the tower replays graphs captured on the slots themselves (no staging copy)
+    eng = model.visual._engine
+    slot_graphs = [k for k in eng.graphs if len(k) == 6]                 # clip shape (5 dims) + buffer address
+    assert len(slot_graphs) == 2 and {k[5] for k in slot_graphs} == {s.data_ptr() for s in st._stage}
+    # a ragged tail batch re-allocates a slot: still identical to direct calls
+    tail = [torch.randn(n, 3, 3, 64, 64, generator=g).pin_memory() for n in (4, 4, 2)]
+    with torch.no_grad():
+        direct = [model(b.to(cuda))[0].cpu().clone() for b in tail]
+    for a, b in zip([o.clone() for o in st.run(tail)], direct):
+        assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("name", ["tiny", "b16_t8", "kapt_b16_t8", "tiny_global_only", "tiny_no_local", "tiny_no_summary"])
