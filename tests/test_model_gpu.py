@@ -776,3 +776,32 @@ def test_training_under_autocast_and_gradscaler(cuda):
     scaler.step(opt)
     scaler.update()
     assert all(torch.isfinite(p).all() for p in amp.parameters())
+
+
+@pytest.mark.parametrize("name", ["tiny", "b16_t8"])
+def test_schedule_switches_agree(cuda, name):
+    """The A/B switches of the inference schedule (norm1 fold, side-stream chain, CUDA graphs) change HOW the
+    step runs, not WHAT it computes: every combination stays inside the parity bound against the reference golden, the
+    overlap / graph switches are bit-neutral, and the fold moves the logits by bf16-rounding noise only."""
+    g = load_golden(name)
+    video = fx.make_inputs(name)["video"].to(cuda)
+    outs = {}
+    for fold in (True, False):
+        for overlap in (True, False):
+            for graph in (True, False):
+                model, kw, B = build_model(name, device=cuda)
+                eng = model.visual.engine(cuda)
+                eng.fold_norm1, eng.overlap_chain, eng.use_graph = fold, overlap, graph
+                with torch.no_grad():
+                    model(video)                                  # first call: eager warm-up (+ capture when graphs are on)
+                    logits = model(video)[0].clone()
+                assert rel_err(logits, g["logits"]) < TOL, (fold, overlap, graph)
+                outs[(fold, overlap, graph)] = logits
+    for fold in (True, False):
+        ref = outs[(fold, True, True)]
+        for key, v in outs.items():
+            if key[0] == fold:
+                assert torch.equal(v, ref), f"overlap / graph switch changed the result: {key}"
+    d = rel_err(outs[(True, True, True)], outs[(False, True, True)])
+    print(f"\n[{name}] norm1 fold on vs off: logits differ by {d:.2e} (relative to max |logit|)")
+    assert d < 1e-2
