@@ -80,8 +80,8 @@ SIGNATURES = {
     "gava_causal_attention_f32_fwd": [_p, _p, _i32, _i32, _i32, _p],
     "gava_prompt_rows_f32_fwd": [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p],
     "gava_layernorm_bwd": [_p, _i64, _i32, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _f32, _p],
-    "gava_attention_train_fwd": [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p],
-    "gava_attention_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p],
+    "gava_attention_train_fwd": [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p],
+    "gava_attention_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p],
     "gava_temporal_attention_bwd": [_p, _p, _p, _i32, _i32, _i32, _p],
     "gava_causal_attention_bwd": [_p, _p, _p, _i32, _i32, _i32, _p],
     "gava_prompt_rows_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _f32, _p],

@@ -134,8 +134,8 @@ int gava_attention_fwd(const void* qkv, const void* kv_aux, void* out, int32_t B
 }
 
 int gava_attention_train_fwd(const void* qkv, const void* kv_aux, void* out, float* lse, int32_t B, int32_t T, int32_t N0,
-                             int32_t G, int32_t H, int32_t n_q, void* stream) {
-  return attention(qkv, kv_aux, out, lse, B, T, N0, G, H, n_q, 3, (cudaStream_t)stream);
+                             int32_t G, int32_t H, int32_t n_q, int32_t key_groups, void* stream) {
+  return attention(qkv, kv_aux, out, lse, B, T, N0, G, H, n_q, key_groups, (cudaStream_t)stream);
 }
 
 int gava_head_fwd(const float* frame_feat, const float* summary_tok, const float* text_hat,
@@ -192,8 +192,8 @@ int gava_layernorm_bwd(const void* dy, int64_t dy_stride, int32_t dy_bf16, const
 
 int gava_attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, const float* lse,
                        void* dqkv, float* dkv_aux, float* scratch, int32_t B, int32_t T, int32_t N0, int32_t G, int32_t H,
-                       int32_t n_q, void* stream) {
-  return attention_bwd(qkv, kv_aux, out, dout, lse, dqkv, dkv_aux, scratch, B, T, N0, G, H, n_q, (cudaStream_t)stream);
+                       int32_t n_q, int32_t key_groups, void* stream) {
+  return attention_bwd(qkv, kv_aux, out, dout, lse, dqkv, dkv_aux, scratch, B, T, N0, G, H, n_q, key_groups, (cudaStream_t)stream);
 }
 
 int gava_temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int32_t B, int32_t T, int32_t H,

@@ -36,7 +36,14 @@ struct AttnBwdArgs {
   float* scratch;               // optional [BT, H, G+T+1, 128]: per-(frame, head) prompt-row gradients, reduced by a 2nd kernel
   int T, N0, G, H, S, BT, q_pad, s_pad;
   int n_q;   // query rows per frame that carry a gradient (N0, or 1 in the last layer: only the cls row reaches the output)
+  int groups;  // bit 0: local-prompt keys took part in the forward, bit 1: the summary-token key did (3 = full Vita-CLIP)
 };
+
+// key row `key` belongs to a prompt group the forward masked out (zero probability): its P, dS, dK, dV are exactly zero
+__device__ __forceinline__ bool key_disabled(const AttnBwdArgs& p, int key) {
+  const int a = key - (p.N0 + p.G);
+  return a >= 0 && key < p.S && ((a < p.T) ? !(p.groups & 1) : !(p.groups & 2));
+}
 
 // Launch shapes: <4 warps, 2 CTAs per SM> (255 registers per thread, K/V A-fragments of a key-tile unit live in
 // registers) while two CTAs' shared memory fits an SM; items with more keys (the 70-frame recipe: 276 keys, ViT-L/14 at
@@ -47,7 +54,9 @@ struct AttnBwdArgs {
 #define GAVA_AB_WARPS 4
 #endif
 
-template <bool HAVE_LSE, int WARPS, int MIN_CTAS>
+// MASKED: partial prompt-flag configurations (use_summary_token / use_local_prompts off): a separate instantiation, so the
+// full configuration's register allocation (209 of 255) is untouched.
+template <bool HAVE_LSE, int WARPS, int MIN_CTAS, bool MASKED>
 __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) attention_bwd_kernel(const AttnBwdArgs p) {
   constexpr int AB_WARPS = WARPS;
   constexpr bool AB_RELOAD_KV = WARPS * MIN_CTAS > 8;   // <= 128 registers per thread: no room for resident K/V fragments
@@ -162,10 +171,11 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) attention_bwd_kernel(con
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
         const int kc = kt * 16 + 8 * n + 2 * tg;
-        s[n][0] = (kc < p.S) ? s[n][0] * scale_log2 : -1e30f;
-        s[n][1] = (kc + 1 < p.S) ? s[n][1] * scale_log2 : -1e30f;
-        s[n][2] = (kc < p.S) ? s[n][2] * scale_log2 : -1e30f;
-        s[n][3] = (kc + 1 < p.S) ? s[n][3] * scale_log2 : -1e30f;
+        const bool on0 = kc < p.S && !(MASKED && key_disabled(p, kc)), on1 = kc + 1 < p.S && !(MASKED && key_disabled(p, kc + 1));
+        s[n][0] = on0 ? s[n][0] * scale_log2 : -1e30f;
+        s[n][1] = on1 ? s[n][1] * scale_log2 : -1e30f;
+        s[n][2] = on0 ? s[n][2] * scale_log2 : -1e30f;
+        s[n][3] = on1 ? s[n][3] * scale_log2 : -1e30f;
         mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
         mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
       }
@@ -234,6 +244,11 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) attention_bwd_kernel(con
           ds[n][1] = exp2f(s[n][1] * scale_log2 - lse0) * (dp[n][1] - dl0);
           ds[n][2] = exp2f(s[n][2] * scale_log2 - lse1) * (dp[n][2] - dl1);
           ds[n][3] = exp2f(s[n][3] * scale_log2 - lse1) * (dp[n][3] - dl1);
+          if constexpr (MASKED) {
+            const int kc = kt * 16 + 8 * n + 2 * tg;
+            if (key_disabled(p, kc)) { ds[n][0] = 0.f; ds[n][2] = 0.f; }
+            if (key_disabled(p, kc + 1)) { ds[n][1] = 0.f; ds[n][3] = 0.f; }
+          }
         }
         a[0] = pack_bf16x2(ds[0][0], ds[0][1]);
         a[1] = pack_bf16x2(ds[0][2], ds[0][3]);
@@ -300,6 +315,10 @@ __global__ void __launch_bounds__(32 * WARPS, MIN_CTAS) attention_bwd_kernel(con
           const float2 dl = *reinterpret_cast<const float2*>(&s_delta[qc]);
           pt[n][0] = exp2f(s[n][0] * scale_log2 - ls.x); pt[n][1] = exp2f(s[n][1] * scale_log2 - ls.y);
           pt[n][2] = exp2f(s[n][2] * scale_log2 - ls.x); pt[n][3] = exp2f(s[n][3] * scale_log2 - ls.y);
+          if constexpr (MASKED) {     // rows are keys kt*16 + g (+8)
+            if (key_disabled(p, kt * 16 + g)) { pt[n][0] = 0.f; pt[n][1] = 0.f; }
+            if (key_disabled(p, kt * 16 + g + 8)) { pt[n][2] = 0.f; pt[n][3] = 0.f; }
+          }
           ds[n][0] = pt[n][0] * (dp[n][0] - dl.x); ds[n][1] = pt[n][1] * (dp[n][1] - dl.y);
           ds[n][2] = pt[n][2] * (dp[n][2] - dl.x); ds[n][3] = pt[n][3] * (dp[n][3] - dl.y);
         }
@@ -393,25 +412,32 @@ __global__ void __launch_bounds__(1024) attention_bwd_reduce_kernel(const float*
   dkv_aux[(long long)arow * 2 * D + (c < 64 ? h * 64 + c : D + h * 64 + (c - 64))] = v;
 }
 
-template <int WARPS, int MIN_CTAS>
-static int launch_attention_bwd(const AttnBwdArgs& a, bool have_lse, size_t smem_bytes, cudaStream_t stream) {
+template <int WARPS, int MIN_CTAS, bool MASKED>
+static int launch_attention_bwd_m(const AttnBwdArgs& a, bool have_lse, size_t smem_bytes, cudaStream_t stream) {
   static size_t attr_bytes_dev[64] = {0};
   size_t& attr_bytes = attr_bytes_dev[device_slot()];
   if (smem_bytes > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<true, WARPS, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<true, WARPS, MIN_CTAS, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_bwd_kernel<false, WARPS, MIN_CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+      e = cudaFuncSetAttribute(attention_bwd_kernel<false, WARPS, MIN_CTAS, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(attention_bwd): %s", cudaGetErrorString(e)); return (int)e; }
     attr_bytes = smem_bytes;
   }
   const dim3 grid(a.H, a.BT);
-  if (have_lse) attention_bwd_kernel<true, WARPS, MIN_CTAS><<<grid, 32 * WARPS, smem_bytes, stream>>>(a);
-  else attention_bwd_kernel<false, WARPS, MIN_CTAS><<<grid, 32 * WARPS, smem_bytes, stream>>>(a);
+  if (have_lse) attention_bwd_kernel<true, WARPS, MIN_CTAS, MASKED><<<grid, 32 * WARPS, smem_bytes, stream>>>(a);
+  else attention_bwd_kernel<false, WARPS, MIN_CTAS, MASKED><<<grid, 32 * WARPS, smem_bytes, stream>>>(a);
   return GAVA_OK;
 }
 
+template <int WARPS, int MIN_CTAS>
+static int launch_attention_bwd(const AttnBwdArgs& a, bool have_lse, size_t smem_bytes, cudaStream_t stream) {
+  return (a.groups & 3) == 3 ? launch_attention_bwd_m<WARPS, MIN_CTAS, false>(a, have_lse, smem_bytes, stream)
+                             : launch_attention_bwd_m<WARPS, MIN_CTAS, true>(a, have_lse, smem_bytes, stream);
+}
+
 int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, const float* lse, void* dqkv,
-                  float* dkv_aux, float* scratch, int B, int T, int N0, int G, int H, int n_q, cudaStream_t stream) {
+                  float* dkv_aux, float* scratch, int B, int T, int N0, int G, int H, int n_q, int key_groups,
+                  cudaStream_t stream) {
   if (!qkv || !kv_aux || !out || !dout || !dqkv || !dkv_aux || B <= 0 || T <= 0 || N0 <= 0 || G < 0 || H <= 0 || n_q <= 0 ||
       n_q > N0) {
     set_error("attention_bwd: bad arguments");
@@ -429,6 +455,7 @@ int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const vo
   a.T = T; a.N0 = N0; a.G = G; a.H = H; a.BT = B * T;
   a.S = N0 + G + T + 1;
   a.n_q = n_q;
+  a.groups = key_groups;
   a.q_pad = (n_q + 15) / 16 * 16;
   a.s_pad = (a.S + 15) / 16 * 16;
   const size_t smem_bytes = (size_t)(2 * a.q_pad + 2 * a.s_pad) * 128 + (size_t)a.q_pad * 8;

@@ -101,7 +101,7 @@ int layernorm_bwd(const void* dy, long long dy_stride, int dy_bf16, const float*
                   long long dx_stride, void* dx_bf16, long long dxb_stride, float* dw, float* db, long long rows, int D,
                   float eps, cudaStream_t stream);
 int attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, const float* lse, void* dqkv,
-                  float* dkv_aux, float* scratch, int B, int T, int N0, int G, int H, int n_q, cudaStream_t stream);
+                  float* dkv_aux, float* scratch, int B, int T, int N0, int G, int H, int n_q, int key_groups, cudaStream_t stream);
 int temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int B, int T, int H, cudaStream_t stream);
 int causal_attention_bwd(const float* qkv, const void* dout, void* dqkv, int n_seq, int L, int H, cudaStream_t stream);
 int prompt_rows_bwd(const void* d_rows_n, const float* global_prompts, const float* local_prompts,

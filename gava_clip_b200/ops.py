@@ -417,7 +417,7 @@ def layernorm_bwd(dy: Tensor, x: Tensor, weight: Tensor, dx_out: Tensor, *, rows
 
 
 def attention_train(qkv: Tensor, kv_aux: Tensor, out: Tensor, lse: Tensor, *, B: int, T: int, N0: int, G: int,
-                    H: int, n_q: Optional[int] = None) -> Tensor:
+                    H: int, n_q: Optional[int] = None, key_groups: int = 3) -> Tensor:
     """attention() over all query rows that also saves the per-row log-sum-exp (f32 [B*T, H, N0]) for attention_bwd."""
     _req(qkv, torch.bfloat16, "attention qkv"); _req(kv_aux, torch.bfloat16, "attention kv_aux")
     _req(out, torch.bfloat16, "attention out"); _req(lse, torch.float32, "attention lse")
@@ -426,14 +426,14 @@ def attention_train(qkv: Tensor, kv_aux: Tensor, out: Tensor, lse: Tensor, *, B:
     assert qkv.shape == (B * T * N0, 3 * D) and kv_aux.shape == (G + 2 * B * T, 2 * D) and out.shape == (B * T * N0, D)
     assert lse.numel() == B * T * H * N0
     rc = _lib.load().gava_attention_train_fwd(qkv.data_ptr(), kv_aux.data_ptr(), out.data_ptr(), lse.data_ptr(), B, T, N0, G,
-                                              H, N0 if n_q is None else n_q, _stream())
+                                              H, N0 if n_q is None else n_q, key_groups, _stream())
     _lib.check(rc, "gava_attention_train_fwd")
     return out
 
 
 def attention_bwd(qkv: Tensor, kv_aux: Tensor, out: Tensor, dout: Tensor, dqkv: Tensor, dkv_aux: Tensor, *, B: int,
                   T: int, N0: int, G: int, H: int, lse: Optional[Tensor] = None, n_q: Optional[int] = None,
-                  scratch: Optional[Tensor] = None) -> None:
+                  scratch: Optional[Tensor] = None, key_groups: int = 3) -> None:
     for t in (qkv, kv_aux, out, dout, dqkv):
         _req(t, torch.bfloat16, "attention_bwd"); assert t.is_contiguous()
     _req(dkv_aux, torch.float32, "attention_bwd dkv_aux")
@@ -448,7 +448,7 @@ def attention_bwd(qkv: Tensor, kv_aux: Tensor, out: Tensor, dout: Tensor, dqkv: 
         assert scratch.is_contiguous() and scratch.numel() >= B * T * H * (G + T + 1) * 128
     rc = _lib.load().gava_attention_bwd(qkv.data_ptr(), kv_aux.data_ptr(), out.data_ptr(), dout.data_ptr(), _ptr(lse),
                                         dqkv.data_ptr(), dkv_aux.data_ptr(), _ptr(scratch), B, T, N0, G, H,
-                                        N0 if n_q is None else n_q, _stream())
+                                        N0 if n_q is None else n_q, key_groups, _stream())
     _lib.check(rc, "gava_attention_bwd")
 
 

@@ -54,31 +54,35 @@ class TowerTrainer(TowerEngine):
         e, dev = self.enc, self.device
         D, L, G, T = e.feature_dim, len(e.blocks), e.num_global_prompts, e.num_frames
         layout: List[Tuple[str, Tuple[int, ...]]] = [("time_embed", (T, D)), ("global_prompts", (L, G, D))]
+        bounds: List[Tuple[int, int]] = []             # [start, end) of each layer's entries in `layout`
         for i in range(L):
             k = f"blocks.{i}."
-            layout += [(k + "local_prompts", (1, T, D)), (k + "summary_ln.weight", (D,)), (k + "summary_ln.bias", (D,)),
-                       (k + "sqkv.weight", (3 * D, D)), (k + "sqkv.bias", (3 * D,)),
-                       (k + "summary_attn_layer.out_proj.weight", (D, D)), (k + "summary_attn_layer.out_proj.bias", (D,))]
-        total = sum(int(torch.Size(s).numel()) for _, s in layout)
-        self.grad_flat = torch.zeros(total, device=dev, dtype=torch.float32)
+            first = len(layout)
+            if e.use_local_prompts:                    # utils.py:137-139
+                layout += [(k + "local_prompts", (1, T, D))]
+            if e.use_summary_token:                    # utils.py:129-134
+                layout += [(k + "summary_ln.weight", (D,)), (k + "summary_ln.bias", (D,)),
+                           (k + "sqkv.weight", (3 * D, D)), (k + "sqkv.bias", (3 * D,)),
+                           (k + "summary_attn_layer.out_proj.weight", (D, D)), (k + "summary_attn_layer.out_proj.bias", (D,))]
+            bounds.append((first, len(layout)))
+        sizes = [int(torch.Size(s).numel()) for _, s in layout]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + n)
+        self.grad_flat = torch.zeros(max(offs[-1], 1), device=dev, dtype=torch.float32)
         self.grads: Dict[str, Tensor] = {}
-        self.layer_slices: List[Tensor] = []          # contiguous per-layer ranges of grad_flat (all-reduce units)
-        off = 0
-        for name, shape in layout:
-            n = int(torch.Size(shape).numel())
+        for (name, shape), off, n in zip(layout, offs, sizes):
             self.grads[name] = self.grad_flat[off: off + n].view(shape)
-            if name.endswith("local_prompts"):
-                lo = off
-            if name.endswith("out_proj.bias"):
-                self.layer_slices.append(self.grad_flat[lo: off + n])
-            off += n
+        # contiguous per-layer ranges of grad_flat (all-reduce units; empty when the layer has no trainable tensor)
+        self.layer_slices: List[Tensor] = [self.grad_flat[offs[a]: offs[b]] for a, b in bounds]
         self.head_slice = self.grad_flat[: T * D + L * G * D]       # time_embed + global_prompts
-        for i in range(L):       # per-parameter views of the fused q|k|v blocks
-            k = f"blocks.{i}."
-            w, b = self.grads[k + "sqkv.weight"], self.grads[k + "sqkv.bias"]
-            for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
-                self.grads[k + f"summary_attn_layer.{nm}.weight"] = w[j * D:(j + 1) * D]
-                self.grads[k + f"summary_attn_layer.{nm}.bias"] = b[j * D:(j + 1) * D]
+        if e.use_summary_token:
+            for i in range(L):       # per-parameter views of the fused q|k|v blocks
+                k = f"blocks.{i}."
+                w, b = self.grads[k + "sqkv.weight"], self.grads[k + "sqkv.bias"]
+                for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
+                    self.grads[k + f"summary_attn_layer.{nm}.weight"] = w[j * D:(j + 1) * D]
+                    self.grads[k + f"summary_attn_layer.{nm}.bias"] = b[j * D:(j + 1) * D]
 
     def grad_of(self, name: str) -> Tensor:
         return self.grads[name]
@@ -111,7 +115,8 @@ class TowerTrainer(TowerEngine):
         for i in range(len(e.blocks)):
             k = f"b{i}."
             for nm in ("qkv", "out", "fc1", "fc2", "cls", "sqkv", "sout"):
-                put_t(k + nm + ".wT", P[k + nm + ".w"])
+                if k + nm + ".w" in P:          # cls / sqkv / sout exist only with the prompt groups that use them
+                    put_t(k + nm + ".wT", P[k + nm + ".w"])
 
     # ------------------------------------------------------------------ tape + scratch
     def train_ws(self, B: int, T: int) -> Dict[str, object]:
@@ -155,6 +160,15 @@ class TowerTrainer(TowerEngine):
             "dxc2": z(BT, D, dt=f32), "dxc2_bf": z(BT, D, dt=bf), "d_sum_ext": z(BT, D, dt=f32),
         }
         W["gx0"] = W["g4"].view(-1)[: 2 * M * D].view(torch.float32).view(M, D)     # tail scratch: g4 is dead by then
+        # inputs of the prompt-row kernels that a disabled prompt group never produces (finite values; the rows are masked)
+        if not e.use_local_prompts:
+            W["zero_local"] = torch.zeros(1, T, D, device=dev, dtype=f32)
+        if not e.use_summary_token:
+            for t in W["summary"]:
+                t.zero_()
+            if not e.use_local_prompts:
+                for t in W["cls_proj"]:
+                    t.zero_()
         self.ws[key] = W
         return W
 
@@ -176,7 +190,7 @@ class TowerTrainer(TowerEngine):
             n0 = ops.launch_count()
             self._forward_train_body(video, W)
             self.launches_last_call = ops.launch_count() - n0
-            return W["frame_feat"], W["summary"][L - 1]
+            return W["frame_feat"], (W["summary"][L - 1] if self.enc.use_summary_token else None)
         key = ("fwd", tuple(video.shape), video.dtype)
         ent = self._train_graphs(W).get(key)
         if ent is None:
@@ -195,7 +209,7 @@ class TowerTrainer(TowerEngine):
             static_in.copy_(video)
         g.replay()
         self.launches_last_call = n_launch
-        return W["frame_feat"], W["summary"][L - 1]
+        return W["frame_feat"], (W["summary"][L - 1] if self.enc.use_summary_token else None)
 
     def train_input_buffer(self, shape, dtype=torch.float32) -> Optional[Tensor]:
         """Static clip buffer of the captured training forward for this shape (None before the first step): a caller that
@@ -241,6 +255,7 @@ class TowerTrainer(TowerEngine):
         main = torch.cuda.current_stream(self.device)
         side = self.side_stream if self.overlap_chain else None
         cap = self.qkv_ctas if side is not None else 0
+        kg = (1 if e.use_local_prompts else 0) | (2 if e.use_summary_token else 0)      # prompt groups among the keys
         for i in range(L):
             k = f"b{i}."
             xin = W["x_in"][i]
@@ -253,14 +268,17 @@ class TowerTrainer(TowerEngine):
                 ev_x.record(main)
                 side.wait_event(ev_x)
             with torch.cuda.stream(side if side is not None else main):
-                ops.layernorm(xin, None, None, W["cls_bf2"], rows=BT, in_row_stride=N0 * D)
-                ops.gemm(W["cls_bf2"], P[k + "cls.w"], cp, mode=ops.EPI_BIAS_F32, bias=P[k + "cls.b"])
-                ops.layernorm(cp, P[k + "summary_ln.w"], P[k + "summary_ln.b"], W["sum_n"][i], rows=BT, in_row_stride=D)
-                ops.gemm(W["sum_n"][i], P[k + "sqkv.w"], W["sqkv"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "sqkv.b"])
-                ops.temporal_attention(W["sqkv"][i], W["smix"][i], B, T, H)
-                ops.gemm(W["smix"][i], P[k + "sout.w"], sm, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "sout.b"], resid=cp)
-                ops.prompt_rows(P["global_prompts"][i], P[k + "local"], cp, sm, P[k + "norm1.w"], P[k + "norm1.b"], W["aux_n"],
-                                B, T, LN_EPS)
+                if e.use_summary_token or e.use_local_prompts:                               # utils.py:160-165
+                    ops.layernorm(xin, None, None, W["cls_bf2"], rows=BT, in_row_stride=N0 * D)
+                    ops.gemm(W["cls_bf2"], P[k + "cls.w"], cp, mode=ops.EPI_BIAS_F32, bias=P[k + "cls.b"])
+                if e.use_summary_token:                                                      # utils.py:168-172
+                    ops.layernorm(cp, P[k + "summary_ln.w"], P[k + "summary_ln.b"], W["sum_n"][i], rows=BT, in_row_stride=D)
+                    ops.gemm(W["sum_n"][i], P[k + "sqkv.w"], W["sqkv"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "sqkv.b"])
+                    ops.temporal_attention(W["sqkv"][i], W["smix"][i], B, T, H)
+                    ops.gemm(W["smix"][i], P[k + "sout.w"], sm, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "sout.b"], resid=cp)
+                # rows of a disabled prompt group are built from zeros and masked out by the attention kernels (key_groups)
+                ops.prompt_rows(P["global_prompts"][i], P[k + "local"] if e.use_local_prompts else W["zero_local"], cp, sm,
+                                P[k + "norm1.w"], P[k + "norm1.b"], W["aux_n"], B, T, LN_EPS)
                 ops.gemm(W["aux_n"], P[k + "qkv.w"][D:], W["kvaux"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"][D:])
                 if side is not None:
                     ev_kv = torch.cuda.Event()
@@ -278,7 +296,7 @@ class TowerTrainer(TowerEngine):
                          bias=P[k + "qkv.b"][:D])
                 if side is not None:
                     main.wait_event(ev_kv)
-                ops.attention_train(qkv, W["kvaux"][i], W["o"][i], W["lse"][i], B=B, T=T, N0=N0, G=G, H=H, n_q=1)
+                ops.attention_train(qkv, W["kvaux"][i], W["o"][i], W["lse"][i], B=B, T=T, N0=N0, G=G, H=H, n_q=1, key_groups=kg)
                 ops.gemm(W["o"][i].view(BT, N0 * D)[:, :D], P[k + "out.w"], W["xc_mid"], mode=ops.EPI_BIAS_RESID_F32,
                          bias=P[k + "out.b"], resid=xin.view(BT, N0 * D)[:, :D])
                 ops.layernorm(W["xc_mid"], P[k + "norm2.w"], P[k + "norm2.b"], W["cls_bf"], rows=BT, in_row_stride=D)
@@ -290,7 +308,7 @@ class TowerTrainer(TowerEngine):
             ops.gemm(xn, P[k + "qkv.w"], W["qkv"][i], mode=ops.EPI_BIAS_BF16, bias=P[k + "qkv.b"], max_ctas=cap)
             if side is not None:
                 main.wait_event(ev_kv)
-            ops.attention_train(W["qkv"][i], W["kvaux"][i], W["o"][i], W["lse"][i], B=B, T=T, N0=N0, G=G, H=H)
+            ops.attention_train(W["qkv"][i], W["kvaux"][i], W["o"][i], W["lse"][i], B=B, T=T, N0=N0, G=G, H=H, key_groups=kg)
             ops.gemm(W["o"][i], P[k + "out.w"], xmid, mode=ops.EPI_BIAS_RESID_F32, bias=P[k + "out.b"], resid=xin)
             # x = x + fc2(QuickGELU(fc1(norm2(x))))   (utils.py:199); the pre-activations stay for the DGELU epilogue
             ops.layernorm(xmid, P[k + "norm2.w"], P[k + "norm2.b"], xn, rows=M, in_row_stride=D)
@@ -378,7 +396,8 @@ class TowerTrainer(TowerEngine):
                         self._bwd_head(W, B, T, have_ff)
                     self._bwd_layer(W, B, T, i, have_ext)
                 run_segment(f"layer{i}", seg)
-                pending.append(hook(self.layer_slices[i]))   # this layer's gradients are final: start their all-reduce now
+                if self.layer_slices[i].numel():
+                    pending.append(hook(self.layer_slices[i]))   # this layer's gradients are final: start their all-reduce now
             run_segment("tail", lambda: self._bwd_tail(W, B, T))
             pending.append(hook(self.head_slice))
             for h in pending:           # stream-level wait: autograd adds these buffers into the parameters' .grad next
@@ -410,6 +429,7 @@ class TowerTrainer(TowerEngine):
         dx, dxb, gD = W["dx"], W["dxb"], W["gD"]
         dx_cls = dx.view(BT, N0 * D)[:, :D]
         ext = W["d_sum_ext"] if have_ext else None
+        kg = (1 if e.use_local_prompts else 0) | (2 if e.use_summary_token else 0)
         k, kb = f"b{i}.", f"blocks.{i}."
         cp, sm = W["cls_proj"][i], W["summary"][i]
         if i == L - 1:
@@ -423,7 +443,7 @@ class TowerTrainer(TowerEngine):
             ops.gemm(W["dxc2_bf"], P[k + "out.wT"], gD.view(BT, N0 * D)[:, :D], mode=ops.EPI_BIAS_BF16)   # dO, cls rows of gD
             W["dqkv"].view(BT * N0, 3, D)[:, 0].zero_()                          # dq of the rows without a query
             ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G,
-                              H=H, lse=W["lse"][i], n_q=1, scratch=W["dkv_slots"])
+                              H=H, lse=W["lse"][i], n_q=1, scratch=W["dkv_slots"], key_groups=kg)
         else:
             # ---- MLP: dx += dLN2( (dx W2 * g'(a1)) W1 )
             ops.gemm(dxb, P[k + "fc2.wT"], W["g4"], mode=ops.EPI_DGELU_BF16, aux=W["a1"][i])
@@ -432,7 +452,7 @@ class TowerTrainer(TowerEngine):
             # ---- attention: dO = dx Wo; (dq, dk, dv, d kv_aux); dx += dLN1(dqkv Wqkv)
             ops.gemm(dxb, P[k + "out.wT"], gD, mode=ops.EPI_BIAS_BF16)
             ops.attention_bwd(W["qkv"][i], W["kvaux"][i], W["o"][i], gD, W["dqkv"], W["dkvaux"], B=B, T=T, N0=N0, G=G,
-                              H=H, lse=W["lse"][i], scratch=W["dkv_slots"])
+                              H=H, lse=W["lse"][i], scratch=W["dkv_slots"], key_groups=kg)
         # The K/V-only prompt rows' backward (~20 latency-bound launches on G + 2 BT rows, everything from d kv_aux down to
         # d cls_proj and the layer's parameter gradients) depends only on the attention backward's d kv_aux and touches none
         # of the stream's buffers: it runs on the side stream next to the qkv^T dgrad GEMM (grid capped, as in the forward)
@@ -449,22 +469,29 @@ class TowerTrainer(TowerEngine):
             # ---- K/V-only prompt rows: d kv_aux -> normalised rows -> global / local / summary / cls_proj gradients
             ops.layernorm(W["dkvaux"].view(2 * R, D), None, None, W["dkvaux_bf"].view(2 * R, D), rows=2 * R, in_row_stride=D)
             ops.gemm(W["dkvaux_bf"], P[k + "qkv.wT"][:, D:], W["daux_n"], mode=ops.EPI_BIAS_BF16)
-            ops.prompt_rows_bwd(W["daux_n"], P["global_prompts"][i], P[k + "local"], cp, sm, P[k + "norm1.w"],
-                                g["global_prompts"][i], W["d_lcp"], W["d_sum"], ext if i == L - 1 else None, B, T, LN_EPS)
-            ops.group_sum(W["d_lcp"], g[kb + "local_prompts"], outer=B, J=T, inner=1)
-            # ---- summary = cls_proj + out_proj(temporal_attention(qkv(summary_ln(cls_proj))))   (utils.py:168-170)
-            ops.layernorm(W["d_sum"], None, None, W["d_sum_bf"], rows=BT, in_row_stride=D)     # cast
-            ops.gemm(W["d_sum_bf"], P[k + "sout.wT"], W["dsmix"], mode=ops.EPI_BIAS_BF16)
-            self._wgrad(W, W["d_sum"], W["smix"][i], g[kb + "summary_attn_layer.out_proj.weight"])
-            ops.group_sum(W["d_sum"], g[kb + "summary_attn_layer.out_proj.bias"], outer=BT, J=1, inner=1)
-            ops.temporal_attention_bwd(W["sqkv"][i], W["dsmix"], W["dsqkv"], B, T, H)
-            ops.gemm(W["dsqkv"], P[k + "sqkv.wT"], W["dsn"], mode=ops.EPI_BIAS_BF16)
-            self._wgrad(W, W["dsqkv"], W["sum_n"][i], g[kb + "sqkv.weight"])
-            ops.group_sum(W["dsqkv"], g[kb + "sqkv.bias"], outer=BT, J=1, inner=1)
-            g[kb + "summary_ln.weight"].zero_(); g[kb + "summary_ln.bias"].zero_()
-            ops.layernorm_bwd(W["dsn"], cp, P[k + "summary_ln.w"], W["d_cp"], rows=BT, D=D, add1=W["d_lcp"],
-                              add2=W["d_sum"], dx_bf16=W["d_cp_bf"], dw=g[kb + "summary_ln.weight"],
-                              db=g[kb + "summary_ln.bias"])
+            # (rows of a disabled prompt group had zero probability: their d kv_aux, hence d_lcp / d_sum, are exact zeros)
+            ops.prompt_rows_bwd(W["daux_n"], P["global_prompts"][i], P[k + "local"] if e.use_local_prompts else W["zero_local"],
+                                cp, sm, P[k + "norm1.w"], g["global_prompts"][i], W["d_lcp"], W["d_sum"],
+                                ext if (i == L - 1 and e.use_summary_token) else None, B, T, LN_EPS)
+            if e.use_local_prompts:
+                ops.group_sum(W["d_lcp"], g[kb + "local_prompts"], outer=B, J=T, inner=1)
+            if e.use_summary_token:
+                # ---- summary = cls_proj + out_proj(temporal_attention(qkv(summary_ln(cls_proj))))   (utils.py:168-170)
+                ops.layernorm(W["d_sum"], None, None, W["d_sum_bf"], rows=BT, in_row_stride=D)     # cast
+                ops.gemm(W["d_sum_bf"], P[k + "sout.wT"], W["dsmix"], mode=ops.EPI_BIAS_BF16)
+                self._wgrad(W, W["d_sum"], W["smix"][i], g[kb + "summary_attn_layer.out_proj.weight"])
+                ops.group_sum(W["d_sum"], g[kb + "summary_attn_layer.out_proj.bias"], outer=BT, J=1, inner=1)
+                ops.temporal_attention_bwd(W["sqkv"][i], W["dsmix"], W["dsqkv"], B, T, H)
+                ops.gemm(W["dsqkv"], P[k + "sqkv.wT"], W["dsn"], mode=ops.EPI_BIAS_BF16)
+                self._wgrad(W, W["dsqkv"], W["sum_n"][i], g[kb + "sqkv.weight"])
+                ops.group_sum(W["dsqkv"], g[kb + "sqkv.bias"], outer=BT, J=1, inner=1)
+                g[kb + "summary_ln.weight"].zero_(); g[kb + "summary_ln.bias"].zero_()
+                ops.layernorm_bwd(W["dsn"], cp, P[k + "summary_ln.w"], W["d_cp"], rows=BT, D=D, add1=W["d_lcp"],
+                                  add2=W["d_sum"], dx_bf16=W["d_cp_bf"], dw=g[kb + "summary_ln.weight"],
+                                  db=g[kb + "summary_ln.bias"])
+            elif e.use_local_prompts:
+                # cls_proj feeds the local rows only (utils.py:176-180): d cls_proj = d(local + cls_proj rows)
+                ops.layernorm(W["d_lcp"], None, None, W["d_cp_bf"], rows=BT, in_row_stride=D)      # cast
             if side is not None:
                 ev_b = torch.cuda.Event()
                 ev_b.record(side)
@@ -472,7 +499,8 @@ class TowerTrainer(TowerEngine):
             main.wait_event(ev_b)
         # ---- cls_proj (frozen): dx[cls rows] += d_cp Wc; then refresh the bf16 copy of dx's cls rows (the LayerNorm-
         # backward kernels keep the other rows of dxb current as a by-product)
-        ops.gemm(W["d_cp_bf"], P[k + "cls.wT"], dx_cls, mode=ops.EPI_BIAS_RESID_F32, resid=dx_cls)
+        if e.use_summary_token or e.use_local_prompts:
+            ops.gemm(W["d_cp_bf"], P[k + "cls.wT"], dx_cls, mode=ops.EPI_BIAS_RESID_F32, resid=dx_cls)
         ops.layernorm(dx, None, None, dxb, rows=BT, in_row_stride=N0 * D, out_row_stride=N0 * D)
 
     def _bwd_tail(self, W: Dict[str, object], B: int, T: int) -> None:
@@ -505,7 +533,7 @@ class TowerFunction(torch.autograd.Function):
         ctx.generation = trainer.tape_generation
         ctx.names = [n for n, _ in trainer.trainable_named()]
         # clones: the workspace is overwritten by the next forward while autograd may still hold these outputs
-        return ff[:, :E].clone(), st.clone()
+        return ff[:, :E].clone(), (st.clone() if st is not None else None)      # no summary token: (frame_feat, None)
 
     @staticmethod
     def backward(ctx, d_ff: Optional[Tensor], d_st: Optional[Tensor]):

@@ -758,9 +758,6 @@ class CLIPVisionEncoder(nn.Module):
         eng = self.engine(x.device)
         B, T, _, _ = _clip_dims(x)
         if self._wants_grad():
-            if not (self.use_summary_token and self.use_local_prompts):
-                raise NotImplementedError("the fine-tune step (tape + backward kernels) covers the summary+local+global prompt "
-                                          "configuration of the shipped recipes; inference runs every combination")
             if self.precision == "fp32":
                 raise NotImplementedError("the fine-tune step runs in the bf16 path (set precision='bf16')")
             from .train_engine import TowerFunction

@@ -238,7 +238,7 @@ int gava_layernorm_bwd(const void* dy, int64_t dy_stride, int32_t dy_bf16, const
 /* gava_attention_fwd for the training forward: additionally writes lse f32 [B*T, H, N0] (rows < n_q) = the log2-domain
  * log-sum-exp of every query row's scaled scores (log2(sum_k 2^(s_k log2 e / 8))), saved for gava_attention_bwd. */
 int gava_attention_train_fwd(const void* qkv, const void* kv_aux, void* out, float* lse, int32_t B, int32_t T, int32_t N0,
-                             int32_t G, int32_t H, int32_t n_q, void* stream);
+                             int32_t G, int32_t H, int32_t n_q, int32_t key_groups, void* stream);
 
 /* Backward of gava_attention_fwd for the first n_q query rows of every frame (n_q = N0, or 1 in the last layer where only
  * the cls row reaches the output: dq is then written for that row only, dk/dv still cover every key).
@@ -247,10 +247,12 @@ int gava_attention_train_fwd(const void* qkv, const void* kv_aux, void* out, flo
  * dqkv: bf16 [B*T*N0, 3D] = [dq | dk | dv] of the live rows; dkv_aux: f32 [G + 2*B*T, 2D] = [dk | dv] of the K/V-only rows
  * (global rows collect all frames, local rows the T frames of a video).  scratch: f32 [B*T, H, G+T+1, 128] workspace: every
  * (frame, head) writes its prompt-row contributions to its own slot and a second kernel sums the slots in a fixed order
- * (reproducible); scratch == NULL: f32 atomics straight into dkv_aux (order-dependent rounding). */
+ * (reproducible); scratch == NULL: f32 atomics straight into dkv_aux (order-dependent rounding).
+ * key_groups as in gava_attention_fwd (the value the forward ran with): keys of a disabled prompt group have zero
+ * probability, so their dk / dv rows come out as exact zeros. */
 int gava_attention_bwd(const void* qkv, const void* kv_aux, const void* out, const void* dout, const float* lse,
                        void* dqkv, float* dkv_aux, float* scratch, int32_t B, int32_t T, int32_t N0, int32_t G, int32_t H,
-                       int32_t n_q, void* stream);
+                       int32_t n_q, int32_t key_groups, void* stream);
 
 /* Backward of gava_temporal_attention_fwd: qkv bf16 [B*T, 3D], dout bf16 [B*T, D] -> dqkv bf16 [B*T, 3D].  T <= 128. */
 int gava_temporal_attention_bwd(const void* qkv, const void* dout, void* dqkv, int32_t B, int32_t T, int32_t H,

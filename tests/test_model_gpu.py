@@ -374,7 +374,8 @@ def _oracle_grads(name, video, labels, trainable):
     for k in trainable:
         sd[k].requires_grad_(True)
     v, _ = vo.vision_encoder(sd, video, num_frames=kw["num_frames"], num_heads=kw.get("num_heads", 12),
-                             num_layers=kw.get("num_layers", 12))
+                             num_layers=kw.get("num_layers", 12), use_summary=kw.get("use_summary_token", False),
+                             use_local=kw.get("use_local_prompts", False))
     prompts = vo.assemble_prompts(sd, cpu.tokenized_prompts, 8, kapt=False)
     tfs = [vo.text_encoder(sd, p, t, heads=kw.get("text_transformer_heads", 8), layers=kw.get("text_transformer_layers", 12))
            for p, t in zip(prompts, cpu.tokenized_prompts)]
@@ -388,11 +389,12 @@ def _cos(a, b):
     return float(a @ b / (a.norm() * b.norm()).clamp_min(1e-300))
 
 
-@pytest.mark.parametrize("name", ["tiny", "b16_t8"])
+@pytest.mark.parametrize("name", ["tiny", "b16_t8", "tiny_global_only", "tiny_no_local", "tiny_no_summary"])
 def test_finetune_gradients_match_oracle(cuda, name):
     """Fine-tune step: forward with tape + backward kernels through the frozen backbone.  Gradients of every
     trainable tensor of the reference recipe (visual prompts / summary attention / time_embed via the sm_100a backward,
-    class context / logit_scale via autograd on the text side) against fp32 CPU autograd through the oracle."""
+    class context / logit_scale via autograd on the text side) against fp32 CPU autograd through the oracle.  The partial
+    prompt-flag configurations (utils.py:160-197) train the tensors they have: masked keys get exactly zero gradient."""
     import torch.nn.functional as Fn
     model, kw, B = build_model(name, device=cuda)
     video = fx.make_inputs(name)["video"]
