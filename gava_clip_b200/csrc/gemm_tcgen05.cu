@@ -87,6 +87,22 @@ __device__ __forceinline__ uint32_t dgelu_mul2(uint32_t dy2, uint32_t a2) {
 // store loop (producer).
 struct FoldRow { float rstd, nmr; const float* colsum_s; };
 
+// Epilogue output stores.  GAVA_EPI_STCS=1 (experiment build): streaming (evict-first) stores, on the theory that outputs
+// far larger than L2 need not displace the operand tiles the mainloop re-reads.  Measured (tools/gemm_epi_bench.py,
+// profiles/r02_gemm_epilogue_cost.txt): no change for the bf16 epilogues, the in-place fp32 stream update of fc2 615 vs
+// 398 us, the whole step 3314 vs 3549 clips/s -- plain stores stay.
+#ifndef GAVA_EPI_STCS
+#define GAVA_EPI_STCS 0
+#endif
+template <typename T>
+__device__ __forceinline__ void epi_store(T* ptr, const T& v) {
+#if GAVA_EPI_STCS
+  __stcs(ptr, v);
+#else
+  *ptr = v;
+#endif
+}
+
 template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage, int row0, int col0,
                                                const uint32_t (&v)[32], const float4 (&resid)[8], const float* bias_s,
@@ -150,7 +166,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
           const uint4 a1 = auxv[i];
           w.x = dgelu_mul2(w.x, a1.x); w.y = dgelu_mul2(w.y, a1.y); w.z = dgelu_mul2(w.z, a1.z); w.w = dgelu_mul2(w.w, a1.w);
         }
-        if (row0 + r < p.M) *reinterpret_cast<uint4*>(obase + (long long)(row0 + r) * ld) = w;
+        if (row0 + r < p.M) epi_store(reinterpret_cast<uint4*>(obase + (long long)(row0 + r) * ld), w);
       }
       __syncwarp();
     };
@@ -180,11 +196,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
       if (grow < p.M) {
         if constexpr (MODE == EPI_BIAS_RESID_F32 || MODE == EPI_BIAS_RESID_STATS_F32) {
           a.x += resid[i].x; a.y += resid[i].y; a.z += resid[i].z; a.w += resid[i].w;
-          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)grow * p.ldo + col) = a;
+          epi_store(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)grow * p.ldo + col), a);
           if constexpr (MODE == EPI_BIAS_RESID_STATS_F32) {
             // the next LayerNorm's operand (raw bf16 copy) and its row statistics, from the values still in registers
-            *reinterpret_cast<uint2*>(p.copy_out + (long long)grow * p.ld_copy + col) =
-                make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+            epi_store(reinterpret_cast<uint2*>(p.copy_out + (long long)grow * p.ld_copy + col),
+                      make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w)));
             rs[i] += (a.x + a.y) + (a.z + a.w);
             rq[i] = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, rq[i]))));
           }
