@@ -67,6 +67,7 @@ struct GemmArgs {
   const float* colsum;       // [N]
   int n_slots;
   float eps;
+  int tma_out;               // bf16 output of modes 0 / 1 / 7 leaves through TMA stores of the swizzled staging tile
 };
 
 // ---- epilogue: TMEM -> registers (one row per thread) -> swizzled smem staging -> transposed, coalesced global access.
@@ -107,7 +108,7 @@ template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage, int row0, int col0,
                                                const uint32_t (&v)[32], const float4 (&resid)[8], const float* bias_s,
                                                int lane, const FoldRow& fold, float (&rs)[8], float (&rq)[8],
-                                               const uint4 (&auxv)[4]) {
+                                               const uint4 (&auxv)[4], const CUtensorMap* tmap_out, int parity) {
   if constexpr (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16 || MODE == EPI_DGELU_BF16 || MODE == EPI_LNFOLD_BF16) {
     float acc[32];
     {  // bias of this chunk from shared memory (staged per tile before the accumulator wait; broadcast LDS.128)
@@ -145,7 +146,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
       }
     }
     // stage as bf16 (row pitch 64 B = 4 chunks of 16 B, chunk' = chunk ^ ((row >> 1) & 3)), then store transposed
-    auto stage_store = [&](const float (&a)[32], __nv_bfloat16* base, long long ld, bool dgelu) {
+    auto stage_store = [&](const float (&a)[32], __nv_bfloat16* base, long long ld, bool dgelu, bool tma) {
+      // TMA drain: the 32 x 32 bf16 block is staged exactly as below (64-byte rows, 16-byte chunk index XOR (row >> 1) & 3
+      // == CU_TENSOR_MAP_SWIZZLE_64B) in one of two 2 KB slots and leaves with ONE bulk tensor store issued by lane 0 (rows
+      // beyond M are clipped by the tensor map): no shared-memory read-back, no per-thread global stores.
+      uint8_t* slot = stage + (tma ? parity * 2048 : 0);
+      if (tma) {
+        if (lane == 0) tma_store_wait_read1();     // the store that used this slot two chunks ago has read it
+        __syncwarp();
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 w;
@@ -153,7 +162,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
         w.y = pack_bf16x2(a[8 * j + 2], a[8 * j + 3]);
         w.z = pack_bf16x2(a[8 * j + 4], a[8 * j + 5]);
         w.w = pack_bf16x2(a[8 * j + 6], a[8 * j + 7]);
-        *reinterpret_cast<uint4*>(stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = w;
+        *reinterpret_cast<uint4*>(slot + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = w;
+      }
+      if (tma) {
+        fence_proxy_async();                       // generic-proxy smem writes -> visible to the bulk store
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tmap_out, slot, col0, row0);
+          tma_store_commit();
+        }
+        return;
       }
       __syncwarp();
       const int c = lane & 3;
@@ -171,11 +189,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
       __syncwarp();
     };
     if constexpr (MODE == EPI_BIAS_GELU_BF16) {
-      if (p.aux_out != nullptr) stage_store(acc, p.aux_out, p.ld_aux, false);   // training forward keeps the pre-activations
+      if (p.aux_out != nullptr) stage_store(acc, p.aux_out, p.ld_aux, false, false);   // training forward keeps the pre-activations
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = quick_gelu(acc[j]);
     }
-    stage_store(acc, reinterpret_cast<__nv_bfloat16*>(p.out), p.ldo, MODE == EPI_DGELU_BF16);
+    stage_store(acc, reinterpret_cast<__nv_bfloat16*>(p.out), p.ldo, MODE == EPI_DGELU_BF16,
+                MODE != EPI_DGELU_BF16 && p.tma_out != 0);
   } else {
     // stage raw fp32 accumulators: row pitch 128 B (8 chunks of 16 B), chunk' = chunk ^ (row & 7)
 #pragma unroll
@@ -226,7 +245,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
 template <int MODE, int NCH>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage, float* bias_s, uint64_t* tmem_full_bar,
                                               uint32_t full_phase, uint32_t t_addr, int row0, int col_base, int lane,
-                                              long long& dbg_wait) {
+                                              long long& dbg_wait, const CUtensorMap* tmap_out) {
   FoldRow fold;
   fold.rstd = 1.f; fold.nmr = 0.f; fold.colsum_s = nullptr;
   float rs[8], rq[8];
@@ -295,7 +314,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage,
       FoldRow fc = fold;
       if constexpr (MODE == EPI_LNFOLD_BF16) fc.colsum_s = fold.colsum_s ? fold.colsum_s + cc * 32 : nullptr;
       epilogue_chunk<MODE>(p, stage, row0, col_base + cc * 32, cur, resid, bias_s + cc * 32, lane, fc, rs, rq,
-                           aux_all[MODE == EPI_DGELU_BF16 ? cc : 0]);
+                           aux_all[MODE == EPI_DGELU_BF16 ? cc : 0], tmap_out, cc & 1);
 #endif
     }
   } else {
@@ -340,7 +359,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage,
       if (v[0] == 0x7fc12345u && resid[0].x == 1.2345f) reinterpret_cast<uint32_t*>(p.out)[0] = v[3];
 #elif GAVA_GEMM_DEBUG != 1
       const uint4 no_aux[4] = {};
-      epilogue_chunk<MODE>(p, stage, row0, col0, v, resid, nullptr, lane, fold, rs, rq, no_aux);
+      epilogue_chunk<MODE>(p, stage, row0, col0, v, resid, nullptr, lane, fold, rs, rq, no_aux, tmap_out, 0);
 #endif
     }
     if constexpr (MODE == EPI_BIAS_RESID_STATS_F32) {
@@ -364,7 +383,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage,
 template <int BN, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmArgs p) {
+                    const __grid_constant__ CUtensorMap tmap_out, const GemmArgs p) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128-byte-swizzle tiles need 1024-byte alignment
@@ -472,11 +491,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int col_base = n_blk * BN + half * kChunksPerWarp * 32;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * kChunksPerWarp * 32);
       epilogue_tile<MODE, kChunksPerWarp>(p, stage, smem_bias + acc * BN + half * kChunksPerWarp * 32, &tmem_full[acc],
-                                          acc_phase, t_addr, row0, col_base, lane, g_dbg_wait);
+                                          acc_phase, t_addr, row0, col_base, lane, g_dbg_wait, &tmap_out);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (p.tma_out && lane == 0) tma_store_wait_all();   // bulk stores of the staging slots have completed
   }
 
   tc_fence_before();
@@ -505,7 +525,7 @@ struct Gemm2Cfg {
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const GemmArgs p) {
+                     const __grid_constant__ CUtensorMap tmap_out, const GemmArgs p) {
   using Cfg = Gemm2Cfg;
   constexpr int kStages = Cfg::kStages;
   constexpr int BN = Cfg::BN;
@@ -654,12 +674,13 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const int col_base = n_blk * BN + half * kChunksPerWarp * 32;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * kChunksPerWarp * 32);
       epilogue_tile<MODE, kChunksPerWarp>(p, stage, smem_bias + acc * BN + half * kChunksPerWarp * 32, &tmem_full[acc],
-                                          acc_phase, t_addr, row0, col_base, lane, g_dbg_wait);
+                                          acc_phase, t_addr, row0, col_base, lane, g_dbg_wait, &tmap_out);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // tell the leader this warp drained its part
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (p.tma_out && lane == 0) tma_store_wait_all();   // bulk stores of the staging slots have completed
 #if GAVA_GEMM_DEBUG == 4
     if ((blockIdx.x == 0 || blockIdx.x == 65) && lane == 0 && (ew == 0 || ew == 7))
       printf("[epi  cta %d warp %d] total %lld cyc, waiting tmem_full %lld\n", blockIdx.x, ew, clock64() - e_start, g_dbg_wait);
@@ -746,6 +767,29 @@ static int encode_tmap_bf16(CUtensorMap* m, const void* ptr, long long rows, lon
   return GAVA_OK;
 }
 
+// 2-D bf16 output map for the epilogue's TMA drain: box = [32 rows, 32 cols] (64-byte rows), 64-byte swizzle
+int make_tmap_bf16_out(CUtensorMap* m, const void* ptr, long long rows, long long cols, long long ld) {
+  const TmapKey key{ptr, rows, cols, ld, -2, 32};
+  TmapSlot* slot = tmap_slot(key);
+  if (slot->valid && slot->key == key) { *m = slot->map; return GAVA_OK; }
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return GAVA_ERR_DRIVER; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15u) || ((ld * 2) & 15)) {
+    set_error("TMA output must be 16-byte aligned (ptr %p, ld %lld)", ptr, ld);
+    return GAVA_ERR_ARG;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(out) failed (%d)", (int)r); return GAVA_ERR_DRIVER; }
+  slot->key = key; slot->map = *m; slot->valid = true;
+  return GAVA_OK;
+}
+
 // 3-D bf16 [planes, rows, cols] (row pitch ld, plane pitch ld_plane elements); box = [1, box_rows, 64 cols], 128B swizzle.
 // Used for TMA STORES of per-frame tiles: rows beyond `rows` are clipped instead of spilling into the next plane.
 int make_tmap_bf16_3d(CUtensorMap* m, const void* ptr, long long planes, long long rows, long long cols, long long ld,
@@ -795,7 +839,7 @@ int num_sms() {
 }
 
 template <int BN, int MODE>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmArgs& args, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set_dev[64] = {false};
   bool& attr_set = attr_set_dev[device_slot()];
@@ -807,12 +851,12 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmA
   }
   const int tiles = ((args.M + BM - 1) / BM) * (args.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, args);
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, tout, args);
   return check_launch("gemm_tcgen05");
 }
 
 template <int MODE>
-static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& args, cudaStream_t stream, int max_ctas = 0) {
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmArgs& args, cudaStream_t stream, int max_ctas = 0) {
   using Cfg = Gemm2Cfg;
   static bool attr_set_dev[64] = {false};
   bool& attr_set = attr_set_dev[device_slot()];
@@ -826,36 +870,36 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
   int max_clusters = num_sms() / 2;
   if (max_ctas > 1 && max_ctas / 2 < max_clusters) max_clusters = max_ctas / 2;   // leave SMs to a concurrent stream
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  kern<<<2 * clusters, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, args);
+  kern<<<2 * clusters, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, tout, args);
   return check_launch("gemm2_tcgen05");
 }
 
-static int dispatch_mode2(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t s, int max_ctas) {
+static int dispatch_mode2(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& a, cudaStream_t s, int max_ctas) {
   switch (mode) {
-    case EPI_BIAS_BF16: return launch_gemm2<EPI_BIAS_BF16>(ta, tb, a, s, max_ctas);
-    case EPI_BIAS_GELU_BF16: return launch_gemm2<EPI_BIAS_GELU_BF16>(ta, tb, a, s);
-    case EPI_BIAS_RESID_F32: return launch_gemm2<EPI_BIAS_RESID_F32>(ta, tb, a, s);
-    case EPI_BIAS_F32: return launch_gemm2<EPI_BIAS_F32>(ta, tb, a, s);
-    case EPI_PATCH_F32: return launch_gemm2<EPI_PATCH_F32>(ta, tb, a, s);
-    case EPI_DGELU_BF16: return launch_gemm2<EPI_DGELU_BF16>(ta, tb, a, s);
-    case EPI_LNFOLD_BF16: return launch_gemm2<EPI_LNFOLD_BF16>(ta, tb, a, s, max_ctas);
-    case EPI_BIAS_RESID_STATS_F32: return launch_gemm2<EPI_BIAS_RESID_STATS_F32>(ta, tb, a, s);
+    case EPI_BIAS_BF16: return launch_gemm2<EPI_BIAS_BF16>(ta, tb, to, a, s, max_ctas);
+    case EPI_BIAS_GELU_BF16: return launch_gemm2<EPI_BIAS_GELU_BF16>(ta, tb, to, a, s);
+    case EPI_BIAS_RESID_F32: return launch_gemm2<EPI_BIAS_RESID_F32>(ta, tb, to, a, s);
+    case EPI_BIAS_F32: return launch_gemm2<EPI_BIAS_F32>(ta, tb, to, a, s);
+    case EPI_PATCH_F32: return launch_gemm2<EPI_PATCH_F32>(ta, tb, to, a, s);
+    case EPI_DGELU_BF16: return launch_gemm2<EPI_DGELU_BF16>(ta, tb, to, a, s);
+    case EPI_LNFOLD_BF16: return launch_gemm2<EPI_LNFOLD_BF16>(ta, tb, to, a, s, max_ctas);
+    case EPI_BIAS_RESID_STATS_F32: return launch_gemm2<EPI_BIAS_RESID_STATS_F32>(ta, tb, to, a, s);
   }
   set_error("gemm: unknown epilogue mode %d", mode);
   return GAVA_ERR_ARG;
 }
 
 template <int BN>
-static int dispatch_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& a, cudaStream_t s) {
+static int dispatch_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& a, cudaStream_t s) {
   switch (mode) {
-    case EPI_BIAS_BF16: return launch_gemm<BN, EPI_BIAS_BF16>(ta, tb, a, s);
-    case EPI_BIAS_GELU_BF16: return launch_gemm<BN, EPI_BIAS_GELU_BF16>(ta, tb, a, s);
-    case EPI_BIAS_RESID_F32: return launch_gemm<BN, EPI_BIAS_RESID_F32>(ta, tb, a, s);
-    case EPI_BIAS_F32: return launch_gemm<BN, EPI_BIAS_F32>(ta, tb, a, s);
-    case EPI_PATCH_F32: return launch_gemm<BN, EPI_PATCH_F32>(ta, tb, a, s);
-    case EPI_DGELU_BF16: return launch_gemm<BN, EPI_DGELU_BF16>(ta, tb, a, s);
-    case EPI_LNFOLD_BF16: return launch_gemm<BN, EPI_LNFOLD_BF16>(ta, tb, a, s);
-    case EPI_BIAS_RESID_STATS_F32: return launch_gemm<BN, EPI_BIAS_RESID_STATS_F32>(ta, tb, a, s);
+    case EPI_BIAS_BF16: return launch_gemm<BN, EPI_BIAS_BF16>(ta, tb, to, a, s);
+    case EPI_BIAS_GELU_BF16: return launch_gemm<BN, EPI_BIAS_GELU_BF16>(ta, tb, to, a, s);
+    case EPI_BIAS_RESID_F32: return launch_gemm<BN, EPI_BIAS_RESID_F32>(ta, tb, to, a, s);
+    case EPI_BIAS_F32: return launch_gemm<BN, EPI_BIAS_F32>(ta, tb, to, a, s);
+    case EPI_PATCH_F32: return launch_gemm<BN, EPI_PATCH_F32>(ta, tb, to, a, s);
+    case EPI_DGELU_BF16: return launch_gemm<BN, EPI_DGELU_BF16>(ta, tb, to, a, s);
+    case EPI_LNFOLD_BF16: return launch_gemm<BN, EPI_LNFOLD_BF16>(ta, tb, to, a, s);
+    case EPI_BIAS_RESID_STATS_F32: return launch_gemm<BN, EPI_BIAS_RESID_STATS_F32>(ta, tb, to, a, s);
   }
   set_error("gemm: unknown epilogue mode %d", mode);
   return GAVA_ERR_ARG;
@@ -925,8 +969,20 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
   a.colsum = epi->colsum; a.n_slots = epi->n_slots; a.eps = epi->eps;
   a.ld_aux = epi->ld_aux;
   a.aux_out = epi->mode == EPI_BIAS_GELU_BF16 ? reinterpret_cast<__nv_bfloat16*>(epi->aux_out) : nullptr;
-  if (pair) return dispatch_mode2(epi->mode, ta, tb, a, stream, epi->max_ctas);
-  return bn_eff == 256 ? dispatch_mode<256>(epi->mode, ta, tb, a, stream) : dispatch_mode<128>(epi->mode, ta, tb, a, stream);
+  // TMA drain of the bf16 output (modes 0 / 1 / 7 without a second output; GAVA_EPI_TMA=0 restores per-thread stores):
+  // the staged 32x32 blocks leave through bulk tensor stores -- no shared-memory read-back, no per-thread global stores.
+  // Measured: fc1 370 -> 354 us in isolation, the inference step +0.7 ... +2.8 % over four same-box A/B pairs.
+  static const bool epi_tma = [] { const char* e = getenv("GAVA_EPI_TMA"); return !(e && e[0] == '0'); }();
+  CUtensorMap tout = ta;
+  a.tma_out = 0;
+  if (epi_tma && (epi->mode == EPI_BIAS_BF16 || epi->mode == EPI_BIAS_GELU_BF16 || epi->mode == EPI_LNFOLD_BF16) &&
+      !a.aux_out && !a.colsum && !(reinterpret_cast<uintptr_t>(epi->out) & 15u) && !((epi->ldo * 2) & 15)) {
+    rc = make_tmap_bf16_out(&tout, epi->out, M, N, epi->ldo);
+    if (rc) return rc;
+    a.tma_out = 1;
+  }
+  if (pair) return dispatch_mode2(epi->mode, ta, tb, tout, a, stream, epi->max_ctas);
+  return bn_eff == 256 ? dispatch_mode<256>(epi->mode, ta, tb, tout, a, stream) : dispatch_mode<128>(epi->mode, ta, tb, tout, a, stream);
 }
 
 }  // namespace gava
