@@ -108,7 +108,7 @@ template <int MODE>
 __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage, int row0, int col0,
                                                const uint32_t (&v)[32], const float4 (&resid)[8], const float* bias_s,
                                                int lane, const FoldRow& fold, float (&rs)[8], float (&rq)[8],
-                                               const uint4 (&auxv)[4], const CUtensorMap* tmap_out, int parity) {
+                                               const uint4 (&auxv)[4], const CUtensorMap* tmap_out, const CUtensorMap* tmap_aux, int parity) {
   if constexpr (MODE == EPI_BIAS_BF16 || MODE == EPI_BIAS_GELU_BF16 || MODE == EPI_DGELU_BF16 || MODE == EPI_LNFOLD_BF16) {
     float acc[32];
     {  // bias of this chunk from shared memory (staged per tile before the accumulator wait; broadcast LDS.128)
@@ -146,7 +146,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
       }
     }
     // stage as bf16 (row pitch 64 B = 4 chunks of 16 B, chunk' = chunk ^ ((row >> 1) & 3)), then store transposed
-    auto stage_store = [&](const float (&a)[32], __nv_bfloat16* base, long long ld, bool dgelu, bool tma) {
+    auto stage_store = [&](const float (&a)[32], __nv_bfloat16* base, long long ld, bool dgelu, bool tma,
+                           const CUtensorMap* tmap, int parity) {
       // TMA drain: the 32 x 32 bf16 block is staged exactly as below (64-byte rows, 16-byte chunk index XOR (row >> 1) & 3
       // == CU_TENSOR_MAP_SWIZZLE_64B) in one of two 2 KB slots and leaves with ONE bulk tensor store issued by lane 0 (rows
       // beyond M are clipped by the tensor map): no shared-memory read-back, no per-thread global stores.
@@ -168,7 +169,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
         fence_proxy_async();                       // generic-proxy smem writes -> visible to the bulk store
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(tmap_out, slot, col0, row0);
+          tma_store_2d(tmap, slot, col0, row0);
           tma_store_commit();
         }
         return;
@@ -189,12 +190,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
       __syncwarp();
     };
     if constexpr (MODE == EPI_BIAS_GELU_BF16) {
-      if (p.aux_out != nullptr) stage_store(acc, p.aux_out, p.ld_aux, false, false);   // training forward keeps the pre-activations
+      // training forward keeps the pre-activations: with the TMA drain the two outputs of a chunk use one slot each
+      if (p.aux_out != nullptr) stage_store(acc, p.aux_out, p.ld_aux, false, p.tma_out != 0, tmap_aux, 0);
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = quick_gelu(acc[j]);
     }
     stage_store(acc, reinterpret_cast<__nv_bfloat16*>(p.out), p.ldo, MODE == EPI_DGELU_BF16,
-                MODE != EPI_DGELU_BF16 && p.tma_out != 0);
+                MODE != EPI_DGELU_BF16 && p.tma_out != 0, tmap_out,
+                (MODE == EPI_BIAS_GELU_BF16 && p.aux_out != nullptr) ? 1 : parity);
   } else {
     // stage raw fp32 accumulators: row pitch 128 B (8 chunks of 16 B), chunk' = chunk ^ (row & 7)
 #pragma unroll
@@ -245,7 +248,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, uint8_t* stage
 template <int MODE, int NCH>
 __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage, float* bias_s, uint64_t* tmem_full_bar,
                                               uint32_t full_phase, uint32_t t_addr, int row0, int col_base, int lane,
-                                              long long& dbg_wait, const CUtensorMap* tmap_out) {
+                                              long long& dbg_wait, const CUtensorMap* tmap_out, const CUtensorMap* tmap_aux) {
   FoldRow fold;
   fold.rstd = 1.f; fold.nmr = 0.f; fold.colsum_s = nullptr;
   float rs[8], rq[8];
@@ -314,7 +317,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage,
       FoldRow fc = fold;
       if constexpr (MODE == EPI_LNFOLD_BF16) fc.colsum_s = fold.colsum_s ? fold.colsum_s + cc * 32 : nullptr;
       epilogue_chunk<MODE>(p, stage, row0, col_base + cc * 32, cur, resid, bias_s + cc * 32, lane, fc, rs, rq,
-                           aux_all[MODE == EPI_DGELU_BF16 ? cc : 0], tmap_out, cc & 1);
+                           aux_all[MODE == EPI_DGELU_BF16 ? cc : 0], tmap_out, tmap_aux, cc & 1);
 #endif
     }
   } else {
@@ -359,7 +362,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage,
       if (v[0] == 0x7fc12345u && resid[0].x == 1.2345f) reinterpret_cast<uint32_t*>(p.out)[0] = v[3];
 #elif GAVA_GEMM_DEBUG != 1
       const uint4 no_aux[4] = {};
-      epilogue_chunk<MODE>(p, stage, row0, col0, v, resid, nullptr, lane, fold, rs, rq, no_aux, tmap_out, 0);
+      epilogue_chunk<MODE>(p, stage, row0, col0, v, resid, nullptr, lane, fold, rs, rq, no_aux, tmap_out, tmap_aux, 0);
 #endif
     }
     if constexpr (MODE == EPI_BIAS_RESID_STATS_F32) {
@@ -383,7 +386,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmArgs& p, uint8_t* stage,
 template <int BN, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const __grid_constant__ CUtensorMap tmap_out, const GemmArgs p) {
+                    const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux, const GemmArgs p) {
   using Cfg = GemmCfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];   // 128-byte-swizzle tiles need 1024-byte alignment
@@ -491,7 +494,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const int col_base = n_blk * BN + half * kChunksPerWarp * 32;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * kChunksPerWarp * 32);
       epilogue_tile<MODE, kChunksPerWarp>(p, stage, smem_bias + acc * BN + half * kChunksPerWarp * 32, &tmem_full[acc],
-                                          acc_phase, t_addr, row0, col_base, lane, g_dbg_wait, &tmap_out);
+                                          acc_phase, t_addr, row0, col_base, lane, g_dbg_wait, &tmap_out, &tmap_aux);
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -525,7 +528,7 @@ struct Gemm2Cfg {
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const __grid_constant__ CUtensorMap tmap_out, const GemmArgs p) {
+                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux, const GemmArgs p) {
   using Cfg = Gemm2Cfg;
   constexpr int kStages = Cfg::kStages;
   constexpr int BN = Cfg::BN;
@@ -674,7 +677,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const int col_base = n_blk * BN + half * kChunksPerWarp * 32;
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * kChunksPerWarp * 32);
       epilogue_tile<MODE, kChunksPerWarp>(p, stage, smem_bias + acc * BN + half * kChunksPerWarp * 32, &tmem_full[acc],
-                                          acc_phase, t_addr, row0, col_base, lane, g_dbg_wait, &tmap_out);
+                                          acc_phase, t_addr, row0, col_base, lane, g_dbg_wait, &tmap_out, &tmap_aux);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);  // tell the leader this warp drained its part
@@ -839,7 +842,7 @@ int num_sms() {
 }
 
 template <int BN, int MODE>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmArgs& args, cudaStream_t stream) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& taux, const GemmArgs& args, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set_dev[64] = {false};
   bool& attr_set = attr_set_dev[device_slot()];
@@ -851,12 +854,12 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   }
   const int tiles = ((args.M + BM - 1) / BM) * (args.N / BN);
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, tout, args);
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, tout, taux, args);
   return check_launch("gemm_tcgen05");
 }
 
 template <int MODE>
-static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const GemmArgs& args, cudaStream_t stream, int max_ctas = 0) {
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tout, const CUtensorMap& taux, const GemmArgs& args, cudaStream_t stream, int max_ctas = 0) {
   using Cfg = Gemm2Cfg;
   static bool attr_set_dev[64] = {false};
   bool& attr_set = attr_set_dev[device_slot()];
@@ -870,36 +873,36 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   int max_clusters = num_sms() / 2;
   if (max_ctas > 1 && max_ctas / 2 < max_clusters) max_clusters = max_ctas / 2;   // leave SMs to a concurrent stream
   const int clusters = tiles < max_clusters ? tiles : max_clusters;
-  kern<<<2 * clusters, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, tout, args);
+  kern<<<2 * clusters, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, tout, taux, args);
   return check_launch("gemm2_tcgen05");
 }
 
-static int dispatch_mode2(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& a, cudaStream_t s, int max_ctas) {
+static int dispatch_mode2(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx, const GemmArgs& a, cudaStream_t s, int max_ctas) {
   switch (mode) {
-    case EPI_BIAS_BF16: return launch_gemm2<EPI_BIAS_BF16>(ta, tb, to, a, s, max_ctas);
-    case EPI_BIAS_GELU_BF16: return launch_gemm2<EPI_BIAS_GELU_BF16>(ta, tb, to, a, s);
-    case EPI_BIAS_RESID_F32: return launch_gemm2<EPI_BIAS_RESID_F32>(ta, tb, to, a, s);
-    case EPI_BIAS_F32: return launch_gemm2<EPI_BIAS_F32>(ta, tb, to, a, s);
-    case EPI_PATCH_F32: return launch_gemm2<EPI_PATCH_F32>(ta, tb, to, a, s);
-    case EPI_DGELU_BF16: return launch_gemm2<EPI_DGELU_BF16>(ta, tb, to, a, s);
-    case EPI_LNFOLD_BF16: return launch_gemm2<EPI_LNFOLD_BF16>(ta, tb, to, a, s, max_ctas);
-    case EPI_BIAS_RESID_STATS_F32: return launch_gemm2<EPI_BIAS_RESID_STATS_F32>(ta, tb, to, a, s);
+    case EPI_BIAS_BF16: return launch_gemm2<EPI_BIAS_BF16>(ta, tb, to, tx, a, s, max_ctas);
+    case EPI_BIAS_GELU_BF16: return launch_gemm2<EPI_BIAS_GELU_BF16>(ta, tb, to, tx, a, s);
+    case EPI_BIAS_RESID_F32: return launch_gemm2<EPI_BIAS_RESID_F32>(ta, tb, to, tx, a, s);
+    case EPI_BIAS_F32: return launch_gemm2<EPI_BIAS_F32>(ta, tb, to, tx, a, s);
+    case EPI_PATCH_F32: return launch_gemm2<EPI_PATCH_F32>(ta, tb, to, tx, a, s);
+    case EPI_DGELU_BF16: return launch_gemm2<EPI_DGELU_BF16>(ta, tb, to, tx, a, s);
+    case EPI_LNFOLD_BF16: return launch_gemm2<EPI_LNFOLD_BF16>(ta, tb, to, tx, a, s, max_ctas);
+    case EPI_BIAS_RESID_STATS_F32: return launch_gemm2<EPI_BIAS_RESID_STATS_F32>(ta, tb, to, tx, a, s);
   }
   set_error("gemm: unknown epilogue mode %d", mode);
   return GAVA_ERR_ARG;
 }
 
 template <int BN>
-static int dispatch_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& a, cudaStream_t s) {
+static int dispatch_mode(int mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tx, const GemmArgs& a, cudaStream_t s) {
   switch (mode) {
-    case EPI_BIAS_BF16: return launch_gemm<BN, EPI_BIAS_BF16>(ta, tb, to, a, s);
-    case EPI_BIAS_GELU_BF16: return launch_gemm<BN, EPI_BIAS_GELU_BF16>(ta, tb, to, a, s);
-    case EPI_BIAS_RESID_F32: return launch_gemm<BN, EPI_BIAS_RESID_F32>(ta, tb, to, a, s);
-    case EPI_BIAS_F32: return launch_gemm<BN, EPI_BIAS_F32>(ta, tb, to, a, s);
-    case EPI_PATCH_F32: return launch_gemm<BN, EPI_PATCH_F32>(ta, tb, to, a, s);
-    case EPI_DGELU_BF16: return launch_gemm<BN, EPI_DGELU_BF16>(ta, tb, to, a, s);
-    case EPI_LNFOLD_BF16: return launch_gemm<BN, EPI_LNFOLD_BF16>(ta, tb, to, a, s);
-    case EPI_BIAS_RESID_STATS_F32: return launch_gemm<BN, EPI_BIAS_RESID_STATS_F32>(ta, tb, to, a, s);
+    case EPI_BIAS_BF16: return launch_gemm<BN, EPI_BIAS_BF16>(ta, tb, to, tx, a, s);
+    case EPI_BIAS_GELU_BF16: return launch_gemm<BN, EPI_BIAS_GELU_BF16>(ta, tb, to, tx, a, s);
+    case EPI_BIAS_RESID_F32: return launch_gemm<BN, EPI_BIAS_RESID_F32>(ta, tb, to, tx, a, s);
+    case EPI_BIAS_F32: return launch_gemm<BN, EPI_BIAS_F32>(ta, tb, to, tx, a, s);
+    case EPI_PATCH_F32: return launch_gemm<BN, EPI_PATCH_F32>(ta, tb, to, tx, a, s);
+    case EPI_DGELU_BF16: return launch_gemm<BN, EPI_DGELU_BF16>(ta, tb, to, tx, a, s);
+    case EPI_LNFOLD_BF16: return launch_gemm<BN, EPI_LNFOLD_BF16>(ta, tb, to, tx, a, s);
+    case EPI_BIAS_RESID_STATS_F32: return launch_gemm<BN, EPI_BIAS_RESID_STATS_F32>(ta, tb, to, tx, a, s);
   }
   set_error("gemm: unknown epilogue mode %d", mode);
   return GAVA_ERR_ARG;
@@ -973,16 +976,21 @@ int gemm_bf16(const void* A, long long lda, const void* W, long long ldw, long l
   // the staged 32x32 blocks leave through bulk tensor stores -- no shared-memory read-back, no per-thread global stores.
   // Measured: fc1 370 -> 354 us in isolation, the inference step +0.7 ... +2.8 % over four same-box A/B pairs.
   static const bool epi_tma = [] { const char* e = getenv("GAVA_EPI_TMA"); return !(e && e[0] == '0'); }();
-  CUtensorMap tout = ta;
+  CUtensorMap tout = ta, taux = ta;
   a.tma_out = 0;
   if (epi_tma && (epi->mode == EPI_BIAS_BF16 || epi->mode == EPI_BIAS_GELU_BF16 || epi->mode == EPI_LNFOLD_BF16) &&
-      !a.aux_out && !a.colsum && !(reinterpret_cast<uintptr_t>(epi->out) & 15u) && !((epi->ldo * 2) & 15)) {
+      !a.colsum && !(reinterpret_cast<uintptr_t>(epi->out) & 15u) && !((epi->ldo * 2) & 15) &&
+      (!a.aux_out || (!(reinterpret_cast<uintptr_t>(a.aux_out) & 15u) && !((a.ld_aux * 2) & 15)))) {
     rc = make_tmap_bf16_out(&tout, epi->out, M, N, epi->ldo);
     if (rc) return rc;
+    if (a.aux_out) {                               // fc1 of the training forward: the pre-activations leave the same way
+      rc = make_tmap_bf16_out(&taux, a.aux_out, M, N, a.ld_aux);
+      if (rc) return rc;
+    }
     a.tma_out = 1;
   }
-  if (pair) return dispatch_mode2(epi->mode, ta, tb, tout, a, stream, epi->max_ctas);
-  return bn_eff == 256 ? dispatch_mode<256>(epi->mode, ta, tb, tout, a, stream) : dispatch_mode<128>(epi->mode, ta, tb, tout, a, stream);
+  if (pair) return dispatch_mode2(epi->mode, ta, tb, tout, taux, a, stream, epi->max_ctas);
+  return bn_eff == 256 ? dispatch_mode<256>(epi->mode, ta, tb, tout, taux, a, stream) : dispatch_mode<128>(epi->mode, ta, tb, tout, taux, a, stream);
 }
 
 }  // namespace gava
