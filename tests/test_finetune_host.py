@@ -80,13 +80,18 @@ def test_two_rank_bucketed_gradient_allreduce():
     assert ret.get(0) is True and ret.get(1) is True
 
 
-def test_tower_gradient_layout_covers_trainable_set():
+import pytest
+
+
+@pytest.mark.parametrize("name", ["tiny", "tiny_no_local", "tiny_no_summary", "tiny_global_only"])
+def test_tower_gradient_layout_covers_trainable_set(name):
     """TowerTrainer's flat gradient buffer (host logic, no kernels): one view per trainable tower parameter of the
     reference's recipe (VitaCLIP_model.py:230-235), right shapes, no overlap, per-layer slices contiguous (the all-reduce
-    units), q|k|v of a summary attention adjacent (one wgrad GEMM fills all three)."""
+    units), q|k|v of a summary attention adjacent (one wgrad GEMM fills all three).  The partial prompt-flag configurations
+    hold only the tensors they have (utils.py:124-139): no local_prompts / no summary attention / neither."""
     from tests.util import build_model
     from gava_clip_b200.train_engine import TowerTrainer, is_trainable_name
-    model, kw, _ = build_model("tiny")
+    model, kw, _ = build_model(name)
     enc = model.visual
     eng = TowerTrainer(enc, torch.device("cpu"))
     eng._alloc_grads()
@@ -109,10 +114,15 @@ def test_tower_gradient_layout_covers_trainable_set():
     assert all(s.numel() == per_layer and s.is_contiguous() for s in eng.layer_slices)
     assert eng.head_slice.numel() == enc.time_embed.numel() + enc.global_prompts.numel()
     assert eng.head_slice.numel() + L * per_layer == eng.grad_flat.numel()
-    w = eng.grads["blocks.0.sqkv.weight"]
-    for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
-        v = eng.grads[f"blocks.0.summary_attn_layer.{nm}.weight"]
-        assert v.data_ptr() == w.data_ptr() + j * D * D * 4
+    assert ("blocks.0.local_prompts" in eng.grads) == bool(kw.get("use_local_prompts"))
+    assert ("blocks.0.sqkv.weight" in eng.grads) == bool(kw.get("use_summary_token"))
+    if kw.get("use_summary_token"):
+        w = eng.grads["blocks.0.sqkv.weight"]
+        for j, nm in enumerate(("q_proj", "k_proj", "v_proj")):
+            v = eng.grads[f"blocks.0.summary_attn_layer.{nm}.weight"]
+            assert v.data_ptr() == w.data_ptr() + j * D * D * 4
+    if name == "tiny_global_only":
+        assert per_layer == 0 and all(s.numel() == 0 for s in eng.layer_slices)     # nothing to all-reduce per layer
     # a backbone weight that requires grad has no backward kernel: refused loudly
     enc.blocks[0].mlp.fc1.weight.requires_grad_(True)
     try:
