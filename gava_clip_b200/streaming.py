@@ -29,16 +29,40 @@ class ClipStreamer:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
+    def _tower_engine(self):
+        visual = getattr(self.model, "visual", None)
+        return visual.engine(self.device) if visual is not None and hasattr(visual, "engine") else None
+
+    def close(self) -> None:
+        """Release the staging slots (and the graphs the tower captured on them).  Called on garbage collection too."""
+        eng = None
+        for k in (0, 1):
+            if self._stage[k] is not None:
+                try:
+                    eng = eng or self._tower_engine()
+                    if eng is not None:
+                        eng.unregister_input(self._stage[k])
+                except Exception:          # interpreter shutdown / model already gone: nothing left to release
+                    pass
+                self._stage[k] = None
+
+    def __del__(self):
+        self.close()
+
     def _upload(self, k: int, host: Tensor) -> None:
         if self._stage[k] is None or self._stage[k].shape != host.shape or self._stage[k].dtype != host.dtype:
+            if self._stage[k] is not None:                 # a re-shaped slot (ragged tail batch): drop the old registration
+                eng = self._tower_engine()
+                if eng is not None:
+                    eng.unregister_input(self._stage[k])
             self._stage[k] = torch.empty(host.shape, device=self.device, dtype=host.dtype)   # fp32 (B,3,T,H,W) or uint8 (B,T,H,W,3)
             # the caching allocator may hand back a block whose last use on the compute stream is still in flight
             self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
             # the two staging slots live as long as the streamer: the tower replays a graph captured on the slot itself
             # instead of copying it into its own static clip buffer first
-            visual = getattr(self.model, "visual", None)
-            if visual is not None and hasattr(visual, "engine"):
-                visual.engine(self.device).register_input(self._stage[k])
+            eng = self._tower_engine()
+            if eng is not None:
+                eng.register_input(self._stage[k])
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self._consumed[k])            # slot free again?
             self._stage[k].copy_(host, non_blocking=True)

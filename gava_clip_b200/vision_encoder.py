@@ -403,6 +403,13 @@ class TowerEngine:
             del self._registered_inputs[oldest]
             self.graphs.pop(oldest[1] + (oldest[0],), None)
 
+    def unregister_input(self, buf: Tensor) -> None:
+        """Forget a registered buffer and drop the graph captured on it (the graph entry holds a reference to the buffer,
+        which would otherwise keep e.g. a finished streaming loop's 308 MB staging slots alive)."""
+        ent = (buf.data_ptr(), tuple(buf.shape), buf.dtype)
+        if self._registered_inputs.pop(ent, None) is not None:
+            self.graphs.pop(ent[1] + (ent[0],), None)
+
     def run(self, video: Tensor) -> Tuple[Tensor, Tensor]:
         """encode_frames, replayed from a CUDA graph per clip shape (launch-bound inner loop: ~190 launches)."""
         if self.enc.precision == "fp32":

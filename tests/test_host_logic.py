@@ -108,3 +108,25 @@ def test_gemm_stats_slots_host_function():
     assert ops.gemm_stats_slots(102, 128) == 2
     with pytest.raises(ValueError):
         ops.gemm_stats_slots(100, 100)
+
+
+def test_registered_input_registry():
+    """TowerEngine.register_input / unregister_input (host bookkeeping of the graphs captured on caller-owned clip buffers):
+    re-registration moves a buffer to the back, the registry is capped (oldest forgotten together with its graph), and
+    unregistering drops the graph entry that would otherwise keep the buffer alive."""
+    from gava_clip_b200.vision_encoder import TowerEngine
+    model, kw, B = build_model("tiny")
+    eng = TowerEngine(model.visual, torch.device("cpu"))
+    key = lambda b: (b.data_ptr(), tuple(b.shape), b.dtype)
+    bufs = [torch.zeros(2, 3, 3, 64, 64) for _ in range(10)]
+    for b in bufs[:8]:
+        eng.register_input(b)
+        eng.graphs[tuple(b.shape) + (b.data_ptr(),)] = ("graph", b, 1)
+    eng.register_input(bufs[0])                                   # refresh: now the newest
+    eng.register_input(bufs[8]); eng.register_input(bufs[9])      # pushes out the two oldest: bufs[1], bufs[2]
+    assert len(eng._registered_inputs) == 8
+    assert key(bufs[0]) in eng._registered_inputs and key(bufs[1]) not in eng._registered_inputs
+    assert tuple(bufs[1].shape) + (bufs[1].data_ptr(),) not in eng.graphs and tuple(bufs[3].shape) + (bufs[3].data_ptr(),) in eng.graphs
+    eng.unregister_input(bufs[3])
+    assert key(bufs[3]) not in eng._registered_inputs and tuple(bufs[3].shape) + (bufs[3].data_ptr(),) not in eng.graphs
+    eng.unregister_input(bufs[3])                                 # idempotent
